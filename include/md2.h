@@ -1,0 +1,173 @@
+/* md2.h -- C ABI of libmd2_b200.so: hand-written sm_100a CUDA kernels for the
+ * view-synthesis loss path of pxl-th/Monodepth2.jl (warp + SSIM/L1 photometric loss,
+ * forward and backward).  This is the drop-in boundary: Julia binds it with `ccall`
+ * (monodepth2.jl_b200/julia/Monodepth2B200.jl), the tests and bench bind it
+ * with Python ctypes.
+ *
+ * The reference has no FFI of its own: each entry point below replaces a plain Julia
+ * function (plus its Zygote/ChainRules pullback) and cites it as file:line in
+ * /root/reference (= pxl-th/Monodepth2.jl).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; the message is available
+ *    through md2_last_error() (thread-local).  Nothing throws or exits.
+ *  - every tensor argument is a caller-owned DEVICE pointer to contiguous float32 in
+ *    Julia (column-major) memory order: image (W,H,C,N), disparity (W,H,1,N), points
+ *    (3,P,N) with p = (h-1)W + (w-1), grid (2,W,H,N), K/invK (3,3), R (3,3,N), t (3,1,N),
+ *    rvec (3,N).  (W,H,C,N) column-major is bit-identical to row-major NCHW.
+ *  - pixel coordinates are 1-based like the reference (src/utils.jl:47-51); frame indices
+ *    passed through this ABI are 0-based.
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *    default stream) and never synchronise the device.  Scratch lives in the md2_ctx
+ *    (one per device and host thread; not thread-safe; grown on demand, which may call
+ *    cudaMalloc on first use of a larger shape).
+ *  - gradient outputs are overwritten unless documented as "accumulated".
+ */
+#ifndef MD2_H
+#define MD2_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MD2_MAX_SOURCES 2
+#define MD2_MAX_SCALES 8
+
+typedef struct md2_ctx md2_ctx;
+typedef void* md2_stream;
+
+const char* md2_version(void);
+const char* md2_last_error(void);
+int md2_create(int device, md2_ctx** out);
+int md2_destroy(md2_ctx* ctx);
+/* number of kernels launched through this ctx since creation (bench's gpu_launches) */
+int64_t md2_launch_count(const md2_ctx* ctx);
+
+/* ---- A1  disparity_to_depth            src/utils.jl:175-179 ------------------------- */
+int md2_disparity_to_depth_fwd(md2_ctx*, const float* disp, float* depth, int64_t count,
+                               float min_depth, float max_depth, md2_stream);
+int md2_disparity_to_depth_bwd(md2_ctx*, const float* disp, const float* gdepth, float* gdisp,
+                               int64_t count, float min_depth, float max_depth, md2_stream);
+
+/* ---- A2  Backproject(depth, invK)      src/utils.jl:41-65 ---------------------------
+ * depth (1,P,N), invK (3,3) -> points (3,P,N) */
+int md2_backproject_fwd(md2_ctx*, const float* depth, const float* invK, float* points,
+                        int32_t W, int32_t H, int32_t N, md2_stream);
+int md2_backproject_bwd(md2_ctx*, const float* gpoints, const float* invK, float* gdepth,
+                        int32_t W, int32_t H, int32_t N, md2_stream);
+
+/* ---- A3  Project(points, K, R, t)      src/utils.jl:67-99 ---------------------------
+ * points (3,P,N), K (3,3), R (3,3,N), t (3,1,N) -> uv (2,P,N) normalised to (-1,1) */
+int md2_project_fwd(md2_ctx*, const float* points, const float* K, const float* R, const float* t,
+                    float* uv, int32_t W, int32_t H, int32_t N, md2_stream);
+int md2_project_bwd(md2_ctx*, const float* points, const float* K, const float* R, const float* t,
+                    const float* guv, float* gpoints, float* gR, float* gt,
+                    int32_t W, int32_t H, int32_t N, md2_stream);
+
+/* ---- A4/A5/A6  so3_exp_map, hat (+rrule), composeT   src/utils.jl:101-141,181-188 ---- */
+int md2_so3_exp_map_fwd(md2_ctx*, const float* rvec, float* R, int32_t N, md2_stream);
+int md2_so3_exp_map_bwd(md2_ctx*, const float* rvec, const float* gR, float* grvec, int32_t N, md2_stream);
+int md2_hat_fwd(md2_ctx*, const float* rvec, float* S, int32_t N, md2_stream);
+int md2_hat_bwd(md2_ctx*, const float* gS, float* grvec, int32_t N, md2_stream);
+int md2_compose_T_fwd(md2_ctx*, const float* rvec, const float* tvec, int32_t invert,
+                      float* R, float* t, int32_t N, md2_stream);
+int md2_compose_T_bwd(md2_ctx*, const float* rvec, const float* tvec, int32_t invert,
+                      const float* gR, const float* gt, float* grvec, float* gtvec, int32_t N, md2_stream);
+
+/* ---- A16  NNlib.grid_sample (bilinear, align-corners)   call src/training.jl:56,
+ *           test/runtests.jl:116.  padding_mode 0 = :zeros, 1 = :border.
+ * input (W,H,C,N), grid (2,Wo,Ho,N) -> out (Wo,Ho,C,N).  ginput is ACCUMULATED. */
+int md2_grid_sample_fwd(md2_ctx*, const float* input, const float* grid, float* out,
+                        int32_t W, int32_t H, int32_t C, int32_t N, int32_t Wo, int32_t Ho,
+                        int32_t padding_mode, md2_stream);
+int md2_grid_sample_bwd(md2_ctx*, const float* input, const float* grid, const float* gout,
+                        float* ginput, float* ggrid, int32_t W, int32_t H, int32_t C, int32_t N,
+                        int32_t Wo, int32_t Ho, int32_t padding_mode, md2_stream);
+
+/* ---- A17  NNlib.upsample_bilinear (align-corners)        call src/training.jl:45 ---- */
+int md2_upsample_bilinear_fwd(md2_ctx*, const float* in, float* out, int32_t w, int32_t h,
+                              int32_t W, int32_t H, int32_t CN, md2_stream);
+int md2_upsample_bilinear_bwd(md2_ctx*, const float* gout, float* gin, int32_t w, int32_t h,
+                              int32_t W, int32_t H, int32_t CN, md2_stream);
+
+/* ---- A7  SSIM()(x, y)                  src/utils.jl:13-39 --------------------------- */
+int md2_ssim_fwd(md2_ctx*, const float* x, const float* y, float* out,
+                 int32_t W, int32_t H, int32_t C, int32_t N, md2_stream);
+int md2_ssim_bwd(md2_ctx*, const float* x, const float* y, const float* gout, float* gx, float* gy,
+                 int32_t W, int32_t H, int32_t C, int32_t N, md2_stream);
+
+/* ---- A10-A13  photometric_loss / prediction_loss / automasking_loss / _apply_mask
+ *               src/training.jl:1-19
+ * out (W,H,1,N) = min( [mask,] photometric(pred_0,target), ..., photometric(pred_{S-1},target) ),
+ * first index wins ties (findmin); argmin (optional, int32 (W,H,1,N)): -1 = mask, else s.
+ * S = 1 and mask = NULL is photometric_loss itself.  pred pointers are (W,H,C,N) views with
+ * an explicit per-image element stride, so frames of the 5-D input x (W,H,C,L,N) can be
+ * passed without slicing (automasking_loss). */
+int md2_photometric_min_fwd(md2_ctx*, int32_t S, const float* const* pred, const int64_t* pred_image_stride,
+                            const float* target, int64_t target_image_stride, const float* mask,
+                            float alpha, float* out, int32_t* argmin,
+                            int32_t W, int32_t H, int32_t C, int32_t N, md2_stream);
+/* gpred[s] (nullable, contiguous (W,H,C,N)), gtarget (nullable), gmask (nullable): overwritten */
+int md2_photometric_min_bwd(md2_ctx*, int32_t S, const float* const* pred, const int64_t* pred_image_stride,
+                            const float* target, int64_t target_image_stride, const float* mask,
+                            float alpha, const float* gout, const int32_t* argmin /* from fwd */,
+                            float* const* gpred, float* gtarget,
+                            float* gmask, int32_t W, int32_t H, int32_t C, int32_t N, md2_stream);
+
+/* ---- A8  smooth_loss(disparity, image) src/utils.jl:143-173 -------------------------
+ * disparity (W,H,N), image (W,H,C,N) -> scalar (device).  normalize != 0 applies the
+ * d / (mean_{W,H} d + 1e-7) of src/training.jl:64-65 first. */
+int md2_smooth_loss_fwd(md2_ctx*, const float* disp, const float* image, int64_t image_stride,
+                        float* out, int32_t normalize, int32_t W, int32_t H, int32_t C, int32_t N, md2_stream);
+int md2_smooth_loss_bwd(md2_ctx*, const float* disp, const float* image, int64_t image_stride,
+                        float gout, float* gdisp, float* gimage, int32_t normalize,
+                        int32_t W, int32_t H, int32_t C, int32_t N, md2_stream);
+
+/* ---- A14/A15  fused hot path ---------------------------------------------------------
+ * warp (undefined in the reference; call src/simple_depth.jl:30-32, body inferred from
+ * src/training.jl:48-57) and the train_loss tail (src/training.jl:29-77). */
+typedef struct md2_vsl_desc {
+    int32_t W, H, N, C, S, L;
+    const float* target;  int64_t target_image_stride;        /* (W,H,C,N) view */
+    const float* source[MD2_MAX_SOURCES];  int64_t source_image_stride[MD2_MAX_SOURCES];
+    const float* disparity[MD2_MAX_SCALES];                   /* (w_i,h_i,1,N) */
+    int32_t disp_w[MD2_MAX_SCALES], disp_h[MD2_MAX_SCALES];   /* upsampled to (W,H) if smaller */
+    const float* K;  const float* invK;                       /* (3,3) device */
+    int32_t pose_mode;       /* 0: rot = R (3,3,N), trans = t (3,1,N) as returned by composeT
+                                1: rot = rvec (3,N), trans = tvec (3,1,N); composeT fused */
+    const float* rot[MD2_MAX_SOURCES];
+    const float* trans[MD2_MAX_SOURCES];
+    int32_t invert[MD2_MAX_SOURCES];                          /* pose_mode 1: source_id < target_id */
+    const float* automask;                                    /* (W,H,1,N) or NULL */
+    float min_depth, max_depth;
+    float smooth_weight[MD2_MAX_SCALES];    /* disparity_smoothness * scale_i */
+    float loss_scale;                       /* 1 / L */
+    int32_t normalize_disparity;            /* 1 in train_loss, 0 in slow_depth */
+    /* outputs */
+    float* loss;                                              /* device scalar */
+    float* grad_disparity[MD2_MAX_SCALES];                    /* (w_i,h_i,1,N) */
+    float* grad_rot[MD2_MAX_SOURCES];                         /* like rot */
+    float* grad_trans[MD2_MAX_SOURCES];
+    float* grad_source[MD2_MAX_SOURCES];    /* nullable; same view as source; ACCUMULATED */
+    float* viz_warped[MD2_MAX_SOURCES];     /* nullable (W,H,C,N): warped sources, last scale */
+    float* viz_loss;                        /* nullable (W,H,1,N): warp-loss map, last scale */
+    float* saved;                           /* nullable (4,N,L): fwd -> bwd statistics */
+} md2_vsl_desc;
+
+int md2_view_synthesis_loss_fwd(md2_ctx*, const md2_vsl_desc*, md2_stream);
+int md2_view_synthesis_loss_bwd(md2_ctx*, const md2_vsl_desc*, float upstream, md2_stream);
+/* value and gradient in one pass (gradient seeded with `seed`, normally 1) */
+int md2_view_synthesis_loss_fwdbwd(md2_ctx*, const md2_vsl_desc*, float seed, md2_stream);
+
+/* warp: disparity (W,H,1,N) -> S warped images (W,H,C,N); uses the desc fields
+ * W,H,N,C,S, source*, disparity[0], K, invK, pose_*, rot, trans, invert, min/max_depth;
+ * out[s] contiguous (W,H,C,N). */
+int md2_warp_fwd(md2_ctx*, const md2_vsl_desc*, float* const* out, md2_stream);
+/* gout[s] (W,H,C,N) -> grad_disparity[0], grad_rot, grad_trans, grad_source (accumulated) */
+int md2_warp_bwd(md2_ctx*, const md2_vsl_desc*, const float* const* gout, md2_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MD2_H */

@@ -1,0 +1,98 @@
+// Host-side plumbing shared by the .cu translation units: context, error reporting,
+// workspace, launch accounting, block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <stdio.h>
+
+#include "../../include/md2.h"
+#include "md2_math.cuh"
+
+namespace md2 {
+
+std::string& last_error_ref();
+int set_error(const char* fmt, ...);
+
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace md2
+
+enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, MD2_WS_GDISP,
+       MD2_WS_POSEIN, MD2_WS_MISC, MD2_WS_COUNT };
+
+struct md2_ctx {
+    int device;
+    int64_t launches;
+    md2::Workspace ws[MD2_WS_COUNT];
+};
+
+namespace md2 {
+
+// returns nullptr (and sets the error) on failure
+void* ws_get(md2_ctx* ctx, int slot, size_t bytes);
+
+#define MD2_CHECK(expr)                                                                  \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return md2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                   \
+    } while (0)
+
+#define MD2_LAUNCH_CHECK(ctx)                                                           \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess)                                                          \
+            return md2::set_error("kernel launch failed: %s (%s:%d)",                   \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);          \
+    } while (0)
+
+#define MD2_REQUIRE(cond, msg)                                  \
+    do {                                                        \
+        if (!(cond)) return md2::set_error("%s: %s", __func__, msg); \
+    } while (0)
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum of NV values per thread; result valid in thread 0's out[].
+// scratch must hold NV * (blockDim.x/32) floats.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float s = warp_sum(v[k]);
+        if (lane == 0) scratch[k * nw + wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += scratch[threadIdx.x * nw + w];
+        scratch[threadIdx.x * nw] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = scratch[k * nw];
+    __syncthreads();
+}
+
+// Julia column-major 3x3 -> row-major doubles
+__device__ __forceinline__ void load_cm3(const float* m, double* o) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o[3 * i + j] = (double)m[3 * j + i];
+}
+#endif
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace md2

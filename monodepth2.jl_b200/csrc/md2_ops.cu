@@ -1,0 +1,780 @@
+// Stand-alone operators of the path (one reference function each, forward + backward) so that
+// every entry point of src/utils.jl and src/training.jl:1-19 has a drop-in.  These are the simple
+// thread-per-element versions; the speed path is the fused kernel in md2_fused.cu.
+#include "md2_common.cuh"
+#include "md2_fused.cuh"
+
+namespace md2 {
+
+int launch_reduce_partials(md2_ctx* ctx, const float* partial, float* out0, int n0, float* out1,
+                           int groups, int bpg, int NP, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------
+// A1 disparity_to_depth (src/utils.jl:175-179)
+// ------------------------------------------------------------------------------------------
+__global__ void d2d_fwd_kernel(const float* __restrict__ d, float* __restrict__ z, long long n, float a, float b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = 1.0f / fmaf(d[i], a, b);
+}
+__global__ void d2d_bwd_kernel(const float* __restrict__ d, const float* __restrict__ gz, float* __restrict__ gd,
+                               long long n, float a, float b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float z = 1.0f / fmaf(d[i], a, b);
+        gd[i] = -a * z * z * gz[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// A2 Backproject (src/utils.jl:41-65)
+// ------------------------------------------------------------------------------------------
+__global__ void backproject_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ invK,
+                                       float* __restrict__ pts, int W, int H, int N) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long P = (long long)W * H;
+    if (i >= P * N) return;
+    const long long p = i % P;
+    const float w = (float)(p % W + 1), h = (float)(p / W + 1);
+    const float z = depth[i];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float ray = fmaf(invK[r], w, fmaf(invK[3 + r], h, invK[6 + r]));
+        pts[3 * i + r] = z * ray;
+    }
+}
+__global__ void backproject_bwd_kernel(const float* __restrict__ gpts, const float* __restrict__ invK,
+                                       float* __restrict__ gdepth, int W, int H, int N) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long P = (long long)W * H;
+    if (i >= P * N) return;
+    const long long p = i % P;
+    const float w = (float)(p % W + 1), h = (float)(p / W + 1);
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float ray = fmaf(invK[r], w, fmaf(invK[3 + r], h, invK[6 + r]));
+        g = fmaf(ray, gpts[3 * i + r], g);
+    }
+    gdepth[i] = g;
+}
+
+// ------------------------------------------------------------------------------------------
+// A3 Project + normalize (src/utils.jl:67-99).  K, R column-major: m[3*col+row]
+// ------------------------------------------------------------------------------------------
+struct ProjPoint { float Y[3], c[3], q, u, v; };
+
+__device__ __forceinline__ void project_point(const float* X, const float* K, const float* R, const float* t,
+                                              ProjPoint& o) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o.Y[r] = fmaf(R[r], X[0], fmaf(R[3 + r], X[1], fmaf(R[6 + r], X[2], t[r])));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o.c[r] = fmaf(K[r], o.Y[0], fmaf(K[3 + r], o.Y[1], K[6 + r] * o.Y[2]));
+    o.q = 1.0f / (o.c[2] + PROJ_EPS);
+    o.u = o.c[0] * o.q;
+    o.v = o.c[1] * o.q;
+}
+
+__global__ void project_fwd_kernel(const float* __restrict__ pts, const float* __restrict__ K,
+                                   const float* __restrict__ R, const float* __restrict__ t,
+                                   float* __restrict__ uv, int W, int H, int N) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long P = (long long)W * H;
+    if (i >= P * N) return;
+    const int n = (int)(i / P);
+    const float X[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    ProjPoint o;
+    project_point(X, K, R + 9 * n, t + 3 * n, o);
+    uv[2 * i] = ((o.u - 1.0f) / (float)(W - 1) - 0.5f) * 2.0f;
+    uv[2 * i + 1] = ((o.v - 1.0f) / (float)(H - 1) - 0.5f) * 2.0f;
+}
+
+__global__ void __launch_bounds__(256) project_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ K,
+                                                          const float* __restrict__ R, const float* __restrict__ t,
+                                                          const float* __restrict__ guv, float* __restrict__ gpts,
+                                                          float* __restrict__ partial, int W, int H, int N) {
+    __shared__ float scratch[12 * 8];
+    const int n = blockIdx.y;
+    const long long P = (long long)W * H;
+    const float* Rn = R + 9 * n;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.f;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const long long i = (long long)n * P + p;
+        const float X[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        ProjPoint o;
+        project_point(X, K, Rn, t + 3 * n, o);
+        const float du = guv[2 * i] * 2.0f / (float)(W - 1), dv = guv[2 * i + 1] * 2.0f / (float)(H - 1);
+        const float cb[3] = {du * o.q, dv * o.q, -(du * o.u + dv * o.v) * o.q};
+        float Yb[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Yb[r] = K[3 * r] * cb[0] + K[3 * r + 1] * cb[1] + K[3 * r + 2] * cb[2];  // K^T cb
+#pragma unroll
+        for (int r = 0; r < 3; ++r) gpts[3 * i + r] = Rn[3 * r] * Yb[0] + Rn[3 * r + 1] * Yb[1] + Rn[3 * r + 2] * Yb[2];  // R^T Yb
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) v[3 * c + r] = fmaf(Yb[r], X[c], v[3 * c + r]);   // column-major gR
+#pragma unroll
+        for (int r = 0; r < 3; ++r) v[9 + r] += Yb[r];
+    }
+    block_sum<12>(v, scratch);
+    if (threadIdx.x < 12) {
+        float* o = partial + ((long long)n * gridDim.x + blockIdx.x) * 12;
+        o[threadIdx.x] = scratch[threadIdx.x * (blockDim.x >> 5)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// A4-A6 so3_exp_map / hat / composeT (src/utils.jl:101-141, 181-188).  Column-major I/O.
+// ------------------------------------------------------------------------------------------
+__global__ void so3_fwd_kernel(const float* __restrict__ rvec, float* __restrict__ R, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double r[3] = {rvec[3 * n], rvec[3 * n + 1], rvec[3 * n + 2]}, M[9];
+    so3_exp(r, M);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[9 * n + 3 * j + i] = (float)M[3 * i + j];
+}
+__global__ void so3_bwd_kernel(const float* __restrict__ rvec, const float* __restrict__ gR, float* __restrict__ grvec, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double r[3] = {rvec[3 * n], rvec[3 * n + 1], rvec[3 * n + 2]}, Rb[9], rb[3];
+    load_cm3(gR + 9 * n, Rb);
+    so3_exp_bwd(r, Rb, rb);
+    for (int k = 0; k < 3; ++k) grvec[3 * n + k] = (float)rb[k];
+}
+__global__ void hat_fwd_kernel(const float* __restrict__ rvec, float* __restrict__ S, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float a = rvec[3 * n], b = rvec[3 * n + 1], c = rvec[3 * n + 2];
+    float* o = S + 9 * n;   // column-major: o[3*col+row]
+    o[0] = 0.f; o[1] = c;   o[2] = -b;
+    o[3] = -c;  o[4] = 0.f; o[5] = a;
+    o[6] = b;   o[7] = -a;  o[8] = 0.f;
+}
+__global__ void hat_bwd_kernel(const float* __restrict__ gS, float* __restrict__ grvec, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* d = gS + 9 * n;   // d[3*col+row]
+    grvec[3 * n + 0] = d[3 * 1 + 2] - d[3 * 2 + 1];   // d[3,2] - d[2,3]
+    grvec[3 * n + 1] = -d[3 * 0 + 2] + d[3 * 2 + 0];  // -d[3,1] + d[1,3]
+    grvec[3 * n + 2] = d[3 * 0 + 1] - d[3 * 1 + 0];   // d[2,1] - d[1,2]
+}
+__global__ void compose_fwd_kernel(const float* __restrict__ rvec, const float* __restrict__ tvec, int invert,
+                                   float* __restrict__ R, float* __restrict__ t, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double r[3], tv[3], M[9], tu[3];
+    for (int k = 0; k < 3; ++k) { r[k] = rvec[3 * n + k]; tv[k] = tvec[3 * n + k]; }
+    compose_T(r, tv, invert, M, tu);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[9 * n + 3 * j + i] = (float)M[3 * i + j];
+    for (int k = 0; k < 3; ++k) t[3 * n + k] = (float)tu[k];
+}
+__global__ void compose_bwd_kernel(const float* __restrict__ rvec, const float* __restrict__ tvec, int invert,
+                                   const float* __restrict__ gR, const float* __restrict__ gt,
+                                   float* __restrict__ grvec, float* __restrict__ gtvec, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double r[3], tv[3], Rub[9], tub[3], rb[3], tb[3];
+    for (int k = 0; k < 3; ++k) { r[k] = rvec[3 * n + k]; tv[k] = tvec[3 * n + k]; tub[k] = gt ? gt[3 * n + k] : 0.0; }
+    if (gR) load_cm3(gR + 9 * n, Rub);
+    else for (int k = 0; k < 9; ++k) Rub[k] = 0.0;
+    compose_T_bwd(r, tv, invert, Rub, tub, rb, tb);
+    for (int k = 0; k < 3; ++k) { grvec[3 * n + k] = (float)rb[k]; gtvec[3 * n + k] = (float)tb[k]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// A16 NNlib.grid_sample bilinear / align-corners, padding :zeros or :border, and its adjoint
+// ------------------------------------------------------------------------------------------
+struct GsTaps { int x0, y0; float ix, iy, mx, my; };
+
+__device__ __forceinline__ GsTaps gs_taps(float gx, float gy, int W, int H, int border) {
+    GsTaps t;
+    float ix = (gx + 1.0f) * 0.5f * (float)(W - 1);   // 0-based un-normalised
+    float iy = (gy + 1.0f) * 0.5f * (float)(H - 1);
+    t.mx = 0.5f * (float)(W - 1);
+    t.my = 0.5f * (float)(H - 1);
+    if (border) {
+        if (!(ix > 0.f)) { ix = 0.f; t.mx = 0.f; } else if (ix >= (float)(W - 1)) { ix = (float)(W - 1); t.mx = 0.f; }
+        if (!(iy > 0.f)) { iy = 0.f; t.my = 0.f; } else if (iy >= (float)(H - 1)) { iy = (float)(H - 1); t.my = 0.f; }
+    } else {
+        // keep the int conversion defined for wild coordinates; such taps are out of range anyway
+        ix = fminf(fmaxf(ix, -2.0f), (float)W + 1.0f);
+        iy = fminf(fmaxf(iy, -2.0f), (float)H + 1.0f);
+    }
+    t.ix = ix; t.iy = iy;
+    t.x0 = (int)floorf(ix); t.y0 = (int)floorf(iy);
+    return t;
+}
+
+__global__ void grid_sample_fwd_kernel(const float* __restrict__ in, const float* __restrict__ grid,
+                                       float* __restrict__ out, int W, int H, int C, int N, int Wo, int Ho, int border) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long Po = (long long)Wo * Ho;
+    if (i >= Po * N) return;
+    const int n = (int)(i / Po);
+    const long long po = i % Po;
+    const GsTaps t = gs_taps(grid[2 * i], grid[2 * i + 1], W, H, border);
+    const float fx = t.ix - (float)t.x0, fy = t.iy - (float)t.y0;
+    const bool xa = t.x0 >= 0 && t.x0 < W, xb = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+    const bool ya = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+    for (int c = 0; c < C; ++c) {
+        const float* b = in + ((long long)n * C + c) * W * H;
+        const float v00 = (xa && ya) ? b[t.y0 * W + t.x0] : 0.f;
+        const float v01 = (xb && ya) ? b[t.y0 * W + t.x0 + 1] : 0.f;
+        const float v10 = (xa && yb) ? b[(t.y0 + 1) * W + t.x0] : 0.f;
+        const float v11 = (xb && yb) ? b[(t.y0 + 1) * W + t.x0 + 1] : 0.f;
+        out[((long long)n * C + c) * Po + po] =
+            v00 * (1.f - fx) * (1.f - fy) + v01 * fx * (1.f - fy) + v10 * (1.f - fx) * fy + v11 * fx * fy;
+    }
+}
+
+__global__ void grid_sample_bwd_kernel(const float* __restrict__ in, const float* __restrict__ grid,
+                                       const float* __restrict__ gout, float* __restrict__ gin,
+                                       float* __restrict__ ggrid, int W, int H, int C, int N, int Wo, int Ho, int border) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long Po = (long long)Wo * Ho;
+    if (i >= Po * N) return;
+    const int n = (int)(i / Po);
+    const long long po = i % Po;
+    const GsTaps t = gs_taps(grid[2 * i], grid[2 * i + 1], W, H, border);
+    const float fx = t.ix - (float)t.x0, fy = t.iy - (float)t.y0;
+    const bool xa = t.x0 >= 0 && t.x0 < W, xb = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+    const bool ya = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+    float gix = 0.f, giy = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const long long pl = ((long long)n * C + c) * W * H;
+        const float* b = in + pl;
+        const float g = gout[((long long)n * C + c) * Po + po];
+        const float v00 = (xa && ya) ? b[t.y0 * W + t.x0] : 0.f;
+        const float v01 = (xb && ya) ? b[t.y0 * W + t.x0 + 1] : 0.f;
+        const float v10 = (xa && yb) ? b[(t.y0 + 1) * W + t.x0] : 0.f;
+        const float v11 = (xb && yb) ? b[(t.y0 + 1) * W + t.x0 + 1] : 0.f;
+        gix += g * ((v01 - v00) * (1.f - fy) + (v11 - v10) * fy);
+        giy += g * ((v10 - v00) * (1.f - fx) + (v11 - v01) * fx);
+        if (gin) {
+            float* gb = gin + pl;
+            if (xa && ya) atomicAdd(gb + t.y0 * W + t.x0, g * (1.f - fx) * (1.f - fy));
+            if (xb && ya) atomicAdd(gb + t.y0 * W + t.x0 + 1, g * fx * (1.f - fy));
+            if (xa && yb) atomicAdd(gb + (t.y0 + 1) * W + t.x0, g * (1.f - fx) * fy);
+            if (xb && yb) atomicAdd(gb + (t.y0 + 1) * W + t.x0 + 1, g * fx * fy);
+        }
+    }
+    if (ggrid) {
+        ggrid[2 * i] = t.mx * gix;
+        ggrid[2 * i + 1] = t.my * giy;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// A7 SSIM (src/utils.jl:13-39) and A10-A13 photometric / min / mask (src/training.jl:1-19).
+// Gather formulation: deterministic, no atomics.
+// ------------------------------------------------------------------------------------------
+struct WinXY {           // SSIM window statistics with the coefficients for both arguments
+    float s, pass;
+    float ax, bx, g;     // dS/dx_j = ax + bx x_j + g y_j
+    float ay, by;        // dS/dy_j = ay + by y_j + g x_j
+};
+
+// x, y: one channel plane; (qx,qy) window centre (in image)
+__device__ __forceinline__ WinXY window_xy(const float* __restrict__ x, const float* __restrict__ y, int qx, int qy,
+                                           int W, int H) {
+    const float xc = x[qy * W + qx], yc = y[qy * W + qx];
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int ry = reflect1(qy + dy, H);
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int rx = reflect1(qx + dx, W);
+            const float a = x[ry * W + rx] - xc, b = y[ry * W + rx] - yc;
+            sx += a; sy += b;
+            sxx = fmaf(a, a, sxx); syy = fmaf(b, b, syy); sxy = fmaf(a, b, sxy);
+        }
+    }
+    const float r9 = 1.0f / 9.0f;
+    const float dx = sx * r9, dy = sy * r9;
+    const float mux = xc + dx, muy = yc + dy;
+    const float vx = fmaf(-dx, dx, sxx * r9), vy = fmaf(-dy, dy, syy * r9), vxy = fmaf(-dx, dy, sxy * r9);
+    const float A = fmaf(2.0f * mux, muy, SSIM_C1), B = fmaf(2.0f, vxy, SSIM_C2);
+    const float Cc = fmaf(mux, mux, fmaf(muy, muy, SSIM_C1)), D = vx + vy + SSIM_C2;
+    const float rC = 1.0f / Cc, rD = 1.0f / D, inv = rC * rD;
+    const float S = A * B * inv;
+    const float raw = (1.0f - S) * 0.5f;
+    WinXY o;
+    o.s = fminf(fmaxf(raw, 0.f), 1.f);
+    o.pass = (raw >= 0.f && raw <= 1.f) ? 1.f : 0.f;
+    const float k = 2.0f / 9.0f;
+    o.bx = -k * S * rD; o.by = o.bx;
+    o.g = k * A * inv;
+    o.ax = k * (muy * (B - A) * inv - S * mux * rC + S * mux * rD);
+    o.ay = k * (mux * (B - A) * inv - S * muy * rC + S * muy * rD);
+    return o;
+}
+
+__device__ __forceinline__ float fold_w(int g, int d, int n) {   // adjoint of reflect-pad(1)
+    return 1.0f + ((g == 1 && d == -1) ? 1.f : 0.f) + ((g == n - 2 && d == 1) ? 1.f : 0.f);
+}
+
+__global__ void ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                int W, int H, long long planes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long HW = (long long)W * H;
+    if (i >= HW * planes) return;
+    const long long pl = i / HW;
+    const int p = (int)(i % HW);
+    out[i] = window_xy(x + pl * HW, y + pl * HW, p % W, p / W, W, H).s;
+}
+
+__global__ void ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gout,
+                                float* __restrict__ gx, float* __restrict__ gy, int W, int H, long long planes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long HW = (long long)W * H;
+    if (i >= HW * planes) return;
+    const long long pl = i / HW;
+    const int p = (int)(i % HW), jx = p % W, jy = p / W;
+    const float* xp = x + pl * HW; const float* yp = y + pl * HW; const float* gp = gout + pl * HW;
+    const float xj = xp[p], yj = yp[p];
+    float ax = 0.f, ay = 0.f;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int qy = jy + dy;
+        if (qy < 0 || qy >= H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int qx = jx + dx;
+            if (qx < 0 || qx >= W) continue;
+            const WinXY w = window_xy(xp, yp, qx, qy, W, H);
+            const float k = fold_w(jx, dx, W) * fold_w(jy, dy, H) * gp[qy * W + qx] * (-0.5f) * w.pass;
+            ax = fmaf(k, w.ax + w.bx * xj + w.g * yj, ax);
+            ay = fmaf(k, w.ay + w.by * yj + w.g * xj, ay);
+        }
+    }
+    if (gx) gx[i] = ax;
+    if (gy) gy[i] = ay;
+}
+
+struct PmArgs {
+    int S, W, H, C, N;
+    const float* pred[MAX_S]; long long pred_ns[MAX_S];
+    const float* target; long long target_ns;
+    const float* mask;
+    float alpha;
+    float* gpred[MAX_S];
+};
+
+template <int C>
+__device__ __forceinline__ float photometric_at(const float* __restrict__ x, const float* __restrict__ y, int qx, int qy,
+                                                int W, int H, float alpha) {
+    const long long HW = (long long)W * H;
+    float ss = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        ss += window_xy(x + c * HW, y + c * HW, qx, qy, W, H).s;
+        l1 += fabsf(y[c * HW + qy * W + qx] - x[c * HW + qy * W + qx]);
+    }
+    return alpha * (ss * (1.0f / C)) + (1.0f - alpha) * (l1 * (1.0f / C));
+}
+
+template <int C>
+__global__ void photomin_fwd_kernel(PmArgs a, float* __restrict__ out, int* __restrict__ argmin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long HW = (long long)a.W * a.H;
+    if (i >= HW * a.N) return;
+    const int n = (int)(i / HW), p = (int)(i % HW), qx = p % a.W, qy = p / a.W;
+    const float* y = a.target + n * a.target_ns;
+    float best = 0.f; int bi = -1;
+    if (a.mask) best = a.mask[i];
+    for (int s = 0; s < a.S; ++s) {
+        const float pe = photometric_at<C>(a.pred[s] + n * a.pred_ns[s], y, qx, qy, a.W, a.H, a.alpha);
+        if ((s == 0 && !a.mask) || pe < best) { best = pe; bi = s; }
+    }
+    out[i] = best;
+    if (argmin) argmin[i] = bi;
+}
+
+template <int C>
+__global__ void photomin_bwd_kernel(PmArgs a, const float* __restrict__ gout, const int* __restrict__ argmin,
+                                    float* __restrict__ gtarget, float* __restrict__ gmask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long HW = (long long)a.W * a.H;
+    if (i >= HW * a.N) return;
+    const int n = (int)(i / HW), p = (int)(i % HW), jx = p % a.W, jy = p / a.W;
+    const float* y = a.target + n * a.target_ns;
+    const int* am = argmin ? argmin + (long long)n * HW : nullptr;
+    float gp[MAX_S][C], gt[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { gt[c] = 0.f; for (int s = 0; s < MAX_S; ++s) gp[s][c] = 0.f; }
+    const float ks = a.alpha * (1.0f / C) * (-0.5f), kl = (1.0f - a.alpha) * (1.0f / C);
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int qy = jy + dy;
+        if (qy < 0 || qy >= a.H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int qx = jx + dx;
+            if (qx < 0 || qx >= a.W) continue;
+            const int sq = am ? am[qy * a.W + qx] : 0;
+            if (sq < 0) continue;
+            const float k = fold_w(jx, dx, a.W) * fold_w(jy, dy, a.H) * gout[(long long)n * HW + qy * a.W + qx] * ks;
+            const float* x = a.pred[sq] + n * a.pred_ns[sq];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const WinXY w = window_xy(x + c * HW, y + c * HW, qx, qy, a.W, a.H);
+                const float xj = x[c * HW + p], yj = y[c * HW + p];
+                const float kk = k * w.pass;
+                const float vx = kk * (w.ax + w.bx * xj + w.g * yj);
+#pragma unroll
+                for (int s = 0; s < MAX_S; ++s) if (s == sq) gp[s][c] += vx;
+                gt[c] = fmaf(kk, w.ay + w.by * yj + w.g * xj, gt[c]);
+            }
+        }
+    }
+    const int sj = am ? am[p] : 0;
+    const float gj = gout[i];
+    if (sj >= 0) {
+        const float* x = a.pred[sj] + n * a.pred_ns[sj];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float df = x[c * HW + p] - y[c * HW + p];
+            const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+#pragma unroll
+            for (int s = 0; s < MAX_S; ++s) if (s == sj) gp[s][c] += gj * kl * sg;
+            gt[c] -= gj * kl * sg;
+        }
+    }
+    for (int s = 0; s < a.S; ++s)
+        if (a.gpred[s])
+#pragma unroll
+            for (int c = 0; c < C; ++c) a.gpred[s][((long long)n * C + c) * HW + p] = gp[s][c];
+    if (gtarget)
+#pragma unroll
+        for (int c = 0; c < C; ++c) gtarget[((long long)n * C + c) * HW + p] = gt[c];
+    if (gmask) gmask[i] = (sj < 0) ? gj : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// A8 smooth_loss (src/utils.jl:143-173), optional mean-normalisation (src/training.jl:64-65)
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) smooth_stats_kernel(const float* __restrict__ disp, const float* __restrict__ img,
+                                                           long long img_ns, float* __restrict__ partial, int W, int H) {
+    __shared__ float scratch[3 * 8];
+    const int n = blockIdx.y;
+    const long long HW = (long long)W * H;
+    float v[3] = {0.f, 0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
+        stats_pixel<C>(disp + n * HW, img + n * img_ns, i, W, H, v[0], v[1], v[2]);
+    block_sum<3>(v, scratch);
+    if (threadIdx.x == 0) {
+        float* o = partial + ((long long)n * gridDim.x + blockIdx.x) * NSTAT;
+        o[0] = 0.f; o[1] = v[0]; o[2] = v[1]; o[3] = v[2];
+    }
+}
+
+__global__ void smooth_final_kernel(const float* __restrict__ stats, float* __restrict__ out, int W, int H, int N, int normalize) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const float one = 1.0f;
+        *out = loss_from_stats(stats, W, H, N, 1, &one, 1.0f, normalize);
+    }
+}
+
+template <int C>
+__global__ void smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img, long long img_ns,
+                                  const float* __restrict__ stats, float gout, float* __restrict__ gdisp,
+                                  float* __restrict__ gimg, int W, int H, int N, int normalize) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long HW = (long long)W * H;
+    if (i >= HW * N) return;
+    const int n = (int)(i / HW), p = (int)(i % HW), x = p % W, y = p / W;
+    const float* d = disp + n * HW;
+    const float* t = img + n * img_ns;
+    const float cx = 1.0f / ((float)(W - 1) * (float)H * (float)N), cy = 1.0f / ((float)W * (float)(H - 1) * (float)N);
+    float sA = gout, sB = 0.f;
+    if (normalize) {
+        const float* st = stats + (long long)n * NSTAT;
+        const float m = st[3] / (float)HW + 1e-7f;
+        sA = gout / m;
+        sB = gout * (cx * st[1] + cy * st[2]) / (m * m * (float)HW);
+    }
+    float gh = 0.f;
+    float gi[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) gi[c] = 0.f;
+    // the four pairs this pixel takes part in: (p,p+1), (p-1,p), (p,p+W), (p-W,p)
+    const int offs[4] = {1, -1, W, -W};
+    const bool ok[4] = {x + 1 < W, x > 0, y + 1 < H, y > 0};
+    const float cw[4] = {cx, cx, cy, cy};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        const int a = (k & 1) ? p + offs[k] : p;       // first pixel of the pair
+        const int b = (k & 1) ? p : p + offs[k];       // second pixel
+        float g = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) g += fabsf(t[c * HW + a] - t[c * HW + b]);
+        const float e = expf(-g * (1.0f / C));
+        const float dd = d[a] - d[b];
+        const float sg = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f);
+        const float side = (k & 1) ? -1.f : 1.f;       // p is the second pixel for odd k
+        gh += side * cw[k] * sg * e;
+        if (gimg) {
+            const float term = sA * cw[k] * fabsf(dd) * e * (1.0f / C);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float dt = t[c * HW + a] - t[c * HW + b];
+                const float st = dt > 0.f ? 1.f : (dt < 0.f ? -1.f : 0.f);
+                gi[c] -= side * term * st;
+            }
+        }
+    }
+    gdisp[i] = sA * gh - sB;
+    if (gimg)
+#pragma unroll
+        for (int c = 0; c < C; ++c) gimg[((long long)n * C + c) * HW + p] = gi[c];
+}
+
+}  // namespace md2
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using namespace md2;
+#define ST ((cudaStream_t)st)
+#define CTX_OK() do { MD2_REQUIRE(ctx != nullptr, "null ctx"); MD2_CHECK(cudaSetDevice(ctx->device)); } while (0)
+
+static inline void depth_ab(float min_depth, float max_depth, float& a, float& b) {
+    const float mind = (float)(1.0 / (double)max_depth), maxd = (float)(1.0 / (double)min_depth);
+    a = maxd - mind; b = mind;
+}
+
+extern "C" {
+
+int md2_disparity_to_depth_fwd(md2_ctx* ctx, const float* disp, float* depth, int64_t count, float min_depth,
+                               float max_depth, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(disp && depth && count >= 0, "bad arguments");
+    if (count == 0) return 0;
+    float a, b; depth_ab(min_depth, max_depth, a, b);
+    d2d_fwd_kernel<<<cdiv(count, 256), 256, 0, ST>>>(disp, depth, count, a, b);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_disparity_to_depth_bwd(md2_ctx* ctx, const float* disp, const float* gdepth, float* gdisp, int64_t count,
+                               float min_depth, float max_depth, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(disp && gdepth && gdisp && count >= 0, "bad arguments");
+    if (count == 0) return 0;
+    float a, b; depth_ab(min_depth, max_depth, a, b);
+    d2d_bwd_kernel<<<cdiv(count, 256), 256, 0, ST>>>(disp, gdepth, gdisp, count, a, b);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int md2_backproject_fwd(md2_ctx* ctx, const float* depth, const float* invK, float* points, int32_t W, int32_t H,
+                        int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(depth && invK && points && W > 0 && H > 0 && N > 0, "bad arguments");
+    backproject_fwd_kernel<<<cdiv((long long)W * H * N, 256), 256, 0, ST>>>(depth, invK, points, W, H, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_backproject_bwd(md2_ctx* ctx, const float* gpoints, const float* invK, float* gdepth, int32_t W, int32_t H,
+                        int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(gpoints && invK && gdepth && W > 0 && H > 0 && N > 0, "bad arguments");
+    backproject_bwd_kernel<<<cdiv((long long)W * H * N, 256), 256, 0, ST>>>(gpoints, invK, gdepth, W, H, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int md2_project_fwd(md2_ctx* ctx, const float* points, const float* K, const float* R, const float* t, float* uv,
+                    int32_t W, int32_t H, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(points && K && R && t && uv && W > 1 && H > 1 && N > 0, "bad arguments");
+    project_fwd_kernel<<<cdiv((long long)W * H * N, 256), 256, 0, ST>>>(points, K, R, t, uv, W, H, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_project_bwd(md2_ctx* ctx, const float* points, const float* K, const float* R, const float* t,
+                    const float* guv, float* gpoints, float* gR, float* gt, int32_t W, int32_t H, int32_t N,
+                    md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(points && K && R && t && guv && gpoints && gR && gt && W > 1 && H > 1 && N > 0, "bad arguments");
+    const int bpi = max(1, min(128, cdiv((long long)W * H, 1024)));
+    float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)bpi * N * 12);
+    if (!partial) return 1;
+    project_bwd_kernel<<<dim3(bpi, N), 256, 0, ST>>>(points, K, R, t, guv, gpoints, partial, W, H, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return launch_reduce_partials(ctx, partial, gR, 9, gt, N, bpi, 12, ST);
+}
+
+int md2_so3_exp_map_fwd(md2_ctx* ctx, const float* rvec, float* R, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(rvec && R && N > 0, "bad arguments");
+    so3_fwd_kernel<<<cdiv(N, 64), 64, 0, ST>>>(rvec, R, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_so3_exp_map_bwd(md2_ctx* ctx, const float* rvec, const float* gR, float* grvec, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(rvec && gR && grvec && N > 0, "bad arguments");
+    so3_bwd_kernel<<<cdiv(N, 64), 64, 0, ST>>>(rvec, gR, grvec, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_hat_fwd(md2_ctx* ctx, const float* rvec, float* S, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(rvec && S && N > 0, "bad arguments");
+    hat_fwd_kernel<<<cdiv(N, 64), 64, 0, ST>>>(rvec, S, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_hat_bwd(md2_ctx* ctx, const float* gS, float* grvec, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(gS && grvec && N > 0, "bad arguments");
+    hat_bwd_kernel<<<cdiv(N, 64), 64, 0, ST>>>(gS, grvec, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_compose_T_fwd(md2_ctx* ctx, const float* rvec, const float* tvec, int32_t invert, float* R, float* t,
+                      int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(rvec && tvec && R && t && N > 0, "bad arguments");
+    compose_fwd_kernel<<<cdiv(N, 64), 64, 0, ST>>>(rvec, tvec, invert, R, t, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_compose_T_bwd(md2_ctx* ctx, const float* rvec, const float* tvec, int32_t invert, const float* gR,
+                      const float* gt, float* grvec, float* gtvec, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(rvec && tvec && grvec && gtvec && N > 0, "bad arguments");
+    compose_bwd_kernel<<<cdiv(N, 64), 64, 0, ST>>>(rvec, tvec, invert, gR, gt, grvec, gtvec, N);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int md2_grid_sample_fwd(md2_ctx* ctx, const float* input, const float* grid, float* out, int32_t W, int32_t H,
+                        int32_t C, int32_t N, int32_t Wo, int32_t Ho, int32_t padding_mode, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(input && grid && out && W > 0 && H > 0 && C > 0 && N > 0 && Wo > 0 && Ho > 0, "bad arguments");
+    MD2_REQUIRE(padding_mode == 0 || padding_mode == 1, "padding_mode must be 0 (:zeros) or 1 (:border)");
+    grid_sample_fwd_kernel<<<cdiv((long long)Wo * Ho * N, 256), 256, 0, ST>>>(input, grid, out, W, H, C, N, Wo, Ho, padding_mode);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_grid_sample_bwd(md2_ctx* ctx, const float* input, const float* grid, const float* gout, float* ginput,
+                        float* ggrid, int32_t W, int32_t H, int32_t C, int32_t N, int32_t Wo, int32_t Ho,
+                        int32_t padding_mode, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(input && grid && gout && W > 0 && H > 0 && C > 0 && N > 0 && Wo > 0 && Ho > 0, "bad arguments");
+    MD2_REQUIRE(padding_mode == 0 || padding_mode == 1, "padding_mode must be 0 (:zeros) or 1 (:border)");
+    grid_sample_bwd_kernel<<<cdiv((long long)Wo * Ho * N, 256), 256, 0, ST>>>(input, grid, gout, ginput, ggrid, W, H, C, N, Wo, Ho, padding_mode);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int md2_ssim_fwd(md2_ctx* ctx, const float* x, const float* y, float* out, int32_t W, int32_t H, int32_t C, int32_t N,
+                 md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(x && y && out && W >= 2 && H >= 2 && C > 0 && N > 0, "bad arguments (W,H >= 2)");
+    const long long planes = (long long)C * N;
+    ssim_fwd_kernel<<<cdiv((long long)W * H * planes, 256), 256, 0, ST>>>(x, y, out, W, H, planes);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_ssim_bwd(md2_ctx* ctx, const float* x, const float* y, const float* gout, float* gx, float* gy, int32_t W,
+                 int32_t H, int32_t C, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(x && y && gout && W >= 2 && H >= 2 && C > 0 && N > 0, "bad arguments (W,H >= 2)");
+    const long long planes = (long long)C * N;
+    ssim_bwd_kernel<<<cdiv((long long)W * H * planes, 256), 256, 0, ST>>>(x, y, gout, gx, gy, W, H, planes);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int fill_pm(PmArgs& a, int32_t S, const float* const* pred, const int64_t* pred_ns, const float* target,
+                   int64_t target_ns, const float* mask, float alpha, int W, int H, int C, int N) {
+    MD2_REQUIRE(S >= 1 && S <= MAX_S, "S must be 1 or 2");
+    MD2_REQUIRE(C == 1 || C == 3, "C must be 1 or 3");
+    MD2_REQUIRE(pred && pred_ns && target && W >= 2 && H >= 2 && N > 0, "bad arguments (W,H >= 2)");
+    a.S = S; a.W = W; a.H = H; a.C = C; a.N = N;
+    for (int s = 0; s < MAX_S; ++s) {
+        a.pred[s] = s < S ? pred[s] : nullptr;
+        a.pred_ns[s] = s < S ? pred_ns[s] : 0;
+        a.gpred[s] = nullptr;
+        if (s < S) MD2_REQUIRE(pred[s] != nullptr, "null prediction");
+    }
+    a.target = target; a.target_ns = target_ns; a.mask = mask; a.alpha = alpha;
+    return 0;
+}
+
+int md2_photometric_min_fwd(md2_ctx* ctx, int32_t S, const float* const* pred, const int64_t* pred_image_stride,
+                            const float* target, int64_t target_image_stride, const float* mask, float alpha,
+                            float* out, int32_t* argmin, int32_t W, int32_t H, int32_t C, int32_t N, md2_stream st) {
+    CTX_OK();
+    PmArgs a;
+    if (fill_pm(a, S, pred, pred_image_stride, target, target_image_stride, mask, alpha, W, H, C, N)) return 1;
+    MD2_REQUIRE(out != nullptr, "null output");
+    const int g = cdiv((long long)W * H * N, 128);
+    if (C == 1) photomin_fwd_kernel<1><<<g, 128, 0, ST>>>(a, out, argmin);
+    else photomin_fwd_kernel<3><<<g, 128, 0, ST>>>(a, out, argmin);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int md2_photometric_min_bwd(md2_ctx* ctx, int32_t S, const float* const* pred, const int64_t* pred_image_stride,
+                            const float* target, int64_t target_image_stride, const float* mask, float alpha,
+                            const float* gout, const int32_t* argmin, float* const* gpred, float* gtarget,
+                            float* gmask, int32_t W, int32_t H, int32_t C, int32_t N, md2_stream st) {
+    CTX_OK();
+    PmArgs a;
+    if (fill_pm(a, S, pred, pred_image_stride, target, target_image_stride, mask, alpha, W, H, C, N)) return 1;
+    MD2_REQUIRE(gout != nullptr, "null upstream gradient");
+    MD2_REQUIRE(argmin != nullptr || (S == 1 && !mask), "argmin from the forward call is required when S > 1 or a mask is used");
+    for (int s = 0; s < S; ++s) a.gpred[s] = gpred ? gpred[s] : nullptr;
+    const int g = cdiv((long long)W * H * N, 128);
+    if (C == 1) photomin_bwd_kernel<1><<<g, 128, 0, ST>>>(a, gout, argmin, gtarget, gmask);
+    else photomin_bwd_kernel<3><<<g, 128, 0, ST>>>(a, gout, argmin, gtarget, gmask);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int smooth_stats(md2_ctx* ctx, const float* disp, const float* image, int64_t image_stride, int W, int H,
+                        int C, int N, float** stats_out, cudaStream_t st) {
+    const int bpi = max(1, min(64, cdiv((long long)W * H, 2048)));
+    float* partial = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)bpi * N * NSTAT);
+    float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)N * NSTAT);
+    if (!partial || !stats) return 1;
+    if (C == 1) smooth_stats_kernel<1><<<dim3(bpi, N), 256, 0, st>>>(disp, image, image_stride, partial, W, H);
+    else smooth_stats_kernel<3><<<dim3(bpi, N), 256, 0, st>>>(disp, image, image_stride, partial, W, H);
+    MD2_LAUNCH_CHECK(ctx);
+    *stats_out = stats;
+    return launch_reduce_partials(ctx, partial, stats, NSTAT, nullptr, N, bpi, NSTAT, st);
+}
+
+int md2_smooth_loss_fwd(md2_ctx* ctx, const float* disp, const float* image, int64_t image_stride, float* out,
+                        int32_t normalize, int32_t W, int32_t H, int32_t C, int32_t N, md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(disp && image && out && W >= 2 && H >= 2 && N > 0, "bad arguments (W,H >= 2)");
+    MD2_REQUIRE(C == 1 || C == 3, "C must be 1 or 3");
+    float* stats;
+    if (smooth_stats(ctx, disp, image, image_stride, W, H, C, N, &stats, ST)) return 1;
+    smooth_final_kernel<<<1, 32, 0, ST>>>(stats, out, W, H, N, normalize);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int md2_smooth_loss_bwd(md2_ctx* ctx, const float* disp, const float* image, int64_t image_stride, float gout,
+                        float* gdisp, float* gimage, int32_t normalize, int32_t W, int32_t H, int32_t C, int32_t N,
+                        md2_stream st) {
+    CTX_OK();
+    MD2_REQUIRE(disp && image && gdisp && W >= 2 && H >= 2 && N > 0, "bad arguments (W,H >= 2)");
+    MD2_REQUIRE(C == 1 || C == 3, "C must be 1 or 3");
+    float* stats = nullptr;
+    if (normalize && smooth_stats(ctx, disp, image, image_stride, W, H, C, N, &stats, ST)) return 1;
+    const int g = cdiv((long long)W * H * N, 256);
+    if (C == 1) smooth_bwd_kernel<1><<<g, 256, 0, ST>>>(disp, image, image_stride, stats, gout, gdisp, gimage, W, H, N, normalize);
+    else smooth_bwd_kernel<3><<<g, 256, 0, ST>>>(disp, image, image_stride, stats, gout, gdisp, gimage, W, H, N, normalize);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // extern "C"
