@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: the fused view-synthesis loss (warp + SSIM/L1 photometric loss,
+forward + backward, all 4 decoder scales) of Monodepth2.jl training.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K    # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one synthetic batch.  Workload at every N:
+BASELINE.json configs[1] -- 416x128, batch 8 per GPU, C=1 (KITTI gray as in train()),
+S=2 sources, 4 scales at the decoder's native sizes, no automask, gradients to the
+disparities, the poses and the source images (g=1 of BASELINE.md's work model).
+Inputs are resident in HBM before the timed region; the steps rotate through a ring of
+input/gradient sets larger than twice the L2, so no step finds its inputs in cache.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+W_, H_, NB, CH, S_, LS = 416, 128, 8, 1, 2, 4
+SCALES = (0.125, 0.25, 0.5, 1.0)
+METRIC = "train frames/s @416x128 R18: view-synthesis loss path (warp + SSIM/L1 loss, fwd+bwd, 4 scales)"
+WORKLOAD = "configs[1]: 416x128, batch 8/GPU, C=1, S=2, L=4 native-size disparities, no automask, g=1"
+
+
+def algorithmic_bytes(W, H, N, C, S, L, m=0, g=1):
+    """fwd 4(1+C+SC+m) + bwd 4(1+C+SC+m) + 4(1+gSC) bytes per unit"""
+    per_unit = 4 * (1 + C + S * C + m) * 2 + 4 * (1 + g * S * C)
+    return per_unit * W * H * N * L, per_unit
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """polls NVML for SM clock and throttle reasons while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.002)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def make_sets(n_sets, dev, seed0):
+    """ring of independent input + gradient-output sets, each built from the seeded synthetic
+    generator shared with the tests (oracle/torch_oracle.synthetic_batch is only used to MAKE
+    data here, never to compute)."""
+    from oracle import torch_oracle as O
+    base = O.synthetic_batch(NB, CH, H_, W_, seed=seed0)
+    sets = []
+    g = torch.Generator().manual_seed(seed0 + 1)
+    for i in range(n_sets):
+        x, disps, rv, tv = base
+        if i:   # cheap decorrelated variants of the base batch (different data per ring slot)
+            x = (x + 0.02 * torch.rand(x.shape, generator=g)).clamp(0, 1)
+            disps = [(d * (0.9 + 0.2 * torch.rand(d.shape, generator=g))).clamp(0.01, 0.99) for d in disps]
+        sets.append(dict(
+            x=x.to(dev), disps=[d.to(dev) for d in disps], rv=[r.to(dev) for r in rv], tv=[t.to(dev) for t in tv],
+            loss=torch.zeros((), device=dev), gd=[torch.empty_like(d, device=dev) for d in disps],
+            gr=[torch.empty(NB, 3, device=dev) for _ in range(S_)], gt=[torch.empty(NB, 3, device=dev) for _ in range(S_)],
+            gx=torch.zeros(x.shape, device=dev)))
+    return sets, base
+
+
+def run_ours(args):
+    import monodepth2_jl_b200 as M
+    from monodepth2_jl_b200 import _lib as L
+    from oracle import torch_oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = M.Context.get(dev)
+    K, invK = O.make_K(W_, H_)
+    K_cm, invK_cm = K.t().contiguous().to(dev), invK.t().contiguous().to(dev)
+    sw = [1e-3 * s for s in SCALES]
+
+    abytes, per_unit = algorithmic_bytes(W_, H_, NB, CH, S_, LS)
+    l2_bytes = 126e6
+    set_bytes = 4 * (NB * 3 * CH * H_ * W_ * 2 + 2 * sum(int(NB * round(H_ * s) * round(W_ * s)) for s in SCALES))
+    n_sets = max(4, int(2.5 * l2_bytes / set_bytes) + 1)
+    sets, base = make_sets(n_sets, dev, 42 + rank)
+
+    def desc_for(st):
+        x = st["x"]
+        return L.make_vsl_desc(
+            target=x[:, 1], target_stride=x.stride(0), sources=[x[:, 0], x[:, 2]], source_strides=[x.stride(0)] * 2,
+            disparities=st["disps"], K_cm=K_cm, invK_cm=invK_cm, rot=st["rv"], trans=st["tv"], pose_mode=1,
+            invert=[1, 0], smooth_weight=sw, loss_scale=1.0 / LS, normalize_disparity=True, loss=st["loss"],
+            grad_disparity=st["gd"], grad_rot=st["gr"], grad_trans=st["gt"],
+            grad_source=[st["gx"][:, 0], st["gx"][:, 2]], shape=(NB, CH, H_, W_))
+
+    descs = [desc_for(st) for st in sets]
+    lib, handle = ctx.lib, ctx.handle
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+    fwdbwd = lib.md2_view_synthesis_loss_fwdbwd
+
+    def step(i):
+        st = sets[i % n_sets]
+        st["gx"].zero_()   # the source-image gradient is accumulated with atomics: zero it per step
+        rc = fwdbwd(handle, C.byref(descs[i % n_sets]), 1.0, sptr)
+        if rc:
+            raise RuntimeError(lib.md2_last_error().decode())
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # warm-up: at least W steps, and enough to bring clocks up and touch every ring slot
+    warm = max(args.warmup, 3, n_sets)
+    t0 = time.time()
+    k = 0
+    while k < warm or time.time() - t0 < 0.3:
+        step(k)
+        k += 1
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.sample()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    sampler.sample()
+    sampler.stop_flag = True
+    launches = ctx.launches - l0 + args.steps   # + one memset (gx) per step
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    frames = NB * world * args.steps
+    value = frames / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: second pass with per-launch CUDA events ----
+    ctx.profile(True)
+    for i in range(args.steps):
+        step(i)
+    kms, kn = ctx.profile_read()
+    ctx.profile(False)
+    k_ms = kms / max(kn, 1)
+    peak, peak_src = peaks()
+    achieved = abytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("fused_bwd_c1_bytes_per_launch")
+
+    # ---- e2e: public API with HOST (pinned) buffers, H2D of inputs + D2H of results per step ----
+    hx, hd, hr, ht = base
+    pin = lambda t: t.contiguous().pin_memory()
+    hx, hd, hr, ht = pin(hx), [pin(d) for d in hd], [pin(r) for r in hr], [pin(t) for t in ht]
+    dx = torch.empty_like(hx, device=dev)
+    dd = [torch.empty_like(d, device=dev).requires_grad_(True) for d in hd]
+    dr = [torch.empty_like(r, device=dev).requires_grad_(True) for r in hr]
+    dt = [torch.empty_like(t, device=dev).requires_grad_(True) for t in ht]
+    h_loss = torch.zeros((), pin_memory=True)
+    h_gd = [torch.empty_like(d).pin_memory() for d in hd]
+    h_gp = [torch.empty(NB, 3).pin_memory() for _ in range(2 * S_)]
+    Kd, invKd = K.to(dev), invK.to(dev)
+    h2d = sum(t.numel() * 4 for t in [hx] + hd + hr + ht)
+    d2h = 4 + sum(t.numel() * 4 for t in h_gd + h_gp)
+
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True)
+        with torch.no_grad():
+            for a, b in zip(dd + dr + dt, hd + hr + ht):
+                a.copy_(b, non_blocking=True)
+        for a in dd + dr + dt:
+            a.grad = None
+        loss = M.view_synthesis_loss(dx, dd, dr, dt, Kd, invKd, K_cm=K_cm, invK_cm=invK_cm)
+        loss.backward()
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        for a, b in zip(h_gd + h_gp, dd + dr + dt):
+            a.copy_(b.grad, non_blocking=True)
+        torch.cuda.synchronize(dev)   # the caller consumes the host results every step
+
+    for _ in range(5):
+        e2e_step()
+    barrier()
+    e_steps = min(args.steps, 200)
+    e0.record(stream)
+    for _ in range(e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e_ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = t.item()
+    e2e_value = NB * world * e_steps / (e_ms * 1e-3)
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded KITTI-shaped triplets, random-init poses/disparities)",
+        "config": {"workload": WORKLOAD, "width": W_, "height": H_, "batch_per_gpu": NB, "channels": CH,
+                   "sources": S_, "scales": LS, "automask": False, "grad_source_images": True,
+                   "l2_policy": f"inputs larger than L2: ring of {n_sets} input/gradient sets ({n_sets * set_bytes / 1e6:.0f} MB) rotated per step",
+                   "api": "md2_view_synthesis_loss_fwdbwd (C ABI), one call per step", "sharding": "batch, no data-path collective"},
+        "images_per_s": round(3 * value, 1),
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e_steps, "api": "monodepth2_jl_b200.view_synthesis_loss(...).backward() with pinned host buffers"},
+        "roofline": {"bound": "hbm", "kernel": "fused_kernel<C=1,S=2,BWD> (fused fwd+bwd tile kernel, all scales in one launch)",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": traffic, "algorithmic_bytes_per_launch": abytes, "bytes_per_unit": per_unit,
+                     "kernel_ms": round(k_ms, 5), "kernel_launches_timed": int(kn), "peak_source": peak_src,
+                     "step_frac_of_peak": round(abytes / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(base, budget_s=15.0)
+        print(json.dumps(out), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_step(base, K, invK):
+    """one step of the reference's CPU path as restated by the oracle (fp32, autograd = Zygote)"""
+    from oracle import torch_oracle as O
+    x, disps, rv, tv = base
+    x = x.clone().requires_grad_(True)   # Zygote also forms the image cotangent inside grid_sample's pullback
+    dd = [d.clone().requires_grad_(True) for d in disps]
+    rr = [r.clone().requires_grad_(True) for r in rv]
+    tt = [t.clone().requires_grad_(True) for t in tv]
+    loss = O.view_synthesis_loss(x, dd, rr, tt, K, invK)
+    loss.backward()
+    return loss.item()
+
+
+def cpu_baseline(base, budget_s=15.0, steps=None, warmup=1):
+    from oracle import torch_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    K, invK = O.make_K(W_, H_)
+    for _ in range(warmup):
+        cpu_step(base, K, invK)
+    times = []
+    t_start = time.time()
+    while (steps is None and time.time() - t_start < budget_s and len(times) < 50) or (steps is not None and len(times) < steps):
+        t0 = time.time()
+        cpu_step(base, K, invK)
+        times.append(time.time() - t0)
+    mean = sum(times) / len(times)
+    return {"value": round(NB / mean, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} steps of the same workload (batch {NB}, 416x128, 4 scales, fwd+bwd) through the "
+                      f"PyTorch-CPU restatement of the reference (Julia is not installed), fp32, {cores} threads; "
+                      f"best {NB / min(times):.3f} frames/s", "ms_per_step": round(mean * 1e3, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import torch_oracle as O
+    base = O.synthetic_batch(NB, CH, H_, W_, seed=42)
+    cb = cpu_baseline(base, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same seeded batch as the GPU arm)",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path timed on rank 0's host cores only; each step is one "
+                   "batch of 8 triplets; the reference itself is single-process"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40   # bounded sample: the CPU arm takes ~1 s per step
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,8 @@ _P = c_void   # device pointers travel as void*
 _SIGS = {
     "md2_create": [C.c_int, C.POINTER(c_void)],
     "md2_destroy": [c_void],
+    "md2_profile_enable": [c_void, _I32],
+    "md2_profile_read": [c_void, C.POINTER(C.c_float), C.POINTER(C.c_int64)],
     "md2_disparity_to_depth_fwd": [c_void, _P, _P, _I64, _F, _F, _P],
     "md2_disparity_to_depth_bwd": [c_void, _P, _P, _P, _I64, _F, _F, _P],
     "md2_backproject_fwd": [c_void, _P, _P, _P, _I32, _I32, _I32, _P],
@@ -210,6 +212,14 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.md2_launch_count(self.handle))
+
+    def profile(self, on):
+        self._check(self.lib.md2_profile_enable(self.handle, int(on)))
+
+    def profile_read(self):
+        ms, n = C.c_float(), C.c_int64()
+        self._check(self.lib.md2_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
 
 def require_cuda(*tensors):

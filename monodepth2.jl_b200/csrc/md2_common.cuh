@@ -24,10 +24,15 @@ struct Workspace {
 enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, MD2_WS_GDISP,
        MD2_WS_POSEIN, MD2_WS_MISC, MD2_WS_COUNT };
 
+#include <vector>
 struct md2_ctx {
     int device;
     int64_t launches;
     md2::Workspace ws[MD2_WS_COUNT];
+    // optional device timing of the dominant (fused tile) kernel, see md2_profile_*
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+    size_t prof_used = 0;
 };
 
 namespace md2 {

@@ -457,8 +457,22 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     }
     p.stats = stats;
 
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) {
+        if (ctx->prof_used + 2 > ctx->prof_ev.size()) {
+            for (int k = 0; k < 2; ++k) {
+                cudaEvent_t e;
+                MD2_CHECK(cudaEventCreate(&e));
+                ctx->prof_ev.push_back(e);
+            }
+        }
+        ev0 = ctx->prof_ev[ctx->prof_used]; ev1 = ctx->prof_ev[ctx->prof_used + 1];
+        ctx->prof_used += 2;
+        MD2_CHECK(cudaEventRecord(ev0, st));
+    }
     if (bwd) { if (dispatch_fused<true>(ctx, C, S, p, st)) return 1; }
     else     { if (dispatch_fused<false>(ctx, C, S, p, st)) return 1; }
+    if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
     if (launch_reduce_partials(ctx, partial, sums, NP, nullptr, L * N, tiles, NP, st)) return 1;
 
     FinalArgs fa;
@@ -662,11 +676,33 @@ int md2_destroy(md2_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < MD2_WS_COUNT; ++i)
         if (ctx->ws[i].ptr) cudaFree(ctx->ws[i].ptr);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
     return 0;
 }
 
 int64_t md2_launch_count(const md2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int md2_profile_enable(md2_ctx* ctx, int32_t on) {
+    MD2_REQUIRE(ctx != nullptr, "null ctx");
+    ctx->prof_on = on;
+    ctx->prof_used = 0;
+    return 0;
+}
+int md2_profile_read(md2_ctx* ctx, float* total_ms, int64_t* launches) {
+    MD2_REQUIRE(ctx != nullptr && total_ms && launches, "bad arguments");
+    float tot = 0.f;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        MD2_CHECK(cudaEventSynchronize(ctx->prof_ev[i + 1]));
+        float ms = 0.f;
+        MD2_CHECK(cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(ctx->prof_used / 2);
+    ctx->prof_used = 0;
+    return 0;
+}
 
 int md2_view_synthesis_loss_fwd(md2_ctx* ctx, const md2_vsl_desc* d, md2_stream st) {
     MD2_REQUIRE(ctx != nullptr, "null ctx");

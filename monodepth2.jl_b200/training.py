@@ -1,0 +1,242 @@
+"""The fused hot path behind the reference's loss entry points: `warp` (undefined in the
+reference, call at src/simple_depth.jl:30-32) and the tail of `train_loss`
+(src/training.jl:29-77), plus the containers that cross the boundary (`Pose`
+src/pose_decoder.jl:1-5, `Params` src/Monodepth.jl:32-42, `TrainCache` :44-55).
+Frame indices here are 0-based (the Julia binding converts from the reference's 1-based ids).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import Context, require_cuda
+from .ops import SSIM, Backproject, Project, _cm, _f32c, _p, composeT
+
+_F32 = torch.float32
+
+
+@dataclass
+class Pose:
+    rvec: torch.Tensor   # (N,3)  so3 rotation   [Julia 3xN]
+    tvec: torch.Tensor   # (N,3)  translation    [Julia 3x1xN]
+
+
+@dataclass
+class Params:
+    target_size: Tuple[int, int]          # (width, height)
+    batch_size: int
+    min_depth: float = 0.1
+    max_depth: float = 100.0
+    disparity_smoothness: float = 1e-3
+    frame_ids: List[int] = field(default_factory=lambda: [0, 1, 2])
+    automasking: bool = True
+
+
+@dataclass
+class TrainCache:
+    ssim: SSIM
+    backprojections: Backproject
+    projections: Project
+    K: torch.Tensor
+    invK: torch.Tensor
+    target_id: int
+    source_ids: Sequence[int]
+    scales: Sequence[float]
+
+    def __post_init__(self):
+        # column-major copies handed to the C ABI, made once
+        self.K_cm = _cm(_f32c(self.K.reshape(3, 3)))
+        self.invK_cm = _cm(_f32c(self.invK.reshape(3, 3)))
+
+
+def _frame_ptr_view(x, idx):
+    return x[:, idx]
+
+
+class _ViewSynthesisLoss(torch.autograd.Function):
+    """loss, d loss/d(disparities, rvecs, tvecs[, x]) through the fused CUDA kernels.  When any
+    input needs a gradient the value and the gradient are produced by ONE fused pass
+    (md2_view_synthesis_loss_fwdbwd, seed 1) and the pullback only scales them."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, *tensors):
+        Lc, S = cfg["L"], cfg["S"]
+        disps = [_f32c(t) for t in tensors[:Lc]]
+        rot = [_f32c(t) for t in tensors[Lc:Lc + S]]
+        trans = [_f32c(t) for t in tensors[Lc + S:Lc + 2 * S]]
+        x = _f32c(x)
+        require_cuda(x, *disps, *rot, *trans)
+        N, Lf, Cc, H, W = x.shape
+        c = Context.get(x.device)
+        need = [ctx.needs_input_grad[2 + i] for i in range(len(tensors))]
+        need_x = ctx.needs_input_grad[1] and cfg.get("grad_x", True)
+        any_grad = any(need) or need_x
+        dev = x.device
+        loss = torch.empty((), device=dev, dtype=_F32)
+        gd = [torch.empty_like(d) for d in disps] if any_grad else None
+        gr = [torch.empty_like(r) for r in rot] if any_grad else None
+        gt = [torch.empty_like(t) for t in trans] if any_grad else None
+        gx = torch.zeros_like(x) if need_x else None
+        viz_w = viz_l = None
+        if cfg.get("viz"):
+            viz_w = [torch.empty(N, Cc, H, W, device=dev, dtype=_F32) for _ in range(S)]
+            viz_l = torch.empty(N, 1, H, W, device=dev, dtype=_F32)
+        sid, tid = cfg["source_ids"], cfg["target_id"]
+        desc = L.make_vsl_desc(
+            target=x[:, tid], target_stride=x.stride(0),
+            sources=[x[:, i] for i in sid], source_strides=[x.stride(0)] * S,
+            disparities=disps, K_cm=cfg["K_cm"], invK_cm=cfg["invK_cm"], rot=rot, trans=trans,
+            pose_mode=cfg["pose_mode"], invert=cfg["invert"], automask=cfg.get("automask"),
+            min_depth=cfg["min_depth"], max_depth=cfg["max_depth"], smooth_weight=cfg["smooth_weight"],
+            loss_scale=cfg["loss_scale"], normalize_disparity=cfg["normalize"], loss=loss,
+            grad_disparity=gd, grad_rot=gr, grad_trans=gt,
+            grad_source=[gx[:, i] for i in sid] if need_x else None,
+            viz_warped=viz_w, viz_loss=viz_l, shape=(N, Cc, H, W))
+        if any_grad:
+            c.call("md2_view_synthesis_loss_fwdbwd", C.byref(desc), 1.0)
+            ctx.grads = (gd, gr, gt, gx)
+        else:
+            c.call("md2_view_synthesis_loss_fwd", C.byref(desc))
+            ctx.grads = None
+        ctx.pose_mode = cfg["pose_mode"]
+        ctx.viz = (viz_w, viz_l)
+        ctx.mark_non_differentiable(*([t for t in (viz_w or [])] + ([viz_l] if viz_l is not None else [])))
+        if cfg.get("viz"):
+            return (loss, viz_l, *viz_w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        gd, gr, gt, gx = ctx.grads
+        scale = lambda t: None if t is None else t * g
+        return (None, scale(gx), *[scale(t) for t in gd], *[scale(t) for t in gr], *[scale(t) for t in gt])
+
+
+def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, source_ids=(0, 2),
+                        scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0,
+                        disparity_smoothness=1e-3, auto_loss=None, normalize_disparity=True,
+                        smooth_weight=None, loss_scale=None, poses_are_rvec=True, invert=None,
+                        return_viz=False, K_cm=None, invK_cm=None):
+    """Everything of train_loss after `model(...)` (src/training.jl:29-77) in fused kernels.
+
+    x (N,L,C,H,W); disparities: list of (N,1,h_i,w_i) at the decoder's native sizes (smaller ones
+    are align-corners upsampled like the reference does); rot/trans: per source either
+    rvec/tvec (N,3) [poses_are_rvec=True: composeT is fused, invert = source_id < target_id]
+    or R (N,3,3)/t (N,3) as returned by composeT.  auto_loss (N,1,H,W) enables automasking.
+    Returns the scalar loss (and, if return_viz, the last scale's warp-loss map and warped
+    images, which the reference copies out for logging)."""
+    S, Lc = len(source_ids), len(disparities)
+    if invert is None:
+        invert = [sid < target_id for sid in source_ids]
+    if not poses_are_rvec:
+        rot = [_cm(r) for r in rot]
+    cfg = dict(L=Lc, S=S, source_ids=list(source_ids), target_id=target_id,
+               K_cm=K_cm if K_cm is not None else _cm(_f32c(K.reshape(3, 3))),
+               invK_cm=invK_cm if invK_cm is not None else _cm(_f32c(invK.reshape(3, 3))),
+               pose_mode=1 if poses_are_rvec else 0, invert=invert,
+               automask=_f32c(auto_loss.detach()) if auto_loss is not None else None,
+               min_depth=min_depth, max_depth=max_depth,
+               smooth_weight=smooth_weight if smooth_weight is not None else
+               [disparity_smoothness * s for s in list(scales)[:Lc]],
+               loss_scale=loss_scale if loss_scale is not None else 1.0 / Lc,
+               normalize=normalize_disparity, viz=return_viz)
+    trans = [t.reshape(-1, 3) for t in trans]
+    out = _ViewSynthesisLoss.apply(cfg, x, *disparities, *rot, *trans)
+    if return_viz:
+        loss, viz_l, *viz_w = out
+        return loss, viz_w, viz_l
+    return out
+
+
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, disp, x, *poses):
+        S = cfg["S"]
+        disp, x = _f32c(disp), _f32c(x)
+        rot = [_cm(_f32c(r)) for r in poses[:S]]
+        trans = [_f32c(t).reshape(-1, 3) for t in poses[S:]]
+        require_cuda(disp, x)
+        N, Lf, Cc, H, W = x.shape
+        outs = [torch.empty(N, Cc, H, W, device=x.device, dtype=_F32) for _ in range(S)]
+        desc = L.make_vsl_desc(
+            target=None, target_stride=0, sources=[x[:, i] for i in cfg["source_ids"]],
+            source_strides=[x.stride(0)] * S, disparities=[disp], K_cm=cfg["K_cm"], invK_cm=cfg["invK_cm"],
+            rot=rot, trans=trans, pose_mode=0, invert=[0] * S, min_depth=cfg["min_depth"],
+            max_depth=cfg["max_depth"], smooth_weight=[0.0], loss_scale=1.0, shape=(N, Cc, H, W))
+        arr = (C.c_void_p * S)(*[o.data_ptr() for o in outs])
+        Context.get(x.device).call("md2_warp_fwd", C.byref(desc), arr)
+        ctx.save_for_backward(disp, x, *rot, *trans)
+        ctx.cfg = cfg
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cfg = ctx.cfg
+        S = cfg["S"]
+        disp, x, *rest = ctx.saved_tensors
+        rot, trans = rest[:S], rest[S:]
+        N, Lf, Cc, H, W = x.shape
+        gouts = [_f32c(g) if g is not None else torch.zeros(N, Cc, H, W, device=x.device, dtype=_F32) for g in gouts]
+        gd = torch.empty_like(disp)
+        gr = [torch.empty_like(r) for r in rot]
+        gt = [torch.empty_like(t) for t in trans]
+        gx = torch.zeros_like(x) if ctx.needs_input_grad[2] else None
+        desc = L.make_vsl_desc(
+            target=None, target_stride=0, sources=[x[:, i] for i in cfg["source_ids"]],
+            source_strides=[x.stride(0)] * S, disparities=[disp], K_cm=cfg["K_cm"], invK_cm=cfg["invK_cm"],
+            rot=rot, trans=trans, pose_mode=0, invert=[0] * S, min_depth=cfg["min_depth"],
+            max_depth=cfg["max_depth"], smooth_weight=[0.0], loss_scale=1.0, grad_disparity=[gd], grad_rot=gr,
+            grad_trans=gt, grad_source=[gx[:, i] for i in cfg["source_ids"]] if gx is not None else None,
+            shape=(N, Cc, H, W))
+        arr = (C.c_void_p * S)(*[g.data_ptr() for g in gouts])
+        Context.get(x.device).call("md2_warp_bwd", C.byref(desc), arr)
+        return (None, gd, gx, *[r.transpose(1, 2) for r in gr], *gt)
+
+
+def warp(disp, x, Ps, backprojections, projections, invKs, Ks, *, min_depth, max_depth, source_ids):
+    """The `warp` the reference calls but never defines (src/simple_depth.jl:30-32); body as in
+    src/training.jl:48-57: disparity -> depth -> backproject -> per (P, sid): project ->
+    grid_sample(border).  disp (N,1,H,W) [Julia (1,W,H,1) in slow_depth], x (N,L,C,H,W),
+    Ps = [(R (N,3,3), t (N,3)), ...].  Returns the list of warped images (N,C,H,W).
+    `backprojections` / `projections` are accepted for signature parity; the fused kernel
+    derives the pixel grid itself."""
+    S = len(source_ids)
+    cfg = dict(S=S, source_ids=list(source_ids), K_cm=_cm(_f32c(Ks.reshape(3, 3))),
+               invK_cm=_cm(_f32c(invKs.reshape(3, 3))), min_depth=float(min_depth), max_depth=float(max_depth))
+    N = x.shape[0]
+    disp = disp.reshape(N, 1, x.shape[-2], x.shape[-1])
+    Rs = [P[0] for P in Ps]
+    ts = [P[1].reshape(-1, 3) for P in Ps]
+    return list(_Warp.apply(cfg, disp, x, *Rs, *ts))
+
+
+def train_loss(model, x, auto_loss, cache: TrainCache, parameters: Params, do_visualization=False):
+    """Drop-in for src/training.jl:21-78.  `model(x, source_ids, target_id)` returns
+    (disparities, poses) exactly like the reference's Model (src/model.jl:8-20); everything
+    after it runs in the fused CUDA path.  Returns (loss, vis_disparity, vis_warped, vis_loss)."""
+    disparities, poses = model(x, cache.source_ids, cache.target_id)
+    out = view_synthesis_loss(
+        x, list(disparities), [p.rvec for p in poses], [p.tvec for p in poses], cache.K, cache.invK,
+        target_id=cache.target_id, source_ids=cache.source_ids, scales=cache.scales,
+        min_depth=parameters.min_depth, max_depth=parameters.max_depth,
+        disparity_smoothness=parameters.disparity_smoothness,
+        auto_loss=auto_loss if parameters.automasking else None, return_viz=do_visualization,
+        K_cm=cache.K_cm, invK_cm=cache.invK_cm)
+    if do_visualization:
+        loss, vis_warped, vis_loss = out
+        # the reference copies these to the host for logging (src/training.jl:34-37,71-74)
+        return loss, disparities[-1].detach().cpu(), [w.cpu() for w in vis_warped], vis_loss.cpu()
+    return out, None, None, None
+
+
+def simple_depth_loss(x, disp, poses, K, invK, *, target_id=1, source_ids=(0, 2), min_depth=0.1, max_depth=100.0):
+    """Objective of the triplet optimiser `slow_depth` (src/simple_depth.jl:25-41):
+    mean(prediction_loss(warp(...))) + smooth_loss(disp, target): one scale, un-normalised
+    smoothness with weight 1, in ONE fused kernel pass."""
+    return view_synthesis_loss(x, [disp], [p.rvec for p in poses], [p.tvec for p in poses], K, invK,
+                               target_id=target_id, source_ids=source_ids, min_depth=min_depth,
+                               max_depth=max_depth, normalize_disparity=False, smooth_weight=[1.0], loss_scale=1.0)

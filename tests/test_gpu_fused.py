@@ -1,0 +1,194 @@
+"""GPU parity of the fused view-synthesis loss (through the C ABI) against the float64 CPU
+oracle: strict on well-conditioned inputs, statistical on arbitrary / full-size inputs (see
+tests/util.py for why), plus size-independent properties at BASELINE.json's full sizes."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import monodepth2_jl_b200 as M
+from oracle import torch_oracle as O
+from util import (check_vsl, check_vsl_statistical, oracle_vsl, rel_l2, rel_max, well_conditioned_batch)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def run_cuda(x, disps, rv, tv, K, invK, *, automask=False, grad_x=True, **kw):
+    d = dev()
+    xg = x.to(d).requires_grad_(grad_x)
+    dg = [t.to(d).requires_grad_(True) for t in disps]
+    rg = [t.to(d).requires_grad_(True) for t in rv]
+    tg = [t.to(d).requires_grad_(True) for t in tv]
+    auto = M.automasking_loss(M.SSIM(), xg, xg[:, 1], (0, 2)) if automask else None
+    loss = M.view_synthesis_loss(xg, dg, rg, tg, K.to(d), invK.to(d), auto_loss=auto, **kw)
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(loss=loss.item(), gdisp=[t.grad.cpu() for t in dg], grvec=[t.grad.cpu() for t in rg],
+                gtvec=[t.grad.cpu() for t in tg], gx=xg.grad.cpu() if grad_x else None, auto=auto)
+
+
+@pytest.mark.parametrize("N,C,H,W,am", [(1, 1, 24, 40, False), (1, 3, 24, 40, True), (1, 3, 20, 37, True),
+                                        (1, 1, 17, 33, False)])
+def test_strict_on_well_conditioned_inputs(N, C, H, W, am):
+    (x, disps, rv, tv, K, invK), seed = well_conditioned_batch(N, C, H, W, am)
+    ref = oracle_vsl(x, disps, rv, tv, K, invK, automask=am)
+    out = run_cuda(x, disps, rv, tv, K, invK, automask=am)
+    if am:
+        assert torch.allclose(out["auto"].cpu().double(), ref["auto"], atol=2e-6)
+    check_vsl(out, ref, tag=f"{N},{C},{H},{W},{am},seed={seed}")
+
+
+@pytest.mark.parametrize("N,C,H,W,am", [(2, 1, 32, 64, False), (1, 3, 48, 80, True), (2, 3, 40, 100, True),
+                                        (3, 1, 64, 200, True), (2, 3, 128, 416, False)])
+def test_statistical_on_arbitrary_inputs(N, C, H, W, am):
+    x, disps, rv, tv = O.synthetic_batch(N, C, H, W, seed=3)
+    K, invK = O.make_K(W, H)
+    ref = oracle_vsl(x, disps, rv, tv, K, invK, automask=am)
+    out = run_cuda(x, disps, rv, tv, K, invK, automask=am)
+    check_vsl_statistical(out, ref, tag=f"{N},{C},{H},{W},{am}")
+
+
+def test_config2_readme_shape():
+    """BASELINE.json configs[1]: 416x128, batch 8, C=1, 4 scales, no automask"""
+    x, disps, rv, tv = O.synthetic_batch(8, 1, 128, 416, seed=42)
+    K, invK = O.make_K(416, 128)
+    ref = oracle_vsl(x, disps, rv, tv, K, invK)
+    out = run_cuda(x, disps, rv, tv, K, invK)
+    check_vsl_statistical(out, ref, tag="config2")
+
+
+def test_stress_poses():
+    x, disps, rv, tv = O.synthetic_batch(2, 3, 48, 96, seed=5, pose_sigma=0.1)
+    K, invK = O.make_K(96, 48)
+    ref = oracle_vsl(x, disps, rv, tv, K, invK, automask=True)
+    out = run_cuda(x, disps, rv, tv, K, invK, automask=True)
+    check_vsl_statistical(out, ref, tag="stress poses", pose_rtol=5e-3)
+
+
+def test_golden_vsl_small():
+    g = np.load(os.path.join(GOLD, "vsl_small.npz"))
+    x = torch.from_numpy(g["x"])
+    disps = [torch.from_numpy(g[f"disp{i}"]) for i in range(4)]
+    rv = [torch.from_numpy(g[f"rvec{s}"]) for s in range(2)]
+    tv = [torch.from_numpy(g[f"tvec{s}"]) for s in range(2)]
+    out = run_cuda(x, disps, rv, tv, torch.from_numpy(g["K"]), torch.from_numpy(g["invK"]), automask=True, grad_x=False)
+    ref = dict(loss=float(g["loss"]), gdisp=[torch.from_numpy(g[f"gdisp{i}"]) for i in range(4)],
+               grvec=[torch.from_numpy(g[f"grvec{s}"]) for s in range(2)],
+               gtvec=[torch.from_numpy(g[f"gtvec{s}"]) for s in range(2)])
+    assert torch.allclose(out["auto"].cpu(), torch.from_numpy(g["auto"]), atol=2e-6)
+    check_vsl_statistical(out, ref, tag="golden vsl_small")
+
+
+def test_golden_simple_depth_c1():
+    """config 1 (BASELINE.json configs[0]): the reference's res/image.png triplet"""
+    g = np.load(os.path.join(GOLD, "simple_depth_c1.npz"))
+    d = dev()
+    x = torch.from_numpy(g["frames"]).permute(0, 3, 1, 2).float().div(255.0).unsqueeze(0).contiguous().to(d)
+    W, H = 416, 128
+    K, invK = O.make_K(W, H, f=float(g["focal"]))
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    cases = [
+        (torch.full((1, 1, H, W), 0.5), [torch.tensor([[0.0, 0.0, 0.01]])] * 2, [torch.zeros(1, 3)] * 2, ""),
+        ((0.5 + 0.2 * torch.sin(xx / 37.0) * torch.cos(yy / 23.0)).reshape(1, 1, H, W).float(),
+         [torch.from_numpy(g["rvec2"][s]).float() for s in range(2)],
+         [torch.from_numpy(g["tvec2"][s]).float() for s in range(2)], "2"),
+    ]
+    for disp, rv, tv, sfx in cases:
+        disp = disp.to(d).requires_grad_(True)
+        poses = [M.Pose(r.clone().to(d).requires_grad_(True), t.clone().to(d).requires_grad_(True)) for r, t in zip(rv, tv)]
+        loss = M.simple_depth_loss(x, disp, poses, K.to(d), invK.to(d))
+        loss.backward()
+        assert abs(loss.item() - float(g["loss" + sfx])) <= 1e-5 * float(g["loss" + sfx])
+        for s in range(2):
+            assert rel_max(poses[s].rvec.grad, torch.from_numpy(g["grvec" + sfx][s])) < 2e-3
+            assert rel_max(poses[s].tvec.grad, torch.from_numpy(g["gtvec" + sfx][s])) < 2e-3
+        if sfx == "":
+            assert disp.grad.abs().max().item() < 1e-7   # t = 0: exactly zero in exact arithmetic
+        else:
+            gd, rd = disp.grad.cpu().double(), torch.from_numpy(g["gdisp2"]).double()
+            err = (gd - rd).abs() / rd.abs().max()
+            assert (err <= 1e-4).double().mean().item() >= 0.995
+
+
+def test_fwd_bwd_split_equals_fused_and_is_linear():
+    """separate forward / backward C-ABI calls reproduce the fused value-and-gradient call"""
+    d = dev()
+    N, Cc, H, W = 2, 3, 48, 96
+    x, disps, rv, tv = [t for t in O.synthetic_batch(N, Cc, H, W, seed=9)]
+    K, invK = O.make_K(W, H)
+    from monodepth2_jl_b200 import _lib as L
+    x = x.to(d)
+    disps = [t.to(d) for t in disps]
+    rv, tv = [t.to(d) for t in rv], [t.to(d) for t in tv]
+    K_cm, invK_cm = K.t().contiguous().to(d), invK.t().contiguous().to(d)
+    ctx = M.Context.get(d)
+
+    def call(mode, up=1.0, saved=None):
+        o = dict(loss=torch.zeros((), device=d), gd=[torch.zeros_like(t) for t in disps],
+                 gr=[torch.zeros_like(t) for t in rv], gt=[torch.zeros_like(t) for t in tv],
+                 gx=torch.zeros_like(x), saved=saved if saved is not None else torch.zeros(4, N, 4, device=d))
+        desc = L.make_vsl_desc(target=x[:, 1], target_stride=x.stride(0), sources=[x[:, 0], x[:, 2]],
+                               source_strides=[x.stride(0)] * 2, disparities=disps, K_cm=K_cm, invK_cm=invK_cm,
+                               rot=rv, trans=tv, pose_mode=1, invert=[1, 0], smooth_weight=[1e-3 * s for s in (0.125, 0.25, 0.5, 1.0)],
+                               loss_scale=0.25, loss=o["loss"], grad_disparity=o["gd"], grad_rot=o["gr"], grad_trans=o["gt"],
+                               grad_source=[o["gx"][:, 0], o["gx"][:, 2]], saved=o["saved"], shape=(N, Cc, H, W))
+        if mode == "fwd":
+            ctx.call("md2_view_synthesis_loss_fwd", C.byref(desc))
+        elif mode == "bwd":
+            ctx.call("md2_view_synthesis_loss_bwd", C.byref(desc), up)
+        else:
+            ctx.call("md2_view_synthesis_loss_fwdbwd", C.byref(desc), up)
+        torch.cuda.synchronize()
+        return o
+
+    fused = call("fwdbwd")
+    fwd = call("fwd")
+    bwd = call("bwd", 1.0, fwd["saved"])
+    half = call("bwd", 0.5, fwd["saved"])
+    assert abs(fwd["loss"].item() - fused["loss"].item()) <= 2e-6 * abs(fused["loss"].item())
+    for a, b, h in zip(bwd["gd"] + bwd["gr"] + bwd["gt"], fused["gd"] + fused["gr"] + fused["gt"],
+                       half["gd"] + half["gr"] + half["gt"]):
+        assert rel_max(a, b) < 2e-5
+        assert rel_max(2 * h, a) < 2e-5
+    assert rel_max(bwd["gx"], fused["gx"]) < 2e-5
+
+
+def test_identity_pose_properties_full_size():
+    """size-independent properties at BASELINE.json's full sizes: identical frames + zero pose
+    => warp is the identity, photometric error is 0, the warped output equals the source"""
+    d = dev()
+    for (N, Cc, H, W) in [(8, 1, 128, 416), (12, 3, 192, 640), (4, 3, 320, 1024)]:
+        g = torch.Generator().manual_seed(0)
+        img = torch.rand(N, 1, Cc, H, W, generator=g)
+        x = img.expand(N, 3, Cc, H, W).contiguous().to(d)
+        disp = (torch.rand(N, 1, H, W, generator=g) * 0.8 + 0.1).to(d)
+        K, invK = O.make_K(W, H)
+        rv = [torch.zeros(N, 3, device=d) for _ in range(2)]
+        tv = [torch.zeros(N, 3, device=d) for _ in range(2)]
+        loss, viz_w, viz_l = M.view_synthesis_loss(x, [disp], rv, tv, K.to(d), invK.to(d), smooth_weight=[0.0],
+                                                   loss_scale=1.0, return_viz=True)
+        for w in viz_w:
+            assert (w - x[:, 1]).abs().max().item() < 2e-3   # reference identity-warp bar (atol 1e-3)
+        assert viz_l.max().item() < 1e-2 and loss.item() < 1e-3
+        # determinism of everything but the atomics: loss is bit-stable
+        loss2 = M.view_synthesis_loss(x, [disp], rv, tv, K.to(d), invK.to(d), smooth_weight=[0.0], loss_scale=1.0)
+        assert loss.item() == loss2.item()
+
+
+def test_error_behaviour():
+    d = dev()
+    x = torch.rand(1, 3, 2, 16, 16, device=d)   # C = 2 is unsupported
+    disp = torch.rand(1, 1, 16, 16, device=d)
+    K, invK = O.make_K(16, 16)
+    with pytest.raises(M.Md2Error):
+        M.view_synthesis_loss(x, [disp], [torch.zeros(1, 3, device=d)] * 2, [torch.zeros(1, 3, device=d)] * 2,
+                              K.to(d), invK.to(d))
+    with pytest.raises(M.Md2Error):
+        M.SSIM()(torch.rand(1, 1, 4, 4), torch.rand(1, 1, 4, 4))   # CPU tensors: no fallback
