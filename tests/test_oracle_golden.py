@@ -83,8 +83,11 @@ def test_disparity_to_depth():  # test/runtests.jl:85-92
 
 def test_identity_warp():  # test/runtests.jl:94-122 (default :zeros padding)
     res, N = 16, 2
+    torch.manual_seed(1)
     image = torch.rand(N, 1, res, res, dtype=F64)
-    depth = torch.rand(N, res * res, dtype=F64)
+    # the reference draws depth in [0,1); depths below ~1e-4 make its own test fail through the
+    # 1e-7 in the perspective divide (src/utils.jl:97), so keep away from 0 here
+    depth = torch.rand(N, res * res, dtype=F64) * 0.9 + 0.1
     K = torch.tensor([[910.0, 0, res / 2], [0, 910.0, res / 2], [0, 0, 1]], dtype=F64)
     invK = torch.linalg.inv(K)
     R = O.so3_exp_map(torch.zeros(N, 3, dtype=F64))
