@@ -115,18 +115,20 @@ MD2_HD SsimWin ssim_window(float xc, float yc, float sx, float sy, float sxx, fl
     const float vx = fmaf(-dx, dx, sxx * r9);
     const float vy = fmaf(-dy, dy, syy * r9);
     const float vxy = fmaf(-dx, dy, sxy * r9);
-    const float A = fmaf(2.0f * mux, muy, SSIM_C1);
-    const float B = fmaf(2.0f, vxy, SSIM_C2);
-    const float Cc = fmaf(mux, mux, fmaf(muy, muy, SSIM_C1));
-    const float D = vx + vy + SSIM_C2;
-    const float rC = 1.0f / Cc, rD = 1.0f / D;
-    const float inv = rC * rD;
-    const float S = A * B * inv;
+    // A and Cc (B and D) are formed so that identical inputs give bit-identical numerator and
+    // denominator: ssim(x, x) is then exactly 0, as in the reference's own test.
+    const float A = 2.0f * mux * muy + SSIM_C1;
+    const float B = 2.0f * vxy + SSIM_C2;
+    const float Cc = (mux * mux + muy * muy) + SSIM_C1;
+    const float D = (vx + vy) + SSIM_C2;
+    const float S = (A * B) / (Cc * D);
     const float raw = (1.0f - S) * 0.5f;
     SsimWin o;
     o.s = fminf(fmaxf(raw, 0.0f), 1.0f);
     if (WITH_COEF) {
         const float k = 2.0f / 9.0f;
+        const float rC = 1.0f / Cc, rD = 1.0f / D;
+        const float inv = rC * rD;
         o.pass = (raw >= 0.0f && raw <= 1.0f) ? 1.0f : 0.0f;
         o.beta = -k * S * rD;
         o.gamma = k * A * inv;

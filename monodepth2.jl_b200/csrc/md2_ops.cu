@@ -298,10 +298,10 @@ __device__ __forceinline__ WinXY window_xy(const float* __restrict__ x, const fl
     const float dx = sx * r9, dy = sy * r9;
     const float mux = xc + dx, muy = yc + dy;
     const float vx = fmaf(-dx, dx, sxx * r9), vy = fmaf(-dy, dy, syy * r9), vxy = fmaf(-dx, dy, sxy * r9);
-    const float A = fmaf(2.0f * mux, muy, SSIM_C1), B = fmaf(2.0f, vxy, SSIM_C2);
-    const float Cc = fmaf(mux, mux, fmaf(muy, muy, SSIM_C1)), D = vx + vy + SSIM_C2;
+    const float A = 2.0f * mux * muy + SSIM_C1, B = 2.0f * vxy + SSIM_C2;
+    const float Cc = (mux * mux + muy * muy) + SSIM_C1, D = (vx + vy) + SSIM_C2;
+    const float S = (A * B) / (Cc * D);   // identical inputs: numerator == denominator bit for bit
     const float rC = 1.0f / Cc, rD = 1.0f / D, inv = rC * rD;
-    const float S = A * B * inv;
     const float raw = (1.0f - S) * 0.5f;
     WinXY o;
     o.s = fminf(fmaxf(raw, 0.f), 1.f);

@@ -114,3 +114,20 @@ def test_golden_vsl_small_pins_oracle():
     out = emul_vsl(x, disps, rv, tv, K, invK, mode=2, automask=torch.from_numpy(g["auto"]))
     out["loss"] = out["loss"].item()
     check_vsl_statistical(out, ref, tag="golden vsl_small")
+
+
+def test_closer_to_float64_than_float32_reference():
+    """the fused kernel's float32 result is at least as close to the float64 truth as the
+    reference's own op sequence evaluated in float32 (what its GPU path computes)"""
+    N, C, H, W = 3, 1, 64, 200
+    x, disps, rv, tv = O.synthetic_batch(N, C, H, W, seed=3)
+    K, invK = O.make_K(W, H)
+    ref = oracle_vsl(x, disps, rv, tv, K, invK, automask=True)
+    ref32 = oracle_vsl(x, disps, rv, tv, K, invK, automask=True, dtype=torch.float32)
+    out = emul_vsl(x, disps, rv, tv, K, invK, mode=2, automask=ref["auto"].float().contiguous())
+    assert abs(out["loss"].item() - ref["loss"]) <= abs(ref32["loss"] - ref["loss"]) + 1e-9
+    for l in range(4):
+        assert rel_l2(out["gdisp"][l], ref["gdisp"][l]) <= rel_l2(ref32["gdisp"][l], ref["gdisp"][l]) + 1e-6
+    for name in ("grvec", "gtvec"):
+        for s in range(2):
+            assert rel_max(out[name][s], ref[name][s]) <= rel_max(ref32[name][s], ref[name][s]) + 1e-6
