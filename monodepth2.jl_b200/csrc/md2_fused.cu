@@ -44,40 +44,8 @@ void* ws_get(md2_ctx* ctx, int slot, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------
-// pose preparation: [composeT] + pre-composition  A = K R K^-1, b = K t      (A3, A4, A6)
+// align-corners bilinear upsample (A17) and its adjoint as stand-alone operators
 // ------------------------------------------------------------------------------------------
-struct PoseArgs {
-    int S, N, mode;
-    const float* rot[MAX_S];
-    const float* trans[MAX_S];
-    int invert[MAX_S];
-    const float* K; const float* invK;
-    float* grot[MAX_S];
-    float* gtrans[MAX_S];
-};
-
-__global__ void pose_prep_kernel(PoseArgs a, float* __restrict__ pose_ab) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.S * a.N) return;
-    const int s = i / a.N, n = i % a.N;
-    double K[9], Ki[9], R[9], t[3];
-    load_cm3(a.K, K);
-    load_cm3(a.invK, Ki);
-    if (a.mode == 0) {
-        load_cm3(a.rot[s] + 9 * n, R);
-        for (int k = 0; k < 3; ++k) t[k] = a.trans[s][3 * n + k];
-    } else {
-        double r[3], tv[3];
-        for (int k = 0; k < 3; ++k) { r[k] = a.rot[s][3 * n + k]; tv[k] = a.trans[s][3 * n + k]; }
-        compose_T(r, tv, a.invert[s], R, t);
-    }
-    precompose(K, Ki, R, t, pose_ab + ((long long)s * a.N + n) * 12);
-}
-
-// ------------------------------------------------------------------------------------------
-// align-corners bilinear upsample of the low-resolution disparities (A17) and its adjoint
-// ------------------------------------------------------------------------------------------
-
 __global__ void upsample_kernel(const float* __restrict__ in, float* __restrict__ out, int w, int h,
                                 int W, int H, int CN) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,7 +68,6 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ gout, float* __res
     const int xi = (int)(i % w), yi = (int)((i / w) % h);
     const long long cn = i / ((long long)w * h);
     const float sx = up_scale(w, W), sy = up_scale(h, H);
-    // candidate full-res range whose taps can touch (xi, yi)
     int xlo = 0, xhi = W - 1, ylo = 0, yhi = H - 1;
     if (sx > 0.f) {
         xlo = max(0, (int)floorf((float)(xi - 1) / sx) - 1);
@@ -127,35 +94,6 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ gout, float* __res
         acc = fmaf(wy, row, acc);
     }
     gin[i] = acc;
-}
-
-// ------------------------------------------------------------------------------------------
-// smoothness / mean-disparity statistics pre-pass (needed before the fused backward because
-// d / mean(d) couples every pixel of an image)
-// ------------------------------------------------------------------------------------------
-struct StatsArgs {
-    int W, H, N, L;
-    const float* tgt; long long tgt_ns;
-    const float* disp[MAX_L];
-};
-
-template <int C>
-__global__ void __launch_bounds__(256) stats_kernel(StatsArgs a, float* __restrict__ partial) {
-    __shared__ float scratch[3 * 8];
-    const int z = blockIdx.y, scale = z / a.N, n = z % a.N;
-    const long long HW = (long long)a.W * a.H;
-    const float* d = a.disp[scale] + n * HW;
-    const float* t = a.tgt + n * a.tgt_ns;
-    float v[3] = {0.f, 0.f, 0.f};
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
-         i += (long long)gridDim.x * blockDim.x) {
-        stats_pixel<C>(d, t, i, a.W, a.H, v[0], v[1], v[2]);
-    }
-    block_sum<3>(v, scratch);
-    if (threadIdx.x == 0) {
-        float* o = partial + ((long long)z * gridDim.x + blockIdx.x) * NSTAT;
-        o[0] = 0.f; o[1] = v[0]; o[2] = v[1]; o[3] = v[2];
-    }
 }
 
 // out[g][k] = sum_b partial[g][b][k], fixed order (deterministic).  NP <= 32.
@@ -186,114 +124,222 @@ int launch_reduce_partials(md2_ctx* ctx, const float* partial, float* out0, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// the fused tile kernel
+// warp-level helpers
+// ------------------------------------------------------------------------------------------
+// Transpose-reduce: every lane passes 32 values; afterwards lane k holds the warp total of
+// value k.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_reduce_32(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// prep kernel (one launch before the fused kernel):
+//   blockIdx.x <  bpi : smoothness / mean-disparity statistics of image blockIdx.y for every
+//                       scale (needed before the backward because d / mean(d) couples all
+//                       pixels of an image); the last block of an image
+//                       reduces the per-block partials in a fixed order (deterministic)
+//   blockIdx.x == bpi : [composeT +] pose pre-composition of image blockIdx.y, and zero fill of
+//                       the low-resolution disparity gradients the fused kernel accumulates into
+// ------------------------------------------------------------------------------------------
+template <int C, int LMAX>
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ FusedParams p, int bpi, int do_stats,
+                                                   int do_zero, float* __restrict__ pose_ab,
+                                                   float* __restrict__ part, float* __restrict__ stats,
+                                                   unsigned int* __restrict__ counters) {
+    const int n = blockIdx.y;
+    if ((int)blockIdx.x == bpi) {
+        if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
+        if (do_zero) {
+            for (int l = 0; l < p.L; ++l) {
+                if (p.dw[l] == p.W && p.dh[l] == p.H) continue;
+                const int cnt = p.dw[l] * p.dh[l];
+                float* g = p.gdisp[l] + (long long)n * cnt;
+                for (int i = threadIdx.x; i < cnt; i += blockDim.x) g[i] = 0.f;
+            }
+        }
+        return;
+    }
+    if (!do_stats) return;
+    __shared__ float red[3 * LMAX * 8];
+    __shared__ bool last;
+    const int HW = p.W * p.H;
+    float v[3 * LMAX];
+#pragma unroll
+    for (int k = 0; k < 3 * LMAX; ++k) v[k] = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += bpi * blockDim.x) {
+        const int gx = i % p.W, gy = i / p.W;
+        const float* t = p.tgt + (long long)n * p.tgt_ns + i;
+        const bool hx = gx + 1 < p.W, hy = gy + 1 < p.H;
+        float wx = 0.f, wy = 0.f;
+        if (hx) {
+            float g = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + 1]);
+            wx = __expf(-g * (1.0f / C));
+        }
+        if (hy) {
+            float g = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + p.W]);
+            wy = __expf(-g * (1.0f / C));
+        }
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l >= p.L) break;
+            const int dw = p.dw[l], dh = p.dh[l];
+            const bool native = (dw == p.W && dh == p.H);
+            const float* dp = p.disp[l] + (long long)n * dw * dh;
+            const float usx = up_scale(dw, p.W), usy = up_scale(dh, p.H);
+            const float d = disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy);
+            v[3 * l + 2] += d;
+            if (hx) v[3 * l + 0] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx + 1, gy)) * wx;
+            if (hy) v[3 * l + 1] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy + 1)) * wy;
+        }
+    }
+    block_sum<3 * LMAX>(v, red);
+    if (threadIdx.x < 3 * LMAX) part[((long long)n * bpi + blockIdx.x) * (3 * LMAX) + threadIdx.x] = red[threadIdx.x * (blockDim.x >> 5)];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&counters[n], 1u) == (unsigned)(bpi - 1));
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if ((int)threadIdx.x < 3 * p.L) {
+        float s = 0.f;
+        for (int b = 0; b < bpi; ++b) s += __ldcg(part + ((long long)n * bpi + b) * (3 * LMAX) + threadIdx.x);
+        const int l = threadIdx.x / 3, k = threadIdx.x % 3;
+        stats[((long long)l * p.N + n) * NSTAT + 1 + k] = s;
+    }
+    if (threadIdx.x == 0) counters[n] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused tile kernel; the last block to finish reduces the partial sums and finalises the
+// loss and the pose gradients (fixed summation order => the loss is run-to-run deterministic)
 // ------------------------------------------------------------------------------------------
 template <int C, int S, bool BWD>
 __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ float sm[];
     using F = Fused<C, S, BWD>;
     const int z = blockIdx.z, scale = z / p.N, n = z % p.N;
-    const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+    const int tx0 = blockIdx.x * F::TW, ty0 = blockIdx.y * F::TH;
     const int tid = threadIdx.x;
+    const int tiles = gridDim.x * gridDim.y;
     FusedAcc<S> acc;
     acc.clear();
-    F::phase_load(p, sm, scale, n, tx0, ty0, tid, FUSED_THREADS);
+    F::phase_load(p, sm, scale, n, tx0, ty0, tid);
     __syncthreads();
-    F::phase_windows(p, sm, scale, n, tx0, ty0, tid, FUSED_THREADS, acc);
+    F::phase_windows(p, sm, scale, n, tx0, ty0, tid, acc);
     if (!BWD) {
-        F::phase_smooth_fwd(p, sm, tx0, ty0, tid, FUSED_THREADS, acc);
+        F::phase_smooth_fwd(p, sm, tx0, ty0, tid, acc);
     } else {
         __syncthreads();
-        F::phase_pixel_bwd(p, sm, scale, n, tx0, ty0, tid, FUSED_THREADS, acc);
+        F::phase_pixel_bwd(p, sm, scale, n, tx0, ty0, tid, acc);
+        if (p.dw[scale] != p.W || p.dh[scale] != p.H) {
+            __syncthreads();
+            F::phase_down_a(p, sm, tid);
+            __syncthreads();
+            F::phase_down_b(p, sm, scale, n, tid);
+        }
     }
     __syncthreads();   // shared memory is re-used as reduction scratch from here on
     constexpr int NP = F::NPART;
-    float v[NP];
-    v[0] = acc.warp_sum; v[1] = acc.sx; v[2] = acc.sy; v[3] = acc.dsum;
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int k = 0; k < 12; ++k) v[NSTAT + 12 * s + k] = acc.pose[s][k];
     constexpr int NW = FUSED_THREADS / 32;
-    const int lane = tid & 31, wid = tid >> 5;
+    {
+        float v[32];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        if (!BWD && k >= NSTAT) break;
-        const float r = warp_sum(v[k]);
-        if (lane == 0) sm[k * NW + wid] = r;
+        for (int k = 0; k < 32; ++k) v[k] = 0.f;
+        v[0] = acc.warp_sum; v[1] = acc.sx; v[2] = acc.sy; v[3] = acc.dsum;
+        if (BWD) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int k = 0; k < 12; ++k) v[NSTAT + 12 * s + k] = acc.pose[s][k];
+        }
+        const float tot = warp_reduce_32(v);
+        sm[(tid >> 5) * 32 + (tid & 31)] = tot;
     }
     __syncthreads();
+    const long long blk = ((long long)z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (tid < NP) {
         float r = 0.f;
-        if (BWD || tid < NSTAT)
-            for (int w = 0; w < NW; ++w) r += sm[tid * NW + w];
-        const long long blk = ((long long)z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) r += sm[w * 32 + tid];
         p.partial[blk * NP + tid] = r;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// finalize: loss scalar, saved statistics, pose gradients
-// ------------------------------------------------------------------------------------------
-struct FinalArgs {
-    int W, H, N, L, S, NP;
-    int mode;              // 0 fwd, 1 bwd, 2 fwdbwd
-    const float* sums;     // (L*N, NP) from the fused kernel
-    float* stats;          // (L*N, NSTAT)
-    float* saved;          // nullable copy of stats for a later bwd
-    float* loss;           // nullable
-    float smooth_w[MAX_L];
-    float loss_scale;
-    int normalize_disp;
-    PoseArgs pose;
-};
-
-__global__ void __launch_bounds__(128) finalize_kernel(FinalArgs a) {
-    const int LN = a.L * a.N;
-    if (a.mode != 1) {
-        for (int z = threadIdx.x; z < LN; z += blockDim.x) {
-            float* st = a.stats + (long long)z * NSTAT;
-            const float* su = a.sums + (long long)z * a.NP;
-            st[0] = su[0];
-            if (a.mode == 0) { st[1] = su[1]; st[2] = su[2]; st[3] = su[3]; }
-            if (a.saved)
-                for (int k = 0; k < NSTAT; ++k) a.saved[(long long)z * NSTAT + k] = st[k];
+    // ---- last-block reductions ----
+    __shared__ int flag;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) flag = (atomicAdd(&p.counters[z], 1u) == (unsigned)(tiles - 1)) ? 1 : 0;
+    __syncthreads();
+    if (!flag) return;
+    __threadfence();
+    {   // this block finished image z last: reduce its tiles in a fixed order
+        const int k = tid & 31, chunk = tid >> 5;
+        float s = 0.f;
+        if (k < NP)
+            for (int b = chunk; b < tiles; b += NW) s += __ldcg(p.partial + ((long long)z * tiles + b) * NP + k);
+        sm[chunk * 32 + k] = s;
+        __syncthreads();
+        if (tid < NP) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += sm[w * 32 + tid];
+            p.sums[(long long)z * NP + tid] = t;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    const int LN = p.L * p.N;
+    if (tid == 0) {
+        p.counters[z] = 0u;
+        flag = (atomicAdd(&p.counters[LN], 1u) == (unsigned)(LN - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!flag) return;
+    __threadfence();
+    // ---- the very last block: loss, saved statistics, pose gradients ----
+    if (p.mode != 1) {
+        for (int zz = tid; zz < LN; zz += FUSED_THREADS) {
+            float* st = p.stats_out + (long long)zz * NSTAT;
+            st[0] = __ldcg(p.sums + (long long)zz * NP);
+            if (p.mode == 0) {
+                st[1] = __ldcg(p.sums + (long long)zz * NP + 1);
+                st[2] = __ldcg(p.sums + (long long)zz * NP + 2);
+                st[3] = __ldcg(p.sums + (long long)zz * NP + 3);
+            }
+            if (p.saved && p.saved != p.stats_out)
+                for (int k = 0; k < NSTAT; ++k) p.saved[(long long)zz * NSTAT + k] = st[k];
         }
         __syncthreads();
-        if (threadIdx.x == 0 && a.loss)
-            *a.loss = loss_from_stats(a.stats, a.W, a.H, a.N, a.L, a.smooth_w, a.loss_scale, a.normalize_disp);
+        if (tid == 0 && p.loss)
+            *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
     }
-    if (a.mode != 0) {
-        double K[9], Ki[9];
-        load_cm3(a.pose.K, K);
-        load_cm3(a.pose.invK, Ki);
-        for (int i = threadIdx.x; i < a.S * a.N; i += blockDim.x) {
-            const int s = i / a.N, n = i % a.N;
+    if (BWD) {
+        for (int i = tid; i < S * p.N; i += FUSED_THREADS) {
+            const int s = i / p.N, nn = i % p.N;
             double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
-            for (int l = 0; l < a.L; ++l) {
-                const float* su = a.sums + ((long long)l * a.N + n) * a.NP + NSTAT + 12 * s;
-                for (int k = 0; k < 9; ++k) G[k] += su[k];
-                for (int k = 0; k < 3; ++k) h[k] += su[9 + k];
+            for (int l = 0; l < p.L; ++l) {
+                const float* su = p.sums + ((long long)l * p.N + nn) * NP + NSTAT + 12 * s;
+                for (int k = 0; k < 9; ++k) G[k] += __ldcg(su + k);
+                for (int k = 0; k < 3; ++k) h[k] += __ldcg(su + 9 + k);
             }
-            double Rub[9], tub[3];
-            precompose_bwd(K, Ki, G, h, Rub, tub);
-            if (a.pose.mode == 0) {
-                if (a.pose.grot[s])
-                    for (int r = 0; r < 3; ++r)
-                        for (int c = 0; c < 3; ++c) a.pose.grot[s][9 * n + 3 * c + r] = (float)Rub[3 * r + c];
-                if (a.pose.gtrans[s])
-                    for (int k = 0; k < 3; ++k) a.pose.gtrans[s][3 * n + k] = (float)tub[k];
-            } else {
-                double r[3], tv[3], rb[3], tb[3];
-                for (int k = 0; k < 3; ++k) { r[k] = a.pose.rot[s][3 * n + k]; tv[k] = a.pose.trans[s][3 * n + k]; }
-                compose_T_bwd(r, tv, a.pose.invert[s], Rub, tub, rb, tb);
-                if (a.pose.grot[s])
-                    for (int k = 0; k < 3; ++k) a.pose.grot[s][3 * n + k] = (float)rb[k];
-                if (a.pose.gtrans[s])
-                    for (int k = 0; k < 3; ++k) a.pose.gtrans[s][3 * n + k] = (float)tb[k];
-            }
+            finalize_pose(p.pose, s, nn, G, h);
         }
     }
+    if (tid == 0) p.counters[LN] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -308,7 +354,7 @@ static int launch_fused(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
         MD2_CHECK(cudaFuncSetAttribute(fused_kernel<C, S, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid(cdiv(p.W, TILE_W), cdiv(p.H, TILE_H), p.L * p.N);
+    dim3 grid(cdiv(p.W, F::TW), cdiv(p.H, F::TH), p.L * p.N);
     fused_kernel<C, S, BWD><<<grid, FUSED_THREADS, smem, st>>>(p);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
@@ -323,9 +369,15 @@ static int dispatch_fused(md2_ctx* ctx, int C, int S, const FusedParams& p, cuda
     return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
 }
 
+template <bool BWD>
+static int tiles_of(int C, int W, int H) {
+    const int tw = BWD ? 30 : 32, th = (C == 1) ? 32 : 16;
+    return cdiv(W, tw) * cdiv(H, th);
+}
+
 static int check_desc(const md2_vsl_desc* d, bool need_loss_inputs) {
     MD2_REQUIRE(d != nullptr, "null descriptor");
-    MD2_REQUIRE(d->W >= 2 && d->H >= 2, "W and H must be >= 2 (reflect padding)");
+    MD2_REQUIRE(d->W >= 2 && d->H >= 2 && d->W <= 65535 && d->H <= 32767, "W, H must be in 2..65535 / 2..32767");
     MD2_REQUIRE(d->N >= 1, "N must be >= 1");
     MD2_REQUIRE(d->C == 1 || d->C == 3, "C must be 1 or 3");
     MD2_REQUIRE(d->S >= 1 && d->S <= MAX_S, "S must be 1 or 2");
@@ -340,35 +392,33 @@ static int check_desc(const md2_vsl_desc* d, bool need_loss_inputs) {
         MD2_REQUIRE(d->target != nullptr, "null target image");
         for (int l = 0; l < d->L; ++l) {
             MD2_REQUIRE(d->disparity[l] != nullptr, "null disparity");
-            MD2_REQUIRE(d->disp_w[l] >= 2 && d->disp_h[l] >= 2 && d->disp_w[l] <= d->W && d->disp_h[l] <= d->H,
-                        "bad disparity size");
+            const bool native = d->disp_w[l] == d->W && d->disp_h[l] == d->H;
+            MD2_REQUIRE(native || (d->disp_w[l] >= 2 && d->disp_h[l] >= 2 && 2 * d->disp_w[l] <= d->W + 1 &&
+                                   2 * d->disp_h[l] <= d->H + 1),
+                        "a disparity must be full-resolution or at most half-resolution (decoder scales 1/2, 1/4, ...)");
         }
     }
     return 0;
 }
 
-int fill_pose_args(const md2_vsl_desc* d, PoseArgs& pa) {
-    pa.S = d->S; pa.N = d->N; pa.mode = d->pose_mode;
-    pa.K = d->K; pa.invK = d->invK;
+static void fill_pose_io(const md2_vsl_desc* d, PoseIO& io) {
+    io.mode = d->pose_mode;
+    io.K = d->K; io.invK = d->invK;
     for (int s = 0; s < MAX_S; ++s) {
-        pa.rot[s] = s < d->S ? d->rot[s] : nullptr;
-        pa.trans[s] = s < d->S ? d->trans[s] : nullptr;
-        pa.invert[s] = s < d->S ? d->invert[s] : 0;
-        pa.grot[s] = s < d->S ? d->grad_rot[s] : nullptr;
-        pa.gtrans[s] = s < d->S ? d->grad_trans[s] : nullptr;
+        io.rot[s] = s < d->S ? d->rot[s] : nullptr;
+        io.trans[s] = s < d->S ? d->trans[s] : nullptr;
+        io.invert[s] = s < d->S ? d->invert[s] : 0;
+        io.grot[s] = s < d->S ? d->grad_rot[s] : nullptr;
+        io.gtrans[s] = s < d->S ? d->grad_trans[s] : nullptr;
     }
-    return 0;
 }
 
-int prepare_pose(md2_ctx* ctx, const md2_vsl_desc* d, float** pose_ab, cudaStream_t st) {
-    float* ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * d->S * d->N);
-    if (!ab) return 1;
-    PoseArgs pa;
-    fill_pose_args(d, pa);
-    pose_prep_kernel<<<cdiv(d->S * d->N, 64), 64, 0, st>>>(pa, ab);
-    MD2_LAUNCH_CHECK(ctx);
-    *pose_ab = ab;
-    return 0;
+static unsigned int* get_counters(md2_ctx* ctx, int count, cudaStream_t st) {
+    Workspace& w = ctx->ws[MD2_WS_POSEIN];
+    const bool fresh = !(w.ptr && w.bytes >= sizeof(unsigned int) * count);
+    unsigned int* c = (unsigned int*)ws_get(ctx, MD2_WS_POSEIN, sizeof(unsigned int) * count);
+    if (c && fresh) cudaMemsetAsync(c, 0, ctx->ws[MD2_WS_POSEIN].bytes, st);   // kernels leave them zero
+    return c;
 }
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FWDBWD = 2 };
@@ -377,12 +427,11 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     if (check_desc(d, true)) return 1;
     MD2_CHECK(cudaSetDevice(ctx->device));
     const int W = d->W, H = d->H, N = d->N, L = d->L, S = d->S, C = d->C;
-    const long long HW = (long long)W * H;
     const bool bwd = mode != MODE_FWD;
 
     FusedParams p;
     memset(&p, 0, sizeof(p));
-    p.W = W; p.H = H; p.N = N; p.L = L;
+    p.W = W; p.H = H; p.N = N; p.L = L; p.S = S;
     p.tgt = d->target; p.tgt_ns = d->target_image_stride;
     for (int s = 0; s < S; ++s) {
         p.src[s] = d->source[s]; p.src_ns[s] = d->source_image_stride[s];
@@ -391,71 +440,50 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     }
     p.viz_loss = d->viz_loss;
     p.automask = d->automask;
-    p.depth_a = (float)(1.0 / d->min_depth - 1.0 / d->max_depth);
     {   // the reference rounds min_disp and max_disp to T first (src/utils.jl:176-178)
         const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
         p.depth_a = maxd - mind; p.depth_b = mind;
     }
-    for (int l = 0; l < L; ++l) p.smooth_w[l] = d->smooth_weight[l];
+    bool any_low = false;
+    for (int l = 0; l < L; ++l) {
+        p.smooth_w[l] = d->smooth_weight[l];
+        p.disp[l] = d->disparity[l]; p.dw[l] = d->disp_w[l]; p.dh[l] = d->disp_h[l];
+        p.gdisp[l] = bwd ? d->grad_disparity[l] : nullptr;
+        if (bwd) MD2_REQUIRE(d->grad_disparity[l] != nullptr, "null grad_disparity");
+        any_low = any_low || d->disp_w[l] != W || d->disp_h[l] != H;
+    }
     p.loss_scale = d->loss_scale;
     p.gloss = gloss;
     p.normalize_disp = d->normalize_disparity;
+    p.mode = mode;
+    fill_pose_io(d, p.pose);
 
-    float* pose_ab = nullptr;
-    if (prepare_pose(ctx, d, &pose_ab, st)) return 1;
-    p.pose_ab = pose_ab;
-
-    // full-resolution disparities (A17: upsample_bilinear when the decoder scale is smaller)
-    int n_up = 0;
-    for (int l = 0; l < L; ++l) n_up += (d->disp_w[l] != W || d->disp_h[l] != H);
-    float* up = nullptr; float* gup = nullptr;
-    if (n_up) {
-        up = (float*)ws_get(ctx, MD2_WS_DISP, sizeof(float) * n_up * N * HW);
-        if (!up) return 1;
-        if (bwd) {
-            gup = (float*)ws_get(ctx, MD2_WS_GDISP, sizeof(float) * n_up * N * HW);
-            if (!gup) return 1;
-        }
-    }
-    for (int l = 0, k = 0; l < L; ++l) {
-        if (d->disp_w[l] != W || d->disp_h[l] != H) {
-            float* o = up + (long long)k * N * HW;
-            upsample_kernel<<<cdiv(N * HW, 256), 256, 0, st>>>(d->disparity[l], o, d->disp_w[l], d->disp_h[l], W, H, N);
-            MD2_LAUNCH_CHECK(ctx);
-            p.disp[l] = o;
-            p.gdisp[l] = bwd ? gup + (long long)k * N * HW : nullptr;
-            ++k;
-        } else {
-            p.disp[l] = d->disparity[l];
-            p.gdisp[l] = bwd ? d->grad_disparity[l] : nullptr;
-        }
-        if (bwd) MD2_REQUIRE(d->grad_disparity[l] != nullptr, "null grad_disparity");
-    }
-
-    const int tiles = cdiv(W, TILE_W) * cdiv(H, TILE_H);
+    const int tiles = bwd ? tiles_of<true>(C, W, H) : tiles_of<false>(C, W, H);
     const int NP = NSTAT + 12 * S;
+    const int bpi = max(1, min(32, cdiv((long long)W * H, 4096)));
+    const int LMAX = L == 1 ? 1 : (L <= 4 ? 4 : 8);
+    float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
     float* sums = (float*)ws_get(ctx, MD2_WS_SUMS, sizeof(float) * (size_t)L * N * NP);
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
-    if (!partial || !sums || !stats) return 1;
-    p.partial = partial;
+    float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)bpi * N * 3 * LMAX);
+    unsigned int* counters = get_counters(ctx, L * N + 1 + N, st);
+    if (!pose_ab || !partial || !sums || !stats || !part2 || !counters) return 1;
+    p.pose_ab = pose_ab; p.partial = partial; p.sums = sums; p.counters = counters;
+    p.stats = stats; p.stats_out = stats; p.saved = (mode == MODE_BWD) ? nullptr : d->saved;
+    if (mode == MODE_BWD && d->saved) p.stats = d->saved;   // else the ctx holds the last forward's statistics
+    p.loss = (mode == MODE_BWD) ? nullptr : d->loss;
 
-    if (mode == MODE_BWD) {
-        if (d->saved) stats = d->saved;   // else: the ctx still holds the last forward's statistics
-    } else if (mode == MODE_FWDBWD) {
-        StatsArgs sa;
-        sa.W = W; sa.H = H; sa.N = N; sa.L = L; sa.tgt = d->target; sa.tgt_ns = d->target_image_stride;
-        for (int l = 0; l < MAX_L; ++l) sa.disp[l] = p.disp[l];
-        const int bpi = max(1, min(64, cdiv(HW, 2048)));
-        float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)bpi * L * N * NSTAT);
-        if (!part2) return 1;
-        dim3 g(bpi, L * N);
-        if (C == 1) stats_kernel<1><<<g, 256, 0, st>>>(sa, part2);
-        else stats_kernel<3><<<g, 256, 0, st>>>(sa, part2);
+    {   // prep: poses (+ zero fill of low-res gradients, + statistics pre-pass for the fused fwd+bwd)
+        const int do_stats = mode == MODE_FWDBWD, do_zero = bwd && any_low;
+        dim3 g(bpi + 1, N);
+        unsigned int* pc = counters + L * N + 1;
+#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 256, 0, st>>>(p, bpi, do_stats, do_zero, pose_ab, part2, stats, pc)
+        if (C == 1) { if (LMAX == 1) MD2_PREP(1, 1); else if (LMAX == 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
+        else        { if (LMAX == 1) MD2_PREP(3, 1); else if (LMAX == 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
+#undef MD2_PREP
         MD2_LAUNCH_CHECK(ctx);
-        if (launch_reduce_partials(ctx, part2, stats, NSTAT, nullptr, L * N, bpi, NSTAT, st)) return 1;
     }
-    p.stats = stats;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {
@@ -473,31 +501,6 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     if (bwd) { if (dispatch_fused<true>(ctx, C, S, p, st)) return 1; }
     else     { if (dispatch_fused<false>(ctx, C, S, p, st)) return 1; }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
-    if (launch_reduce_partials(ctx, partial, sums, NP, nullptr, L * N, tiles, NP, st)) return 1;
-
-    FinalArgs fa;
-    memset(&fa, 0, sizeof(fa));
-    fa.W = W; fa.H = H; fa.N = N; fa.L = L; fa.S = S; fa.NP = NP; fa.mode = mode;
-    fa.sums = sums; fa.stats = stats; fa.saved = (mode == MODE_BWD) ? nullptr : d->saved;
-    if (fa.saved == stats) fa.saved = nullptr;
-    fa.loss = d->loss;
-    for (int l = 0; l < L; ++l) fa.smooth_w[l] = d->smooth_weight[l];
-    fa.loss_scale = d->loss_scale; fa.normalize_disp = d->normalize_disparity;
-    fill_pose_args(d, fa.pose);
-    finalize_kernel<<<1, 128, 0, st>>>(fa);
-    MD2_LAUNCH_CHECK(ctx);
-
-    if (bwd) {
-        for (int l = 0, k = 0; l < L; ++l) {
-            if (d->disp_w[l] != W || d->disp_h[l] != H) {
-                const long long cnt = (long long)d->disp_w[l] * d->disp_h[l] * N;
-                upsample_bwd_kernel<<<cdiv(cnt, 128), 128, 0, st>>>(gup + (long long)k * N * HW, d->grad_disparity[l],
-                                                                    d->disp_w[l], d->disp_h[l], W, H, N);
-                MD2_LAUNCH_CHECK(ctx);
-                ++k;
-            }
-        }
-    }
     return 0;
 }
 
@@ -510,8 +513,26 @@ struct WarpIO {
     const float* gout[MAX_S];   // bwd
 };
 
+__global__ void pose_prep_kernel(PoseIO io, int S, int N, float* __restrict__ pose_ab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * N) return;
+    prepare_pose_one(io, i / N, i % N, pose_ab + (long long)i * 12);
+}
+
+__global__ void pose_final_kernel(PoseIO io, int S, int N, int NP, const float* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * N) return;
+    const int s = i / N, n = i % N;
+    double G[9], h[3];
+    const float* su = sums + (long long)n * NP + NSTAT + 12 * s;
+    for (int k = 0; k < 9; ++k) G[k] = su[k];
+    for (int k = 0; k < 3; ++k) h[k] = su[9 + k];
+    finalize_pose(io, s, n, G, h);
+}
+
 template <int C, int S>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const __grid_constant__ FusedParams p, WarpIO io) {
+    using F = Fused<C, S, false>;
     const long long HW = (long long)p.W * p.H;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= HW * p.N) return;
@@ -519,16 +540,17 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const __grid_constant__ F
     const float d = p.disp[0][i];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        float val[C]; Taps tp; Proj pr; float z;
-        Fused<C, S, false>::template warp_pixel<false>(p, n, s, gx, gy, d, p.pose_ab + ((long long)s * p.N + n) * 12,
-                                                       val, nullptr, nullptr, tp, pr, z);
+        typename F::Warped w; Taps tp; Proj pr; float z;
+        F::project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, d, pr, tp, z);
+        F::template gather<false>(p, n, s, tp, w);
 #pragma unroll
-        for (int c = 0; c < C; ++c) io.out[s][((long long)n * C + c) * HW + pix] = val[c];
+        for (int c = 0; c < C; ++c) io.out[s][((long long)n * C + c) * HW + pix] = w.val[c];
     }
 }
 
 template <int C, int S>
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const __grid_constant__ FusedParams p, WarpIO io) {
+    using F = Fused<C, S, true>;
     __shared__ float scratch[(NSTAT + 12 * S) * 8];
     const long long HW = (long long)p.W * p.H;
     const int n = blockIdx.y;
@@ -542,16 +564,16 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const __grid_constant__ F
         float dbar_z = 0.f, zz = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            float val[C], dix[C], diy[C], ibar[C]; Taps tp; Proj pr; float z;
-            Fused<C, S, true>::template warp_pixel<true>(p, n, s, gx, gy, d, p.pose_ab + ((long long)s * p.N + n) * 12,
-                                                         val, dix, diy, tp, pr, z);
+            typename F::Warped w; float ibar[C]; Taps tp; Proj pr; float z;
+            F::project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, d, pr, tp, z);
+            F::template gather<true>(p, n, s, tp, w);
             zz = z;
             float du = 0.f, dv = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 ibar[c] = io.gout[s][((long long)n * C + c) * HW + pix];
-                du = fmaf(ibar[c], dix[c], du);
-                dv = fmaf(ibar[c], diy[c], dv);
+                du = fmaf(ibar[c], w.dix[c], du);
+                dv = fmaf(ibar[c], w.diy[c], dv);
             }
             du *= tp.mx; dv *= tp.my;
             if (p.gsrc[s]) {
@@ -595,7 +617,7 @@ static int run_warp(md2_ctx* ctx, const md2_vsl_desc* d, float* const* out, cons
     MD2_REQUIRE(d->disp_w[0] == W && d->disp_h[0] == H, "warp needs a full-resolution disparity");
     FusedParams p;
     memset(&p, 0, sizeof(p));
-    p.W = W; p.H = H; p.N = N; p.L = 1;
+    p.W = W; p.H = H; p.N = N; p.L = 1; p.S = S;
     WarpIO io;
     memset(&io, 0, sizeof(io));
     for (int s = 0; s < S; ++s) {
@@ -606,9 +628,12 @@ static int run_warp(md2_ctx* ctx, const md2_vsl_desc* d, float* const* out, cons
     }
     const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
     p.depth_a = maxd - mind; p.depth_b = mind;
-    p.disp[0] = d->disparity[0];
-    float* pose_ab = nullptr;
-    if (prepare_pose(ctx, d, &pose_ab, st)) return 1;
+    p.disp[0] = d->disparity[0]; p.dw[0] = W; p.dh[0] = H;
+    fill_pose_io(d, p.pose);
+    float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
+    if (!pose_ab) return 1;
+    pose_prep_kernel<<<cdiv(S * N, 64), 64, 0, st>>>(p.pose, S, N, pose_ab);
+    MD2_LAUNCH_CHECK(ctx);
     p.pose_ab = pose_ab;
     if (!bwd) {
         const int g = cdiv(HW * N, 256);
@@ -634,12 +659,7 @@ static int run_warp(md2_ctx* ctx, const md2_vsl_desc* d, float* const* out, cons
     else warp_bwd_kernel<3, 2><<<g, 256, 0, st>>>(p, io);
     MD2_LAUNCH_CHECK(ctx);
     if (launch_reduce_partials(ctx, partial, sums, NP, nullptr, N, bpi, NP, st)) return 1;
-    FinalArgs fa;
-    memset(&fa, 0, sizeof(fa));
-    fa.W = W; fa.H = H; fa.N = N; fa.L = 1; fa.S = S; fa.NP = NP; fa.mode = MODE_BWD;
-    fa.sums = sums;
-    fill_pose_args(d, fa.pose);
-    finalize_kernel<<<1, 128, 0, st>>>(fa);
+    pose_final_kernel<<<cdiv(S * N, 64), 64, 0, st>>>(p.pose, S, N, NP, sums);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
