@@ -460,7 +460,7 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
 
     const int tiles = bwd ? tiles_of<true>(C, W, H) : tiles_of<false>(C, W, H);
     const int NP = NSTAT + 12 * S;
-    const int bpi = max(1, min(32, cdiv((long long)W * H, 4096)));
+    const int bpi = max(1, min(256, cdiv((long long)W * H, 512)));
     const int LMAX = L == 1 ? 1 : (L <= 4 ? 4 : 8);
     float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
@@ -540,8 +540,9 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const __grid_constant__ F
     const float d = p.disp[0][i];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        typename F::Warped w; Taps tp; Proj pr; float z;
-        F::project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, d, pr, tp, z);
+        typename F::Warped w; Taps tp; Proj pr;
+        const float z = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
+        F::project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, z, pr, tp);
         F::template gather<false>(p, n, s, tp, w);
 #pragma unroll
         for (int c = 0; c < C; ++c) io.out[s][((long long)n * C + c) * HW + pix] = w.val[c];
@@ -564,8 +565,9 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const __grid_constant__ F
         float dbar_z = 0.f, zz = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            typename F::Warped w; float ibar[C]; Taps tp; Proj pr; float z;
-            F::project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, d, pr, tp, z);
+            typename F::Warped w; float ibar[C]; Taps tp; Proj pr;
+            const float z = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
+            F::project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, z, pr, tp);
             F::template gather<true>(p, n, s, tp, w);
             zz = z;
             float du = 0.f, dv = 0.f;

@@ -84,7 +84,12 @@ struct FusedAcc {              // per-thread accumulators, block-reduced at the 
 
 #if defined(__CUDA_ARCH__)
 #define MD2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
-#define MD2_RCP_FAST(x) __fdividef(1.0f, (x))
+__device__ __forceinline__ float md2_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define MD2_RCP_FAST(x) md2_rcp_approx(x)
 #define MD2_EXP(x) __expf(x)
 #else
 #define MD2_ATOMIC_ADD(p, v) (*(p) += (v))
@@ -95,14 +100,14 @@ struct FusedAcc {              // per-thread accumulators, block-reduced at the 
 // reciprocal for the geometry (depth, perspective divide): approx + one Newton step, <= 1 ulp
 MD2_HD float rcp_acc(float x) {
 #if defined(__CUDA_ARCH__)
-    float r = __fdividef(1.0f, x);
+    const float r = md2_rcp_approx(x);
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 #else
     return 1.0f / x;
 #endif
 }
 
-MD2_HD float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+MD2_HD float sgnf(float v) { return (float)(v > 0.f) - (float)(v < 0.f); }
 
 // disparity of scale `l` at full-resolution pixel (gx,gy): direct read or on-the-fly
 // align-corners bilinear upsample (A17)
@@ -176,9 +181,8 @@ struct Fused {
     };
 
     // geometry of one pixel for source s (pose row `ab`)
-    static MD2_HD void project_pixel(const FusedParams& p, const float* __restrict__ ab, int gx, int gy,
-                                     float d, Proj& pr, Taps& tp, float& z) {
-        z = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
+    static MD2_HD void project_pixel(const FusedParams& p, const float* ab, int gx, int gy,
+                                     float z, Proj& pr, Taps& tp) {
         const float px = (float)(gx + 1), py = (float)(gy + 1);
         pr.ap[0] = fmaf(ab[0], px, fmaf(ab[1], py, ab[2]));
         pr.ap[1] = fmaf(ab[3], px, fmaf(ab[4], py, ab[5]));
@@ -218,6 +222,11 @@ struct Fused {
         const bool native = (dw == p.W && dh == p.H);
         const float* dp = p.disp[scale] + (long long)n * dw * dh;
         const float usx = up_scale(dw, p.W), usy = up_scale(dh, p.H);
+        float ab[S][12];   // pose rows in registers for the whole loop
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ab[s][k] = p.pose_ab[((long long)s * p.N + n) * 12 + k];
         for (int i = tid; i < RN; i += FUSED_THREADS) {
             const int lx = i % RW, ly = i / RW;
             int gx = tx0 - HALO + lx, gy = ty0 - HALO + ly;
@@ -230,6 +239,7 @@ struct Fused {
             float d = 0.f;
             if (ok) d = disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy);
             sm[OFF_DISP + i] = d;
+            const float z = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
 #pragma unroll
             for (int c = 0; c < C; ++c) sm[OFF_TGT + c * RN + i] = ok ? tg[c * HW + gy * p.W + gx] : 0.f;
             const bool in_tile = BWD && lx >= HALO && lx < HALO + TW && ly >= HALO && ly < HALO + TH;
@@ -240,8 +250,8 @@ struct Fused {
 #pragma unroll
                 for (int c = 0; c < C; ++c) { w.val[c] = 0.f; w.dix[c] = 0.f; w.diy[c] = 0.f; }
                 if (ok) {
-                    Taps tp; Proj pr; float z;
-                    project_pixel(p, p.pose_ab + ((long long)s * p.N + n) * 12, gx, gy, d, pr, tp, z);
+                    Taps tp; Proj pr;
+                    project_pixel(p, ab[s], gx, gy, z, pr, tp);
                     gather<BWD>(p, n, s, tp, w);
                 }
 #pragma unroll
@@ -444,11 +454,12 @@ struct Fused {
     // emit the source-image gradient of one tap pair row (x0,y) / (x0+1,y)
     static MD2_HD void red2(const FusedParams& p, float* gb, int x0, int y, const float (&v0)[C], const float (&v1)[C],
                             bool emit1) {
-        const long long HW = (long long)p.W * p.H;
+        const int HW = p.W * p.H;
+        float* a = gb + (y * p.W + x0);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            MD2_ATOMIC_ADD(gb + c * HW + y * p.W + x0, v0[c]);
-            if (emit1) MD2_ATOMIC_ADD(gb + c * HW + y * p.W + x0 + 1, v1[c]);
+            MD2_ATOMIC_ADD(a + c * HW, v0[c]);
+            if (emit1) MD2_ATOMIC_ADD(a + c * HW + 1, v1[c]);
         }
     }
 
@@ -475,9 +486,11 @@ struct Fused {
             sB = up_s * (cx * st[1] + cy * st[2]) / (m * m * (float)HW);
         }
         const float wl = (gx == 1) ? 2.f : 1.f, wr = (gx == p.W - 2) ? 2.f : 1.f;
-        const float* ab[S];
+        float ab[S][12];
 #pragma unroll
-        for (int s = 0; s < S; ++s) ab[s] = p.pose_ab + ((long long)s * p.N + n) * 12;
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ab[s][k] = p.pose_ab[((long long)s * p.N + n) * 12 + k];
 
         // vertical carry of the lower tap pair of the previous row, per source
         float car0[S][C], car1[S][C];
@@ -501,7 +514,8 @@ struct Fused {
             const int ti = py * TW + pxc;
             const float selj = sm[OFF_SEL + (py + 1) * QW + pxc + 1];
             const float d = sm[OFF_DISP + r];
-            float dbar_z = 0.f, zz = 0.f;
+            const float z = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
+            float dbar_z = 0.f;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 // d loss / d warped_s at this pixel
@@ -526,9 +540,8 @@ struct Fused {
                     if (selj == (float)s) g += up_photo * ((1.0f - PHOTO_ALPHA) / C) * sgnf(xj - yj);
                     ibar[c] = valid ? g : 0.f;
                 }
-                Taps tp; Proj pr; float z;
-                project_pixel(p, ab[s], gx < p.W ? gx : p.W - 1, gy < p.H ? gy : p.H - 1, d, pr, tp, z);
-                zz = z;
+                Taps tp; Proj pr;
+                project_pixel(p, ab[s], gx < p.W ? gx : p.W - 1, gy < p.H ? gy : p.H - 1, z, pr, tp);
                 float du = 0.f, dv = 0.f;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -590,7 +603,7 @@ struct Fused {
                 }
             }
             // depth -> disparity:  dz/dd = -a z^2
-            float gd = -p.depth_a * zz * zz * dbar_z;
+            float gd = -p.depth_a * z * z * dbar_z;
             // smoothness gradient (src/utils.jl:159-173 with the mean-normalisation of
             // src/training.jl:64-65 folded in):  A ghat_j - B
             float gh = 0.f;
@@ -647,35 +660,50 @@ struct Fused {
         if (nex > PATCH_MAX) nex = PATCH_MAX;          // cannot happen for decoder scales <= 1/2
     }
     static MD2_HD void phase_down_a(const FusedParams& p, float* sm, int tid) {
+        // one thread per tile row: each pixel feeds the two patch columns x0 and x0+1
         int ex0, nex, ey0, ney;
         patch_extent(sm, ex0, nex, ey0, ney);
-        for (int i = tid; i < TH * nex; i += FUSED_THREADS) {
-            const int y = i / nex, e = i % nex;
-            const float ex = (float)(ex0 + e);
-            float acc = 0.f;
+        for (int y = tid; y < TH; y += FUSED_THREADS) {
+            float* row = sm + OFF_TMP + y * PATCH_MAX;
+            int cur = 0;                 // patch column of accumulator a0 (a1 is cur + 1)
+            float a0 = 0.f, a1 = 0.f;
             for (int x = 0; x < TW; ++x) {
-                const float a0 = sm[OFF_TAPX + x], f = sm[OFF_TAPX + TW + x];
-                const float w = (a0 == ex ? 1.f - f : 0.f) + (a0 + 1.f == ex ? f : 0.f);
-                acc = fmaf(w, sm[OFF_GD + y * TW + x], acc);
+                const int e = (int)sm[OFF_TAPX + x] - ex0;
+                const float f = sm[OFF_TAPX + TW + x], g = sm[OFF_GD + y * TW + x];
+                while (cur < e) {        // columns only advance: flush the finished one
+                    if (cur < PATCH_MAX) row[cur] = a0;
+                    a0 = a1; a1 = 0.f; ++cur;
+                }
+                a0 = fmaf(1.f - f, g, a0);
+                a1 = fmaf(f, g, a1);
             }
-            sm[OFF_TMP + y * PATCH_MAX + e] = acc;
+            if (cur < PATCH_MAX) row[cur] = a0;
+            if (cur + 1 < PATCH_MAX) row[cur + 1] = a1;
+            for (int e = cur + 2; e < nex; ++e) row[e] = 0.f;
         }
     }
     static MD2_HD void phase_down_b(const FusedParams& p, float* sm, int scale, int n, int tid) {
+        // one thread per patch column: march down the tile rows, flush a patch row when y0 advances
         int ex0, nex, ey0, ney;
         patch_extent(sm, ex0, nex, ey0, ney);
         const int dw = p.dw[scale], dh = p.dh[scale];
         float* g = p.gdisp[scale] + (long long)n * dw * dh;
-        for (int i = tid; i < ney * nex; i += FUSED_THREADS) {
-            const int ej = i / nex, e = i % nex;
-            const float ey = (float)(ey0 + ej);
-            float acc = 0.f;
+        for (int e = tid; e < nex; e += FUSED_THREADS) {
+            if (ex0 + e >= dw) continue;
+            int cur = ey0;
+            float a0 = 0.f, a1 = 0.f;   // accumulators of patch rows cur and cur+1
             for (int y = 0; y < TH; ++y) {
-                const float a0 = sm[OFF_TAPY + y], f = sm[OFF_TAPY + TH + y];
-                const float w = (a0 == ey ? 1.f - f : 0.f) + (a0 + 1.f == ey ? f : 0.f);
-                acc = fmaf(w, sm[OFF_TMP + y * PATCH_MAX + e], acc);
+                const int r = (int)sm[OFF_TAPY + y];
+                const float f = sm[OFF_TAPY + TH + y], v = sm[OFF_TMP + y * PATCH_MAX + e];
+                while (cur < r) {   // rows only advance; flush the finished one
+                    if (a0 != 0.f && cur < dh) MD2_ATOMIC_ADD(g + cur * dw + ex0 + e, a0);
+                    a0 = a1; a1 = 0.f; ++cur;
+                }
+                a0 = fmaf(1.f - f, v, a0);
+                a1 = fmaf(f, v, a1);
             }
-            if (ey0 + ej < dh && ex0 + e < dw && acc != 0.f) MD2_ATOMIC_ADD(g + (ey0 + ej) * dw + ex0 + e, acc);
+            if (a0 != 0.f && cur < dh) MD2_ATOMIC_ADD(g + cur * dw + ex0 + e, a0);
+            if (a1 != 0.f && cur + 1 < dh) MD2_ATOMIC_ADD(g + (cur + 1) * dw + ex0 + e, a1);
         }
     }
 };
