@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ Fused
 // loss and the pose gradients (fixed summation order => the loss is run-to-run deterministic)
 // ------------------------------------------------------------------------------------------
 template <int C, int S, bool BWD>
-__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(FUSED_THREADS, BWD ? (C == 1 ? 5 : 3) : 4) fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ float sm[];
     using F = Fused<C, S, BWD>;
     const int z = blockIdx.z, scale = z / p.N, n = z % p.N;
@@ -371,7 +371,7 @@ static int dispatch_fused(md2_ctx* ctx, int C, int S, const FusedParams& p, cuda
 
 template <bool BWD>
 static int tiles_of(int C, int W, int H) {
-    const int tw = BWD ? 30 : 32, th = (C == 1) ? 32 : 16;
+    const int tw = BWD ? 30 : 32, th = 16;
     return cdiv(W, tw) * cdiv(H, th);
 }
 

@@ -155,7 +155,7 @@ template <int C, int S, bool BWD>
 struct Fused {
     static constexpr int HALO = BWD ? 2 : 1;
     static constexpr int TW = BWD ? 30 : 32;          // BWD: 30 + 2 window halo = 32 = one warp of window columns
-    static constexpr int TH = (C == 1) ? 32 : 16;
+    static constexpr int TH = 16;
     static constexpr int RW = TW + 2 * HALO, RH = TH + 2 * HALO;          // pixel region
     static constexpr int QW = TW + 2 * (HALO - 1), QH = TH + 2 * (HALO - 1);  // window region
     static constexpr int RN = RW * RH, QN = QW * QH, TN = TW * TH;
@@ -171,8 +171,8 @@ struct Fused {
     static constexpr int OFF_SEL = OFF_COEF + (BWD ? 3 * C * QN : 0);   // BWD: [QN] selected source or -1
     static constexpr int OFF_SLOPE = OFF_SEL + (BWD ? QN : 0);  // BWD: [S*C*2][TN] d warped / d (ix, iy)
     static constexpr int OFF_GD = OFF_SLOPE + (BWD ? 2 * S * C * TN : 0);   // BWD: [TN] full-res disparity gradient
-    static constexpr int OFF_TMP = OFF_GD + (BWD ? TN : 0);     // BWD: [TH][PATCH_MAX] phase-4 scratch
-    static constexpr int OFF_TAPX = OFF_TMP + (BWD ? TH * PATCH_MAX : 0);   // BWD: [TW] x0 (as float), [TW] fx
+    static constexpr int OFF_TMP = OFF_GD + (BWD ? TN : 0);     // BWD: [NSEG][TH][PATCH_MAX] phase-4 scratch
+    static constexpr int OFF_TAPX = OFF_TMP + (BWD ? 4 * TH * PATCH_MAX : 0);   // BWD: [TW] x0 (as float), [TW] fx
     static constexpr int OFF_TAPY = OFF_TAPX + (BWD ? 2 * TW : 0);          // BWD: [TH] y0, [TH] fy
     static constexpr int SMEM_FLOATS = OFF_TAPY + (BWD ? 2 * TH : 0);
 
@@ -200,18 +200,29 @@ struct Fused {
     static MD2_HD void gather(const FusedParams& p, int n, int s, const Taps& tp, Warped& w) {
         const long long HW = (long long)p.W * p.H;
         const float* base = p.src[s] + (long long)n * p.src_ns[s];
-        const int o00 = tp.y0 * p.W + tp.x0, o01 = tp.y0 * p.W + tp.x1;
-        const int o10 = tp.y1 * p.W + tp.x0, o11 = tp.y1 * p.W + tp.x1;
+        const float* r0 = base + (tp.y0 * p.W + tp.x0);   // the 2x2 cell is always inside the image
+        const float* r1 = r0 + p.W;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float* b = base + c * HW;
-            const float v00 = b[o00], v01 = b[o01], v10 = b[o10], v11 = b[o11];
+            const float v00 = r0[c * HW], v01 = r0[c * HW + 1], v10 = r1[c * HW], v11 = r1[c * HW + 1];
             w.val[c] = bilerp(v00, v01, v10, v11, tp.fx, tp.fy);
             if (DERIV) {
                 w.dix[c] = fmaf(tp.fy, (v11 - v10) - (v01 - v00), v01 - v00);
                 w.diy[c] = fmaf(tp.fx, (v11 - v01) - (v10 - v00), v10 - v00);
             }
         }
+    }
+
+    // image coordinates of region pixel i (reflect-pad(1): only -1 and W, resp. H, are ever read
+    // by an in-image window); false if the pixel is outside the image
+    static MD2_HD bool region_coords(const FusedParams& p, int i, int tx0, int ty0, int& gx, int& gy) {
+        const int lx = i % RW, ly = i / RW;
+        gx = tx0 - HALO + lx; gy = ty0 - HALO + ly;
+        if (gx == -1) gx = 1;
+        if (gx == p.W) gx = p.W - 2;
+        if (gy == -1) gy = 1;
+        if (gy == p.H) gy = p.H - 2;
+        return gx >= 0 && gx < p.W && gy >= 0 && gy < p.H;
     }
 
     // ---- phase 1 ----
@@ -227,21 +238,26 @@ struct Fused {
         for (int s = 0; s < S; ++s)
 #pragma unroll
             for (int k = 0; k < 12; ++k) ab[s][k] = p.pose_ab[((long long)s * p.N + n) * 12 + k];
+        // pass A: target + disparity of every region pixel (independent loads, all in flight)
+#pragma unroll
+        for (int k = 0; k < (RN + FUSED_THREADS - 1) / FUSED_THREADS; ++k) {
+            const int i = tid + k * FUSED_THREADS;
+            if (i < RN) {
+                int gx, gy;
+                const bool ok = region_coords(p, i, tx0, ty0, gx, gy);
+                sm[OFF_DISP + i] = ok ? disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy) : 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) sm[OFF_TGT + c * RN + i] = ok ? tg[c * HW + gy * p.W + gx] : 0.f;
+            }
+        }
+        // pass B: geometry + gather of both sources (each thread re-reads its own disparities)
+#pragma unroll 2
         for (int i = tid; i < RN; i += FUSED_THREADS) {
             const int lx = i % RW, ly = i / RW;
-            int gx = tx0 - HALO + lx, gy = ty0 - HALO + ly;
-            // reflect-pad(1): only -1 and W (resp. H) are ever read by an in-image window
-            if (gx == -1) gx = 1;
-            if (gx == p.W) gx = p.W - 2;
-            if (gy == -1) gy = 1;
-            if (gy == p.H) gy = p.H - 2;
-            const bool ok = gx >= 0 && gx < p.W && gy >= 0 && gy < p.H;
-            float d = 0.f;
-            if (ok) d = disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy);
-            sm[OFF_DISP + i] = d;
+            int gx, gy;
+            const bool ok = region_coords(p, i, tx0, ty0, gx, gy);
+            const float d = sm[OFF_DISP + i];
             const float z = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
-#pragma unroll
-            for (int c = 0; c < C; ++c) sm[OFF_TGT + c * RN + i] = ok ? tg[c * HW + gy * p.W + gx] : 0.f;
             const bool in_tile = BWD && lx >= HALO && lx < HALO + TW && ly >= HALO && ly < HALO + TH;
             const int ti = (ly - HALO) * TW + (lx - HALO);
 #pragma unroll
@@ -540,25 +556,33 @@ struct Fused {
                     if (selj == (float)s) g += up_photo * ((1.0f - PHOTO_ALPHA) / C) * sgnf(xj - yj);
                     ibar[c] = valid ? g : 0.f;
                 }
-                Taps tp; Proj pr;
-                project_pixel(p, ab[s], gx < p.W ? gx : p.W - 1, gy < p.H ? gy : p.H - 1, z, pr, tp);
-                float du = 0.f, dv = 0.f;
+                bool act = false;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    du = fmaf(ibar[c], sm[OFF_SLOPE + ((s * C + c) * 2 + 0) * TN + ti], du);
-                    dv = fmaf(ibar[c], sm[OFF_SLOPE + ((s * C + c) * 2 + 1) * TN + ti], dv);
+                for (int c = 0; c < C; ++c) act = act || (ibar[c] != 0.f);
+                Taps tp;
+                tp.x0 = 0; tp.y0 = 0; tp.x1 = 0; tp.y1 = 0; tp.fx = 0.f; tp.fy = 0.f; tp.mx = 0.f; tp.my = 0.f;
+                if (act) {   // (sources that were not selected anywhere in the 3x3 neighbourhood skip all of this)
+                    Proj pr;
+                    project_pixel(p, ab[s], gx, gy, z, pr, tp);
+                    float du = 0.f, dv = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        du = fmaf(ibar[c], sm[OFF_SLOPE + ((s * C + c) * 2 + 0) * TN + ti], du);
+                        dv = fmaf(ibar[c], sm[OFF_SLOPE + ((s * C + c) * 2 + 1) * TN + ti], dv);
+                    }
+                    du *= tp.mx; dv *= tp.my;
+                    float cb[3];
+                    project_ab_bwd(pr, du, dv, cb);
+                    dbar_z += cb[0] * pr.ap[0] + cb[1] * pr.ap[1] + cb[2] * pr.ap[2];
+                    const float zp[3] = {z * (float)(gx + 1), z * (float)(gy + 1), z};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) acc.pose[s][3 * a + b] = fmaf(cb[a], zp[b], acc.pose[s][3 * a + b]);
+                        acc.pose[s][9 + a] += cb[a];
+                    }
                 }
-                du *= tp.mx; dv *= tp.my;
-                float cb[3];
-                project_ab_bwd(pr, du, dv, cb);
-                dbar_z += cb[0] * pr.ap[0] + cb[1] * pr.ap[1] + cb[2] * pr.ap[2];
-                const float zp[3] = {z * (float)(gx + 1), z * (float)(gy + 1), z};
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) acc.pose[s][3 * a + b] = fmaf(cb[a], zp[b], acc.pose[s][3 * a + b]);
-                    acc.pose[s][9 + a] += cb[a];
-                }
+                const bool sval = valid && act;   // this pixel scatters into source s
                 // source-image gradient: scatter with vertical carry (+ warp merge on the device)
                 if (p.gsrc[s]) {
                     float* gb = p.gsrc[s] + (long long)n * p.src_ns[s];
@@ -568,22 +592,22 @@ struct Fused {
 #pragma unroll
                     for (int c = 0; c < C; ++c) { t0[c] = w00 * ibar[c]; t1[c] = w01 * ibar[c]; }
                     const bool have = cx0[s] >= 0;
-                    const bool aligned = have && valid && tp.x0 == cx0[s] && tp.y0 == cy0[s] + 1;
+                    const bool aligned = have && sval && tp.x0 == cx0[s] && tp.y0 == cy0[s] + 1;
                     if (aligned) {
 #pragma unroll
                         for (int c = 0; c < C; ++c) { t0[c] += car0[s][c]; t1[c] += car1[s][c]; }
-                    } else if (have && cy0[s] + 1 < p.H) {
-                        red2(p, gb, cx0[s], cy0[s] + 1, car0[s], car1[s], cx0[s] + 1 < p.W);
+                    } else if (have) {
+                        red2(p, gb, cx0[s], cy0[s] + 1, car0[s], car1[s], true);
                     }
-                    bool emit1 = valid && tp.x0 + 1 < p.W;
+                    bool emit1 = sval;
 #if defined(__CUDA_ARCH__)
                     {   // merge with the horizontal neighbours: my right tap is the right lane's left tap
-                        const int key = valid ? ((tp.y0 << 16) | tp.x0) : -2;
+                        const int key = sval ? ((tp.y0 << 16) | tp.x0) : -2;
                         const int key_r = __shfl_down_sync(0xffffffffu, key, 1);
                         const int key_l = __shfl_up_sync(0xffffffffu, key, 1);
                         const int lane = threadIdx.x & 31;
-                        const bool absorbed = valid && lane < 31 && key_r == key + 1;
-                        const bool absorb = valid && lane > 0 && key_l >= 0 && key_l + 1 == key;
+                        const bool absorbed = sval && lane < 31 && key_r == key + 1;
+                        const bool absorb = sval && lane > 0 && key_l >= 0 && key_l + 1 == key;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             const float fl = __shfl_up_sync(0xffffffffu, t1[c], 1);
@@ -592,8 +616,8 @@ struct Fused {
                         if (absorbed) emit1 = false;
                     }
 #endif
-                    if (valid) red2(p, gb, tp.x0, tp.y0, t0, t1, emit1);
-                    if (valid) {
+                    if (sval) red2(p, gb, tp.x0, tp.y0, t0, t1, emit1);
+                    if (sval) {
                         cx0[s] = tp.x0; cy0[s] = tp.y0;
 #pragma unroll
                         for (int c = 0; c < C; ++c) { car0[s][c] = w10 * ibar[c]; car1[s][c] = w11 * ibar[c]; }
@@ -646,8 +670,8 @@ struct Fused {
         // flush the carried lower tap pairs of the strip's last row
 #pragma unroll
         for (int s = 0; s < S; ++s)
-            if (p.gsrc[s] && cx0[s] >= 0 && cy0[s] + 1 < p.H)
-                red2(p, p.gsrc[s] + (long long)n * p.src_ns[s], cx0[s], cy0[s] + 1, car0[s], car1[s], cx0[s] + 1 < p.W);
+            if (p.gsrc[s] && cx0[s] >= 0)
+                red2(p, p.gsrc[s] + (long long)n * p.src_ns[s], cx0[s], cy0[s] + 1, car0[s], car1[s], true);
     }
 
     // ---- phase 4 (BWD, low-res scale): adjoint of the bilinear upsample, separable gather ----
@@ -659,42 +683,53 @@ struct Fused {
         ney = (int)sm[OFF_TAPY + TH - 1] + 2 - ey0;
         if (nex > PATCH_MAX) nex = PATCH_MAX;          // cannot happen for decoder scales <= 1/2
     }
+    // 4a: thread (row y, segment g): horizontal pass over its NSEG-th of the tile columns into its own
+    //     slice tmp[g][y][.]; 4b: thread (patch column e, segment g of the rows): vertical pass over the
+    //     sum of the slices, flushed with one atomic per finished low-res element
+    static constexpr int NSEG = 4;
     static MD2_HD void phase_down_a(const FusedParams& p, float* sm, int tid) {
-        // one thread per tile row: each pixel feeds the two patch columns x0 and x0+1
         int ex0, nex, ey0, ney;
         patch_extent(sm, ex0, nex, ey0, ney);
-        for (int y = tid; y < TH; y += FUSED_THREADS) {
-            float* row = sm + OFF_TMP + y * PATCH_MAX;
-            int cur = 0;                 // patch column of accumulator a0 (a1 is cur + 1)
+        constexpr int SEGW = (TW + NSEG - 1) / NSEG;
+        for (int i = tid; i < TH * NSEG; i += FUSED_THREADS) {
+            const int y = i / NSEG, g = i % NSEG;
+            float* row = sm + OFF_TMP + (g * TH + y) * PATCH_MAX;
+            const int xa = g * SEGW, xb = (xa + SEGW < TW) ? xa + SEGW : TW;
+            for (int e = 0; e < nex; ++e) row[e] = 0.f;
+            int cur = (int)sm[OFF_TAPX + xa] - ex0;   // patch column of accumulator a0 (a1 is cur + 1)
             float a0 = 0.f, a1 = 0.f;
-            for (int x = 0; x < TW; ++x) {
+            for (int x = xa; x < xb; ++x) {
                 const int e = (int)sm[OFF_TAPX + x] - ex0;
-                const float f = sm[OFF_TAPX + TW + x], g = sm[OFF_GD + y * TW + x];
+                const float f = sm[OFF_TAPX + TW + x], gdv = sm[OFF_GD + y * TW + x];
                 while (cur < e) {        // columns only advance: flush the finished one
                     if (cur < PATCH_MAX) row[cur] = a0;
                     a0 = a1; a1 = 0.f; ++cur;
                 }
-                a0 = fmaf(1.f - f, g, a0);
-                a1 = fmaf(f, g, a1);
+                a0 = fmaf(1.f - f, gdv, a0);
+                a1 = fmaf(f, gdv, a1);
             }
             if (cur < PATCH_MAX) row[cur] = a0;
             if (cur + 1 < PATCH_MAX) row[cur + 1] = a1;
-            for (int e = cur + 2; e < nex; ++e) row[e] = 0.f;
         }
     }
     static MD2_HD void phase_down_b(const FusedParams& p, float* sm, int scale, int n, int tid) {
-        // one thread per patch column: march down the tile rows, flush a patch row when y0 advances
         int ex0, nex, ey0, ney;
         patch_extent(sm, ex0, nex, ey0, ney);
         const int dw = p.dw[scale], dh = p.dh[scale];
         float* g = p.gdisp[scale] + (long long)n * dw * dh;
-        for (int e = tid; e < nex; e += FUSED_THREADS) {
+        constexpr int SEGH = (TH + NSEG - 1) / NSEG;
+        for (int i = tid; i < nex * NSEG; i += FUSED_THREADS) {
+            const int e = i / NSEG, sg = i % NSEG;
             if (ex0 + e >= dw) continue;
-            int cur = ey0;
-            float a0 = 0.f, a1 = 0.f;   // accumulators of patch rows cur and cur+1
-            for (int y = 0; y < TH; ++y) {
+            const int ya = sg * SEGH, yb = (ya + SEGH < TH) ? ya + SEGH : TH;
+            int cur = (int)sm[OFF_TAPY + ya];
+            float a0 = 0.f, a1 = 0.f;   // accumulators of low-res rows cur and cur+1
+            for (int y = ya; y < yb; ++y) {
                 const int r = (int)sm[OFF_TAPY + y];
-                const float f = sm[OFF_TAPY + TH + y], v = sm[OFF_TMP + y * PATCH_MAX + e];
+                const float f = sm[OFF_TAPY + TH + y];
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < NSEG; ++k) v += sm[OFF_TMP + (k * TH + y) * PATCH_MAX + e];
                 while (cur < r) {   // rows only advance; flush the finished one
                     if (a0 != 0.f && cur < dh) MD2_ATOMIC_ADD(g + cur * dw + ex0 + e, a0);
                     a0 = a1; a1 = 0.f; ++cur;

@@ -75,13 +75,15 @@ MD2_HD Taps border_taps(float u, float v, int W, int H) {
     const float cv = fminf(fmaxf(v, 1.0f), (float)H) - 1.0f;
     t.mx = (u > 1.0f && u < (float)W) ? 1.0f : 0.0f;
     t.my = (v > 1.0f && v < (float)H) ? 1.0f : 0.0f;
-    const float flx = floorf(cu), fly = floorf(cv);
-    t.fx = cu - flx;
-    t.fy = cv - fly;
-    t.x0 = (int)flx;
-    t.y0 = (int)fly;
-    t.x1 = t.x0 + 1 < W ? t.x0 + 1 : W - 1;  // out-of-range tap has weight 0 (fx == 0)
-    t.y1 = t.y0 + 1 < H ? t.y0 + 1 : H - 1;
+    // the cell is kept inside the image (x0 <= W-2): at the last column the sample is expressed as
+    // (x0 = W-2, fx = 1) instead of (x0 = W-1, fx = 0) -- same value, same image gradient, the
+    // coordinate gradient is masked there anyway -- so that all four taps are always in range
+    int x0 = (int)cu, y0 = (int)cv;                            // cu, cv >= 0: truncation == floor
+    x0 = x0 < W - 2 ? x0 : W - 2;
+    y0 = y0 < H - 2 ? y0 : H - 2;
+    t.fx = cu - (float)x0;
+    t.fy = cv - (float)y0;
+    t.x0 = x0; t.y0 = y0; t.x1 = x0 + 1; t.y1 = y0 + 1;
     return t;
 }
 
