@@ -1,0 +1,385 @@
+# Monodepth2B200.jl -- Julia binding of libmd2_b200.so (include/md2.h): drop-in replacements, with
+# ChainRulesCore rrules, for the view-synthesis loss entry points of pxl-th/Monodepth2.jl
+# (src/utils.jl, src/training.jl, and the `warp` that src/simple_depth.jl:30-32 calls but the
+# reference never defines).
+#
+# STATUS: written against include/md2.h and reviewed, but NOT executed -- there is no Julia in the
+# build image or on the GPU box.  The same C ABI is exercised end to end by the Python ctypes
+# binding (monodepth2.jl_b200/_lib.py) and the -m gpu tests.
+#
+# Usage inside the reference (see INTEGRATION.md):
+#     include("Monodepth2B200.jl"); using .Monodepth2B200
+#     # src/utils.jl / src/training.jl definitions of the functions below are then shadowed for
+#     # CuArray{Float32} arguments; CPU / Float64 arrays keep using the reference's own methods.
+module Monodepth2B200
+
+using CUDA
+using ChainRulesCore
+import ChainRulesCore: rrule
+
+const LIB = get(ENV, "MD2_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libmd2_b200.so"))
+const CuF = CuArray{Float32}
+const P32 = CuPtr{Float32}
+const MAX_S, MAX_L = 2, 8
+
+# ---------------------------------------------------------------------------------------------
+# context / errors
+# ---------------------------------------------------------------------------------------------
+const CTX = Dict{Int, Ptr{Cvoid}}()
+
+last_error() = unsafe_string(ccall((:md2_last_error, LIB), Cstring, ()))
+check(status::Cint) = status == 0 ? nothing : error("md2: " * last_error())
+
+function ctx()
+    dev = CUDA.deviceid(CUDA.device())
+    get!(CTX, dev) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:md2_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), dev, h))
+        h[]
+    end
+end
+stream() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
+ptr(x::CuF) = pointer(x)
+ptr(::Nothing) = P32(0)
+
+# ---------------------------------------------------------------------------------------------
+# A1 disparity_to_depth (src/utils.jl:175-179)
+# ---------------------------------------------------------------------------------------------
+function disparity_to_depth(disparity::CuF, min_depth, max_depth)
+    out = similar(disparity)
+    check(ccall((:md2_disparity_to_depth_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Int64, Cfloat, Cfloat, Ptr{Cvoid}),
+                ctx(), disparity, out, length(disparity), min_depth, max_depth, stream()))
+    out
+end
+function rrule(::typeof(disparity_to_depth), disparity::CuF, min_depth, max_depth)
+    y = disparity_to_depth(disparity, min_depth, max_depth)
+    function pb(Δ)
+        g = similar(disparity)
+        check(ccall((:md2_disparity_to_depth_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Int64, Cfloat, Cfloat, Ptr{Cvoid}),
+                    ctx(), disparity, CuF(unthunk(Δ)), g, length(disparity), min_depth, max_depth, stream()))
+        NoTangent(), g, NoTangent(), NoTangent()
+    end
+    y, pb
+end
+
+# ---------------------------------------------------------------------------------------------
+# A2 Backproject / A3 Project (src/utils.jl:41-99): same callable structs as the reference
+# ---------------------------------------------------------------------------------------------
+struct Backproject; width::Int; height::Int; end
+Backproject(::Type{T} = Float32; width, height) where T = Backproject(width, height)
+function (b::Backproject)(depth::CuF, invK::CuF)            # depth (1,P,N), invK (3,3) -> (3,P,N)
+    N = length(depth) ÷ (b.width * b.height)
+    pts = CUDA.zeros(Float32, 3, b.width * b.height, N)
+    check(ccall((:md2_backproject_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
+                ctx(), depth, invK, pts, b.width, b.height, N, stream()))
+    pts
+end
+function rrule(b::Backproject, depth::CuF, invK::CuF)
+    y = b(depth, invK)
+    function pb(Δ)
+        g = similar(depth)
+        check(ccall((:md2_backproject_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
+                    ctx(), CuF(unthunk(Δ)), invK, g, b.width, b.height, size(y, 3), stream()))
+        NoTangent(), g, NoTangent()
+    end
+    y, pb
+end
+
+struct Project; width::Int; height::Int; end
+Project(::Type{T} = Float32; width, height) where T = Project(width, height)
+function (p::Project)(points::CuF, K::CuF, R::CuF, t::CuF)  # (3,P,N),(3,3[,1]),(3,3,N),(3,1,N) -> (2,P,N)
+    N = size(points, 3)
+    uv = CUDA.zeros(Float32, 2, size(points, 2), N)
+    check(ccall((:md2_project_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
+                ctx(), points, K, R, t, uv, p.width, p.height, N, stream()))
+    uv
+end
+function rrule(p::Project, points::CuF, K::CuF, R::CuF, t::CuF)
+    y = p(points, K, R, t)
+    function pb(Δ)
+        gp, gR, gt = similar(points), similar(R), similar(t)
+        check(ccall((:md2_project_bwd, LIB), Cint,
+                    (Ptr{Cvoid}, P32, P32, P32, P32, P32, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
+                    ctx(), points, K, R, t, CuF(unthunk(Δ)), gp, gR, gt, p.width, p.height, size(points, 3), stream()))
+        NoTangent(), gp, NoTangent(), gR, gt
+    end
+    y, pb
+end
+
+# ---------------------------------------------------------------------------------------------
+# A4-A6 so3_exp_map / hat / composeT (src/utils.jl:101-141, 181-188)
+# ---------------------------------------------------------------------------------------------
+function so3_exp_map(rvec::CuF)
+    N = size(rvec, 2); R = CUDA.zeros(Float32, 3, 3, N)
+    check(ccall((:md2_so3_exp_map_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Cint, Ptr{Cvoid}), ctx(), rvec, R, N, stream()))
+    R
+end
+function rrule(::typeof(so3_exp_map), rvec::CuF)
+    R = so3_exp_map(rvec)
+    function pb(Δ)
+        g = similar(rvec)
+        check(ccall((:md2_so3_exp_map_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Ptr{Cvoid}),
+                    ctx(), rvec, CuF(unthunk(Δ)), g, size(rvec, 2), stream()))
+        NoTangent(), g
+    end
+    R, pb
+end
+function hat(rvec::CuF)
+    N = size(rvec, 2); S = CUDA.zeros(Float32, 3, 3, N)
+    check(ccall((:md2_hat_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Cint, Ptr{Cvoid}), ctx(), rvec, S, N, stream()))
+    S
+end
+function rrule(::typeof(hat), v::CuF)                       # the reference's one hand-written rrule
+    Y = hat(v)
+    function hat_pullback(Δ)
+        g = similar(v)
+        check(ccall((:md2_hat_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Cint, Ptr{Cvoid}), ctx(), CuF(unthunk(Δ)), g, size(v, 2), stream()))
+        NoTangent(), g
+    end
+    Y, hat_pullback
+end
+function composeT(rvec::CuF, t::CuF, invert::Bool)
+    N = size(rvec, 2); R = CUDA.zeros(Float32, 3, 3, N); tu = similar(t)
+    check(ccall((:md2_compose_T_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Cint, P32, P32, Cint, Ptr{Cvoid}),
+                ctx(), rvec, t, invert, R, tu, N, stream()))
+    R, tu
+end
+function rrule(::typeof(composeT), rvec::CuF, t::CuF, invert::Bool)
+    y = composeT(rvec, t, invert)
+    function pb(Δ)
+        ΔR, Δt = unthunk(Δ)
+        gR = ΔR isa AbstractZero ? P32(0) : ptr(CuF(ΔR)); gt = Δt isa AbstractZero ? P32(0) : ptr(CuF(Δt))
+        gr, gtv = similar(rvec), similar(t)
+        check(ccall((:md2_compose_T_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Cint, P32, P32, P32, P32, Cint, Ptr{Cvoid}),
+                    ctx(), rvec, t, invert, gR, gt, gr, gtv, size(rvec, 2), stream()))
+        NoTangent(), gr, gtv, NoTangent()
+    end
+    y, pb
+end
+
+# ---------------------------------------------------------------------------------------------
+# A7 SSIM (src/utils.jl:13-39)
+# ---------------------------------------------------------------------------------------------
+struct SSIM; c1::Float64; c2::Float64; end
+SSIM() = SSIM(0.01^2, 0.03^2)
+function (ssim::SSIM)(x::CuF, y::CuF)
+    W, H, C, N = size(x); out = similar(x)
+    check(ccall((:md2_ssim_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+                ctx(), x, y, out, W, H, C, N, stream()))
+    out
+end
+function rrule(ssim::SSIM, x::CuF, y::CuF)
+    out = ssim(x, y)
+    function pb(Δ)
+        W, H, C, N = size(x); gx, gy = similar(x), similar(y)
+        check(ccall((:md2_ssim_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, P32, P32, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+                    ctx(), x, y, CuF(unthunk(Δ)), gx, gy, W, H, C, N, stream()))
+        NoTangent(), gx, gy
+    end
+    out, pb
+end
+
+# ---------------------------------------------------------------------------------------------
+# A10-A13 photometric_loss / prediction_loss / automasking_loss / _apply_mask (src/training.jl:1-19)
+# ---------------------------------------------------------------------------------------------
+function _photomin(preds::Vector{<:CuF}, strides::Vector{Int64}, target::CuF, tstride::Int64, α, dims)
+    W, H, C, N = dims; S = length(preds)
+    out = CUDA.zeros(Float32, W, H, 1, N); arg = CUDA.zeros(Int32, W, H, 1, N)
+    pp = [ptr(p) for p in preds]
+    check(ccall((:md2_photometric_min_fwd, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{P32}, Ptr{Int64}, P32, Int64, P32, Cfloat, P32, CuPtr{Int32}, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+                ctx(), S, pp, strides, target, tstride, P32(0), α, out, arg, W, H, C, N, stream()))
+    out, arg
+end
+function _photomin_rrule(preds::Vector{<:CuF}, target::CuF, α)
+    W, H, C, N = size(target); chw = Int64(W * H * C); S = length(preds)
+    out, arg = _photomin(preds, fill(chw, S), target, chw, α, size(target))
+    function pb(Δ)
+        gp = [similar(p) for p in preds]; gt = similar(target)
+        check(ccall((:md2_photometric_min_bwd, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{P32}, Ptr{Int64}, P32, Int64, P32, Cfloat, P32, CuPtr{Int32}, Ptr{P32}, P32, P32,
+                     Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+                    ctx(), S, [ptr(p) for p in preds], fill(chw, S), target, chw, P32(0), α, CuF(unthunk(Δ)), arg,
+                    [ptr(g) for g in gp], gt, P32(0), W, H, C, N, stream()))
+        gp, gt
+    end
+    out, pb
+end
+photometric_loss(ssim, predicted::CuF, target::CuF; α = 0.85f0) =
+    _photomin([predicted], [Int64(length(predicted) ÷ size(predicted, 4))], target, Int64(length(target) ÷ size(target, 4)), α, size(target))[1]
+function rrule(::typeof(photometric_loss), ssim, predicted::CuF, target::CuF; α = 0.85f0)
+    out, pb = _photomin_rrule([predicted], target, α)
+    out, Δ -> ((gp, gt) = pb(Δ); (NoTangent(), NoTangent(), gp[1], gt))
+end
+prediction_loss(ssim, predictions, target::CuF) =
+    _photomin(collect(predictions), fill(Int64(length(target) ÷ size(target, 4)), length(predictions)), target,
+              Int64(length(target) ÷ size(target, 4)), 0.85f0, size(target))[1]
+function rrule(::typeof(prediction_loss), ssim, predictions, target::CuF)
+    out, pb = _photomin_rrule(collect(predictions), target, 0.85f0)
+    out, Δ -> ((gp, gt) = pb(Δ); (NoTangent(), NoTangent(), Tangent{typeof(predictions)}(gp...), gt))
+end
+function automasking_loss(ssim, inputs::CuF, target::CuF; source_ids)      # inputs (W,H,C,L,N): frames passed as views
+    W, H, C, L, N = size(inputs); fstride = W * H * C
+    preds = [unsafe_wrap(CuArray, pointer(inputs, (i - 1) * fstride + 1), (W, H, C, 1)) for i in source_ids]
+    _photomin(preds, fill(Int64(fstride * L), length(source_ids)), target, Int64(W * H * C), 0.85f0, (W, H, C, N))[1]
+end
+ChainRulesCore.@non_differentiable automasking_loss(::Any...)              # a constant in train() (src/Monodepth.jl:159-164)
+_apply_mask(mask::CuF, warp_loss::CuF) = ifelse.(mask .<= warp_loss, mask, warp_loss)   # mask first: wins ties
+
+# ---------------------------------------------------------------------------------------------
+# A8 smooth_loss (src/utils.jl:143-173)
+# ---------------------------------------------------------------------------------------------
+function smooth_loss(disparity::CuF, image::CuF; normalize::Bool = false)
+    W, H, C, N = size(image); out = CUDA.zeros(Float32, 1)
+    check(ccall((:md2_smooth_loss_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Int64, P32, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+                ctx(), disparity, image, W * H * C, out, normalize, W, H, C, N, stream()))
+    CUDA.@allowscalar out[1]
+end
+function rrule(::typeof(smooth_loss), disparity::CuF, image::CuF; normalize::Bool = false)
+    y = smooth_loss(disparity, image; normalize)
+    function pb(Δ)
+        W, H, C, N = size(image); gd, gi = similar(disparity), similar(image)
+        check(ccall((:md2_smooth_loss_bwd, LIB), Cint,
+                    (Ptr{Cvoid}, P32, P32, Int64, Cfloat, P32, P32, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
+                    ctx(), disparity, image, W * H * C, Float32(unthunk(Δ)), gd, gi, normalize, W, H, C, N, stream()))
+        NoTangent(), gd, gi
+    end
+    y, pb
+end
+
+# ---------------------------------------------------------------------------------------------
+# A14 / A15 fused hot path: md2_vsl_desc mirror (include/md2.h), warp, view_synthesis_loss
+# ---------------------------------------------------------------------------------------------
+struct VslDesc
+    W::Int32; H::Int32; N::Int32; C::Int32; S::Int32; L::Int32
+    target::P32; target_image_stride::Int64
+    source::NTuple{MAX_S, P32}; source_image_stride::NTuple{MAX_S, Int64}
+    disparity::NTuple{MAX_L, P32}; disp_w::NTuple{MAX_L, Int32}; disp_h::NTuple{MAX_L, Int32}
+    K::P32; invK::P32
+    pose_mode::Int32
+    rot::NTuple{MAX_S, P32}; trans::NTuple{MAX_S, P32}; invert::NTuple{MAX_S, Int32}
+    automask::P32
+    min_depth::Float32; max_depth::Float32
+    smooth_weight::NTuple{MAX_L, Float32}; loss_scale::Float32; normalize_disparity::Int32
+    loss::P32
+    grad_disparity::NTuple{MAX_L, P32}
+    grad_rot::NTuple{MAX_S, P32}; grad_trans::NTuple{MAX_S, P32}; grad_source::NTuple{MAX_S, P32}
+    viz_warped::NTuple{MAX_S, P32}; viz_loss::P32
+    saved::P32
+end
+pad(v, n, z) = ntuple(i -> i <= length(v) ? v[i] : z, n)
+frameptr(x::CuF, id) = pointer(x, (id - 1) * size(x, 1) * size(x, 2) * size(x, 3) + 1)   # x (W,H,C,L,N), 1-based frame id
+
+"""
+    view_synthesis_loss(x, disparities, poses, K, invK; target_id, source_ids, scales, ...)
+
+Everything of `train_loss` after `model(...)` (src/training.jl:29-77) in two kernel launches.
+Returns `(loss::CuArray{Float32,1}, grads)` where `grads = (disparities, rvecs, tvecs)` are the
+gradients for a unit cotangent (the pullback scales them).
+"""
+function vsl_fwdbwd(x::CuF, disparities, rvecs, tvecs, K::CuF, invK::CuF; target_id, source_ids, scales,
+                    min_depth, max_depth, disparity_smoothness, auto_loss = nothing, normalize = true,
+                    smooth_weight = nothing, loss_scale = nothing, viz = false)
+    W, H, C, Lf, N = size(x); S = length(source_ids); L = length(disparities)
+    loss = CUDA.zeros(Float32, 1)
+    gd = [similar(d) for d in disparities]; gr = [similar(r) for r in rvecs]; gt = [similar(t) for t in tvecs]
+    vw = viz ? [CUDA.zeros(Float32, W, H, C, N) for _ in 1:S] : CuF[]
+    vl = viz ? CUDA.zeros(Float32, W, H, 1, N) : nothing
+    sw = smooth_weight === nothing ? Float32[disparity_smoothness * s for s in scales[1:L]] : Float32.(smooth_weight)
+    fs = Int64(W * H * C * Lf)
+    desc = Ref(VslDesc(W, H, N, C, S, L, frameptr(x, target_id), fs,
+        pad([frameptr(x, i) for i in source_ids], MAX_S, P32(0)), pad(fill(fs, S), MAX_S, Int64(0)),
+        pad([ptr(d) for d in disparities], MAX_L, P32(0)), pad(Int32[size(d, 1) for d in disparities], MAX_L, Int32(0)),
+        pad(Int32[size(d, 2) for d in disparities], MAX_L, Int32(0)), ptr(K), ptr(invK), Int32(1),
+        pad([ptr(r) for r in rvecs], MAX_S, P32(0)), pad([ptr(t) for t in tvecs], MAX_S, P32(0)),
+        pad(Int32[i < target_id for i in source_ids], MAX_S, Int32(0)), ptr(auto_loss),
+        Float32(min_depth), Float32(max_depth), pad(sw, MAX_L, 0f0),
+        Float32(loss_scale === nothing ? 1 / L : loss_scale), Int32(normalize), ptr(loss),
+        pad([ptr(g) for g in gd], MAX_L, P32(0)), pad([ptr(g) for g in gr], MAX_S, P32(0)),
+        pad([ptr(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
+        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0)))
+    GC.@preserve x disparities rvecs tvecs K invK auto_loss loss gd gr gt vw vl begin
+        check(ccall((:md2_view_synthesis_loss_fwdbwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Ptr{Cvoid}),
+                    ctx(), desc, 1f0, stream()))
+    end
+    loss, (gd, gr, gt), vw, vl
+end
+
+# the tail of train_loss as one differentiable function of (disparities, rvecs, tvecs)
+function view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK; kw...)
+    loss, _, _, _ = vsl_fwdbwd(x, disparities, rvecs, tvecs, K, invK; kw...)
+    CUDA.@allowscalar loss[1]
+end
+function rrule(::typeof(view_synthesis_loss), x, disparities, rvecs, tvecs, K, invK; kw...)
+    loss, (gd, gr, gt), _, _ = vsl_fwdbwd(x, disparities, rvecs, tvecs, K, invK; kw...)
+    function pb(Δ)
+        s = Float32(unthunk(Δ))
+        NoTangent(), NoTangent(), Tangent{typeof(disparities)}((s .* g for g in gd)...),
+        Tangent{typeof(rvecs)}((s .* g for g in gr)...), Tangent{typeof(tvecs)}((s .* g for g in gt)...),
+        NoTangent(), NoTangent()
+    end
+    (CUDA.@allowscalar loss[1]), pb
+end
+
+"""
+Drop-in for `train_loss` (src/training.jl:21-78): `model`, `cache::TrainCache`, `parameters::Params`
+are the reference's own objects; frame ids stay 1-based here.
+"""
+function train_loss(model, x::CuF, auto_loss, cache, parameters, do_visualization)
+    disparities, poses = model(x, cache.source_ids, cache.target_id)
+    kw = (; target_id = cache.target_id, source_ids = cache.source_ids, scales = cache.scales,
+          min_depth = parameters.min_depth, max_depth = parameters.max_depth,
+          disparity_smoothness = parameters.disparity_smoothness,
+          auto_loss = parameters.automasking ? auto_loss : nothing)
+    rvecs = [p.rvec for p in poses]; tvecs = [p.tvec for p in poses]
+    loss = view_synthesis_loss(x, collect(disparities), rvecs, tvecs, cache.K, cache.invK; kw...)
+    if do_visualization     # forward-only second pass for the logging outputs (every 50 iterations)
+        _, _, vw, vl = ChainRulesCore.ignore_derivatives() do
+            vsl_fwdbwd(x, collect(disparities), rvecs, tvecs, cache.K, cache.invK; kw..., viz = true)
+        end
+        return loss, Array(disparities[end]), Array.(vw), Array(vl)
+    end
+    loss, nothing, nothing, nothing
+end
+
+"""
+`warp` -- called at src/simple_depth.jl:30-32 but never defined by the reference; body as in
+src/training.jl:48-57.  `Ps` = vector of `(R, t)` from `composeT`.  Returns the warped images.
+"""
+function warp(disp::CuF, x::CuF, Ps, backprojections, projections, invKs::CuF, Ks::CuF; min_depth, max_depth, source_ids)
+    W, H, C, Lf, N = size(x); S = length(source_ids); fs = Int64(W * H * C * Lf)
+    outs = [CUDA.zeros(Float32, W, H, C, N) for _ in 1:S]
+    desc = Ref(_warp_desc(disp, x, Ps, invKs, Ks, min_depth, max_depth, source_ids, nothing))
+    GC.@preserve disp x Ps invKs Ks outs begin
+        check(ccall((:md2_warp_fwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Ptr{P32}, Ptr{Cvoid}), ctx(), desc, [ptr(o) for o in outs], stream()))
+    end
+    outs
+end
+function _warp_desc(disp, x, Ps, invKs, Ks, min_depth, max_depth, source_ids, grads)
+    W, H, C, Lf, N = size(x); S = length(source_ids); fs = Int64(W * H * C * Lf); z = P32(0)
+    gd, gR, gt = grads === nothing ? (z, fill(z, S), fill(z, S)) : (ptr(grads[1]), ptr.(grads[2]), ptr.(grads[3]))
+    VslDesc(W, H, N, C, S, 1, z, 0, pad([frameptr(x, i) for i in source_ids], MAX_S, z), pad(fill(fs, S), MAX_S, Int64(0)),
+            pad([ptr(disp)], MAX_L, z), pad(Int32[W], MAX_L, Int32(0)), pad(Int32[H], MAX_L, Int32(0)), ptr(Ks), ptr(invKs),
+            Int32(0), pad([ptr(P[1]) for P in Ps], MAX_S, z), pad([ptr(P[2]) for P in Ps], MAX_S, z), pad(Int32[], MAX_S, Int32(0)),
+            z, Float32(min_depth), Float32(max_depth), pad(Float32[], MAX_L, 0f0), 1f0, Int32(0), z,
+            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z)
+end
+function rrule(::typeof(warp), disp::CuF, x::CuF, Ps, backprojections, projections, invKs::CuF, Ks::CuF; min_depth, max_depth, source_ids)
+    outs = warp(disp, x, Ps, backprojections, projections, invKs, Ks; min_depth, max_depth, source_ids)
+    function pb(Δ)
+        gouts = [CuF(unthunk(d)) for d in unthunk(Δ)]
+        gd = similar(disp); gR = [similar(P[1]) for P in Ps]; gt = [similar(P[2]) for P in Ps]
+        desc = Ref(_warp_desc(disp, x, Ps, invKs, Ks, min_depth, max_depth, source_ids, (gd, gR, gt)))
+        GC.@preserve disp x Ps invKs Ks gouts gd gR gt begin
+            check(ccall((:md2_warp_bwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Ptr{P32}, Ptr{Cvoid}), ctx(), desc, [ptr(g) for g in gouts], stream()))
+        end
+        NoTangent(), gd, NoTangent(), Tangent{typeof(Ps)}((Tangent{typeof(P)}(r, t) for (P, r, t) in zip(Ps, gR, gt))...),
+        NoTangent(), NoTangent(), NoTangent(), NoTangent()
+    end
+    outs, pb
+end
+
+export disparity_to_depth, Backproject, Project, so3_exp_map, hat, composeT, SSIM, photometric_loss, prediction_loss,
+       automasking_loss, _apply_mask, smooth_loss, warp, train_loss, view_synthesis_loss
+
+end # module
