@@ -185,11 +185,8 @@ def run_ours(args):
     sampler.sample()
     sampler.stop_flag = True
     launches = ctx.launches - l0 + args.steps   # + one memset (gx) per step
-    ms = e0.elapsed_time(e1)
-    if dist:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+    from monodepth2_jl_b200 import dist as D
+    ms = D.max_over_ranks(e0.elapsed_time(e1), device=dev)   # device time, max over ranks
     frames = NB * world * args.steps
     value = frames / (ms * 1e-3)
 
@@ -245,11 +242,7 @@ def run_ours(args):
         e2e_step()
     e1.record(stream)
     barrier()
-    e_ms = e0.elapsed_time(e1)
-    if dist:
-        t = torch.tensor([e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = t.item()
+    e_ms = D.max_over_ranks(e0.elapsed_time(e1), device=dev)
     e2e_value = NB * world * e_steps / (e_ms * 1e-3)
 
     out = {
