@@ -2,7 +2,7 @@
 the reference's datasets (src/kitty.jl, src/dtk.jl) and networks hand to `train_loss`, with no
 files involved.  Host-side data only -- nothing here computes the loss.
 
-The tests check that these generators produce exactly the data of the oracle's own generator, so
+The tests check that these generators produce exactly the data of the test-side generator, so
 the CUDA arm, the CPU arm and the parity tests all see identical inputs.
 """
 from __future__ import annotations
