@@ -258,7 +258,7 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e_steps, "api": "monodepth2_jl_b200.view_synthesis_loss(...).backward() with pinned host buffers"},
-        "roofline": {"bound": "hbm", "kernel": "fused_kernel<C=1,S=2,BWD> (fused fwd+bwd tile kernel, all scales in one launch)",
+        "roofline": {"bound": "hbm", "kernel": "march_kernel<C=1,S=2,BWD> (fused fwd+bwd marching-warp kernel, all scales in one launch)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "algorithmic_bytes_per_launch": abytes, "bytes_per_unit": per_unit,
                      "kernel_ms": round(k_ms, 5), "kernel_launches_timed": int(kn), "peak_source": peak_src,

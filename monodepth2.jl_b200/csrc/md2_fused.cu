@@ -3,8 +3,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "md2_common.cuh"
 #include "md2_fused.cuh"
+#include "md2_march.cuh"
 
 namespace md2 {
 
@@ -343,6 +346,84 @@ __global__ void __launch_bounds__(FUSED_THREADS, BWD ? (C == 1 ? 5 : 3) : 4) fus
 }
 
 // ------------------------------------------------------------------------------------------
+// the marching-warp kernel (md2_march.cuh): one warp per block, grid (strips, chunks, L*N).
+// The last warp of a (scale, image) reduces that group's partial sums in a fixed order, the
+// very last warp finalises the loss and the pose gradients (deterministic loss).
+// ------------------------------------------------------------------------------------------
+template <int C, int S, bool BWD>
+__global__ void __launch_bounds__(32, BWD ? (C == 1 ? 16 : 10) : 16) march_kernel(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(16) float wsm[];
+    using M = March<C, S, BWD>;
+    constexpr int NP = M::NPART;
+    const int lane = threadIdx.x;
+    const int z = blockIdx.z;
+    const int ipg = gridDim.x * gridDim.y;
+    {
+        float v[32];
+        M::run(p, blockIdx.x, blockIdx.y, z, lane, wsm, v);
+        const float tot = warp_reduce_32(v);
+        const long long item = (long long)z * ipg + blockIdx.y * gridDim.x + blockIdx.x;
+        if (lane < NP) p.partial[item * NP + lane] = tot;
+    }
+    __threadfence();
+    __syncwarp();
+    int flag = 0;
+    if (lane == 0) flag = (atomicAdd(&p.counters[z], 1u) == (unsigned)(ipg - 1)) ? 1 : 0;
+    flag = __shfl_sync(0xffffffffu, flag, 0);
+    if (!flag) return;
+    __threadfence();
+    if (lane < NP) {   // this warp finished (scale, image) z last: reduce its items in a fixed order
+        float s0 = 0.f, s1 = 0.f;
+        const float* pp = p.partial + (long long)z * ipg * NP + lane;
+        int b = 0;
+        for (; b + 1 < ipg; b += 2) { s0 += __ldcg(pp + (long long)b * NP); s1 += __ldcg(pp + (long long)(b + 1) * NP); }
+        if (b < ipg) s0 += __ldcg(pp + (long long)b * NP);
+        p.sums[(long long)z * NP + lane] = s0 + s1;
+    }
+    __threadfence();
+    __syncwarp();
+    const int LN = p.L * p.N;
+    if (lane == 0) {
+        p.counters[z] = 0u;
+        flag = (atomicAdd(&p.counters[LN], 1u) == (unsigned)(LN - 1)) ? 1 : 0;
+    }
+    flag = __shfl_sync(0xffffffffu, flag, 0);
+    if (!flag) return;
+    __threadfence();
+    // ---- the very last warp: loss, saved statistics, pose gradients ----
+    if (p.mode != 1) {
+        for (int zz = lane; zz < LN; zz += 32) {
+            float* st = p.stats_out + (long long)zz * NSTAT;
+            st[0] = __ldcg(p.sums + (long long)zz * NP);
+            if (p.mode == 0) {
+                st[1] = __ldcg(p.sums + (long long)zz * NP + 1);
+                st[2] = __ldcg(p.sums + (long long)zz * NP + 2);
+                st[3] = __ldcg(p.sums + (long long)zz * NP + 3);
+            }
+            if (p.saved && p.saved != p.stats_out)
+                for (int k = 0; k < NSTAT; ++k) p.saved[(long long)zz * NSTAT + k] = st[k];
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0 && p.loss)
+            *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
+    }
+    if (BWD) {
+        for (int i = lane; i < S * p.N; i += 32) {
+            const int s = i / p.N, nn = i % p.N;
+            double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
+            for (int l = 0; l < p.L; ++l) {
+                const float* su = p.sums + ((long long)l * p.N + nn) * NP + NSTAT + 12 * s;
+                for (int k = 0; k < 9; ++k) G[k] += __ldcg(su + k);
+                for (int k = 0; k < 3; ++k) h[k] += __ldcg(su + 9 + k);
+            }
+            finalize_pose(p.pose, s, nn, G, h);
+        }
+    }
+    if (lane == 0) p.counters[LN] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
 template <int C, int S, bool BWD>
@@ -358,6 +439,37 @@ static int launch_fused(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     fused_kernel<C, S, BWD><<<grid, FUSED_THREADS, smem, st>>>(p);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+template <int C, int S, bool BWD>
+static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
+    using M = March<C, S, BWD>;
+    const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
+    dim3 grid(cdiv(p.W, M::OW), cdiv(p.H, p.m_R), p.L * p.N);
+    march_kernel<C, S, BWD><<<grid, 32, smem, st>>>(p);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+template <bool BWD>
+static int dispatch_march(md2_ctx* ctx, int C, int S, const FusedParams& p, cudaStream_t st) {
+    if (C == 1 && S == 1) return launch_march<1, 1, BWD>(ctx, p, st);
+    if (C == 1 && S == 2) return launch_march<1, 2, BWD>(ctx, p, st);
+    if (C == 3 && S == 1) return launch_march<3, 1, BWD>(ctx, p, st);
+    if (C == 3 && S == 2) return launch_march<3, 2, BWD>(ctx, p, st);
+    return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
+}
+
+// rows per chunk of the marching kernel: long chunks amortise the 2*HALO warm-up rows, short ones
+// give enough warps to fill 148 SMs x ~16 resident warps
+static int choose_march_rows(int W, int H, int LN, bool bwd) {
+    static const int env = [] { const char* e = getenv("MD2_MARCH_ROWS"); return e ? atoi(e) : 0; }();
+    if (env > 0) return env < H ? env : H;
+    const int ow = bwd ? 28 : 30;
+    const long long strips = cdiv(W, ow);
+    int R = 32;
+    while (R > 8 && strips * cdiv(H, R) * LN < 148LL * 12) R -= 8;
+    return R < H ? R : H;
 }
 
 template <bool BWD>
@@ -378,6 +490,7 @@ static int tiles_of(int C, int W, int H) {
 static int check_desc(const md2_vsl_desc* d, bool need_loss_inputs) {
     MD2_REQUIRE(d != nullptr, "null descriptor");
     MD2_REQUIRE(d->W >= 2 && d->H >= 2 && d->W <= 65535 && d->H <= 32767, "W, H must be in 2..65535 / 2..32767");
+    MD2_REQUIRE((long long)d->W * d->H * d->C < (1LL << 31), "one image must have fewer than 2^31 elements");
     MD2_REQUIRE(d->N >= 1, "N must be >= 1");
     MD2_REQUIRE(d->C == 1 || d->C == 3, "C must be 1 or 3");
     MD2_REQUIRE(d->S >= 1 && d->S <= MAX_S, "S must be 1 or 2");
@@ -458,8 +571,15 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     p.mode = mode;
     fill_pose_io(d, p.pose);
 
-    const int tiles = bwd ? tiles_of<true>(C, W, H) : tiles_of<false>(C, W, H);
+    static const bool use_tiles = [] { const char* e = getenv("MD2_KERNEL"); return e && !strcmp(e, "tile"); }();
+    p.m_R = choose_march_rows(W, H, L * N, bwd);
+    const int tiles = use_tiles ? (bwd ? tiles_of<true>(C, W, H) : tiles_of<false>(C, W, H))
+                                : cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);
     const int NP = NSTAT + 12 * S;
+    // this call's pose rows in the constant-memory table: a slot per ctx (re-entrant across ctxs)
+    const int pose_floats = 12 * S * N;
+    MD2_REQUIRE(pose_floats <= POSE_CONST_FLOATS, "S*N too large for one call (max 1024 source-image pairs)");
+    p.pose_slot = pose_floats <= POSE_SLOT_FLOATS ? ctx->pose_slot * POSE_SLOT_FLOATS : 0;
     const int bpi = max(1, min(256, cdiv((long long)W * H, 512)));
     const int LMAX = L == 1 ? 1 : (L <= 4 ? 4 : 8);
     float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
@@ -484,6 +604,9 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
 #undef MD2_PREP
         MD2_LAUNCH_CHECK(ctx);
     }
+    if (!use_tiles)
+        MD2_CHECK(cudaMemcpyToSymbolAsync(c_pose, pose_ab, sizeof(float) * pose_floats, sizeof(float) * p.pose_slot,
+                                          cudaMemcpyDeviceToDevice, st));
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {
@@ -498,8 +621,13 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
         ctx->prof_used += 2;
         MD2_CHECK(cudaEventRecord(ev0, st));
     }
-    if (bwd) { if (dispatch_fused<true>(ctx, C, S, p, st)) return 1; }
-    else     { if (dispatch_fused<false>(ctx, C, S, p, st)) return 1; }
+    if (use_tiles) {
+        if (bwd) { if (dispatch_fused<true>(ctx, C, S, p, st)) return 1; }
+        else     { if (dispatch_fused<false>(ctx, C, S, p, st)) return 1; }
+    } else {
+        if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
+        else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
+    }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
     return 0;
 }
@@ -686,6 +814,8 @@ int md2_create(int device, md2_ctx** out) {
     if (device < 0 || device >= count) return md2::set_error("md2_create: bad device %d", device);
     MD2_CHECK(cudaSetDevice(device));
     md2_ctx* c = new md2_ctx();
+    static std::atomic<int> next_slot{0};
+    c->pose_slot = next_slot.fetch_add(1) % (md2::POSE_CONST_FLOATS / md2::POSE_SLOT_FLOATS);
     c->device = device;
     c->launches = 0;
     *out = c;

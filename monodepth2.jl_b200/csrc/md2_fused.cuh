@@ -69,6 +69,9 @@ struct FusedParams {
     float* saved;                       // nullable copy of stats_out for a later bwd
     float* loss;                        // nullable device scalar
     PoseIO pose;
+    // marching-warp kernel (md2_march.cuh): rows per chunk, offset of this call's pose rows in the
+    // constant-memory pose table
+    int m_R, pose_slot;
 };
 
 template <int S>

@@ -3,12 +3,17 @@
 // on the CPU (one "thread" at a time, phase by phase) so that the halo / reflect / fold / reduction
 // logic of the fused CUDA kernel can be checked against the oracle in a container without a GPU.
 // All pointers in the descriptor are HOST pointers here.
+#include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 #include "../../include/md2.h"
 #include "../../monodepth2.jl_b200/csrc/md2_fused.cuh"
+#define MD2_WARP_EMU 1
+#include "warp_emu.h"
+#include "../../monodepth2.jl_b200/csrc/md2_march.cuh"
 
 using namespace md2;
 
@@ -50,8 +55,41 @@ static void run_tiles(const FusedParams& p, std::vector<float>& sums) {
     }
 }
 
+// marching-warp kernel (md2_march.cuh): every work item runs as 32 lockstep fibers
+template <int C, int S, bool BWD>
+static void run_march(const FusedParams& p, std::vector<float>& sums) {
+    using M = March<C, S, BWD>;
+    const int NP = M::NPART;
+    const int strips = (p.W + M::OW - 1) / M::OW, chunks = (p.H + p.m_R - 1) / p.m_R;
+    sums.assign((size_t)p.L * p.N * NP, 0.f);
+    std::vector<float> wsm(M::SMEM_FLOATS + 4);
+    float* wsm_al = (float*)(((uintptr_t)wsm.data() + 15) & ~(uintptr_t)15);
+    WarpEmu emu;
+    std::vector<float> lane_v(32 * 32);
+    for (int z = 0; z < p.L * p.N; ++z)
+        for (int cy = 0; cy < chunks; ++cy)
+            for (int sx = 0; sx < strips; ++sx) {
+                for (int k = 0; k < M::SMEM_FLOATS; ++k) wsm_al[k] = NAN;
+                emu.run([&](int lane) {
+                    float v[32];
+                    M::run(p, sx, cy, z, lane, wsm_al, v);
+                    for (int k = 0; k < 32; ++k) lane_v[lane * 32 + k] = v[k];
+                });
+                float* su = sums.data() + (size_t)z * NP;
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int k = 0; k < NP; ++k) su[k] += lane_v[lane * 32 + k];
+            }
+}
+
 template <bool BWD>
-static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums) {
+static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums, int variant) {
+    if (variant == 1) {
+        if (C == 1 && S == 1) { run_march<1, 1, BWD>(p, sums); return 0; }
+        if (C == 1 && S == 2) { run_march<1, 2, BWD>(p, sums); return 0; }
+        if (C == 3 && S == 1) { run_march<3, 1, BWD>(p, sums); return 0; }
+        if (C == 3 && S == 2) { run_march<3, 2, BWD>(p, sums); return 0; }
+        return 1;
+    }
     if (C == 1 && S == 1) { run_tiles<1, 1, BWD>(p, sums); return 0; }
     if (C == 1 && S == 2) { run_tiles<1, 2, BWD>(p, sums); return 0; }
     if (C == 3 && S == 1) { run_tiles<3, 1, BWD>(p, sums); return 0; }
@@ -59,8 +97,8 @@ static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums
     return 1;
 }
 
-// mode: 0 fwd, 1 bwd (uses d->saved), 2 fwdbwd
-extern "C" int md2_emul_vsl(const md2_vsl_desc* d, int mode, float gloss) {
+// mode: 0 fwd, 1 bwd (uses d->saved), 2 fwdbwd; variant: 0 tile phases, 1 marching warps (R rows per chunk)
+static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, int R) {
     const int W = d->W, H = d->H, N = d->N, L = d->L, S = d->S, C = d->C;
     const bool bwd = mode != 0;
     FusedParams p;
@@ -93,6 +131,8 @@ extern "C" int md2_emul_vsl(const md2_vsl_desc* d, int mode, float gloss) {
     for (int s = 0; s < S; ++s)
         for (int n = 0; n < N; ++n) prepare_pose_one(p.pose, s, n, ab.data() + ((size_t)s * N + n) * 12);
     p.pose_ab = ab.data();
+    p.pose_slot = 0;
+    p.m_R = R > 0 ? R : 32;
 
     std::vector<float> stats((size_t)L * N * NSTAT, 0.f);
     if (mode == 1) {
@@ -112,7 +152,7 @@ extern "C" int md2_emul_vsl(const md2_vsl_desc* d, int mode, float gloss) {
     p.stats = stats.data();
     std::vector<float> sums;
     const int NP = NSTAT + 12 * S;
-    if (bwd ? dispatch<true>(C, S, p, sums) : dispatch<false>(C, S, p, sums)) return 1;
+    if (bwd ? dispatch<true>(C, S, p, sums, variant) : dispatch<false>(C, S, p, sums, variant)) return 1;
 
     if (mode != 1) {
         for (int z = 0; z < L * N; ++z) {
@@ -137,3 +177,6 @@ extern "C" int md2_emul_vsl(const md2_vsl_desc* d, int mode, float gloss) {
     }
     return 0;
 }
+
+extern "C" int md2_emul_vsl(const md2_vsl_desc* d, int mode, float gloss) { return emul_vsl(d, mode, gloss, 0, 0); }
+extern "C" int md2_emul_march(const md2_vsl_desc* d, int mode, float gloss, int R) { return emul_vsl(d, mode, gloss, 1, R); }

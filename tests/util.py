@@ -137,7 +137,7 @@ def check_vsl_statistical(out, ref, source_ids=(0, 2), tag="", frac=0.995, pose_
     # hundreds of pixels per element through the upsample adjoint, so a flip is not local there
     stat(out["gdisp"][-1], ref["gdisp"][-1], "gdisp[full-res]")
     for i, (a, b) in enumerate(zip(out["gdisp"][:-1], ref["gdisp"][:-1])):
-        assert rel_l2(a, b) <= 2e-2, (tag, "gdisp", i, rel_l2(a, b))
+        assert rel_l2(a, b) <= 3e-2, (tag, "gdisp", i, rel_l2(a, b))
     for name in ("grvec", "gtvec"):
         for s, (a, b) in enumerate(zip(out[name], ref[name])):
             assert rel_max(a, b) <= pose_rtol, (tag, name, s, rel_max(a, b))
