@@ -28,6 +28,7 @@ enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, 
 struct md2_ctx {
     int device;
     int64_t launches;
+    int sm_count = 148;
     int pose_slot = 0;   // this ctx's slot in the constant-memory pose table (md2_march.cuh)
     md2::Workspace ws[MD2_WS_COUNT];
     // optional device timing of the dominant (fused tile) kernel, see md2_profile_*

@@ -70,33 +70,7 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ gout, float* __res
     if (i >= (long long)w * h * CN) return;
     const int xi = (int)(i % w), yi = (int)((i / w) % h);
     const long long cn = i / ((long long)w * h);
-    const float sx = up_scale(w, W), sy = up_scale(h, H);
-    int xlo = 0, xhi = W - 1, ylo = 0, yhi = H - 1;
-    if (sx > 0.f) {
-        xlo = max(0, (int)floorf((float)(xi - 1) / sx) - 1);
-        xhi = min(W - 1, (int)ceilf((float)(xi + 1) / sx) + 1);
-    }
-    if (sy > 0.f) {
-        ylo = max(0, (int)floorf((float)(yi - 1) / sy) - 1);
-        yhi = min(H - 1, (int)ceilf((float)(yi + 1) / sy) + 1);
-    }
-    const float* g = gout + cn * W * H;
-    float acc = 0.f;
-    for (int y = ylo; y <= yhi; ++y) {
-        int y0, y1; float fy;
-        up_taps(y, sy, h, y0, y1, fy);
-        const float wy = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
-        if (wy == 0.f) continue;
-        float row = 0.f;
-        for (int x = xlo; x <= xhi; ++x) {
-            int x0, x1; float fx;
-            up_taps(x, sx, w, x0, x1, fx);
-            const float wx = (x0 == xi ? 1.f - fx : 0.f) + (x1 == xi ? fx : 0.f);
-            row = fmaf(wx, g[y * W + x], row);
-        }
-        acc = fmaf(wy, row, acc);
-    }
-    gin[i] = acc;
+    gin[i] = upsample_adjoint_at(gout + cn * W * H, w, h, W, H, xi, yi);
 }
 
 // out[g][k] = sum_b partial[g][b][k], fixed order (deterministic).  NP <= 32.
@@ -147,33 +121,25 @@ __device__ __forceinline__ float warp_reduce_32(float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// prep kernel (one launch before the fused kernel):
-//   blockIdx.x <  bpi : smoothness / mean-disparity statistics of image blockIdx.y for every
-//                       scale (needed before the backward because d / mean(d) couples all
-//                       pixels of an image); the last block of an image
-//                       reduces the per-block partials in a fixed order (deterministic)
-//   blockIdx.x == bpi : [composeT +] pose pre-composition of image blockIdx.y, and zero fill of
-//                       the low-resolution disparity gradients the fused kernel accumulates into
+// prep kernel (one launch before the marching kernel):
+//   blockIdx.x <  bpi : a grid-stride pass over the pixels of image blockIdx.y that (a) writes the
+//                       align-corners bilinear upsample (A17) of every low-res disparity into its
+//                       full-resolution scratch and (b) for the fused fwd+bwd call accumulates the
+//                       smoothness / mean-disparity statistics of every scale (needed before the
+//                       backward because d / mean(d) couples all pixels of an image, SURVEY.md
+//                       appendix A.6); the last block of an image reduces the per-block partials in
+//                       a fixed order (deterministic)
+//   blockIdx.x == bpi : [composeT +] pose pre-composition of image blockIdx.y
 // ------------------------------------------------------------------------------------------
 template <int C, int LMAX>
 __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ FusedParams p, int bpi, int do_stats,
-                                                   int do_zero, float* __restrict__ pose_ab,
-                                                   float* __restrict__ part, float* __restrict__ stats,
-                                                   unsigned int* __restrict__ counters) {
+                                                   float* __restrict__ pose_ab, float* __restrict__ part,
+                                                   float* __restrict__ stats, unsigned int* __restrict__ counters) {
     const int n = blockIdx.y;
     if ((int)blockIdx.x == bpi) {
         if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
-        if (do_zero) {
-            for (int l = 0; l < p.L; ++l) {
-                if (p.dw[l] == p.W && p.dh[l] == p.H) continue;
-                const int cnt = p.dw[l] * p.dh[l];
-                float* g = p.gdisp[l] + (long long)n * cnt;
-                for (int i = threadIdx.x; i < cnt; i += blockDim.x) g[i] = 0.f;
-            }
-        }
         return;
     }
-    if (!do_stats) return;
     __shared__ float red[3 * LMAX * 8];
     __shared__ bool last;
     const int HW = p.W * p.H;
@@ -182,34 +148,41 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ Fused
     for (int k = 0; k < 3 * LMAX; ++k) v[k] = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += bpi * blockDim.x) {
         const int gx = i % p.W, gy = i / p.W;
-        const float* t = p.tgt + (long long)n * p.tgt_ns + i;
         const bool hx = gx + 1 < p.W, hy = gy + 1 < p.H;
         float wx = 0.f, wy = 0.f;
-        if (hx) {
-            float g = 0.f;
+        if (do_stats) {
+            const float* t = p.tgt + (long long)n * p.tgt_ns + i;
+            if (hx) {
+                float g = 0.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + 1]);
-            wx = __expf(-g * (1.0f / C));
-        }
-        if (hy) {
-            float g = 0.f;
+                for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + 1]);
+                wx = __expf(-g * (1.0f / C));
+            }
+            if (hy) {
+                float g = 0.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + p.W]);
-            wy = __expf(-g * (1.0f / C));
+                for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + p.W]);
+                wy = __expf(-g * (1.0f / C));
+            }
         }
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) {
             if (l >= p.L) break;
             const int dw = p.dw[l], dh = p.dh[l];
             const bool native = (dw == p.W && dh == p.H);
+            if (native && !do_stats) continue;
             const float* dp = p.disp[l] + (long long)n * dw * dh;
             const float usx = up_scale(dw, p.W), usy = up_scale(dh, p.H);
             const float d = disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy);
-            v[3 * l + 2] += d;
-            if (hx) v[3 * l + 0] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx + 1, gy)) * wx;
-            if (hy) v[3 * l + 1] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy + 1)) * wy;
+            if (!native) const_cast<float*>(p.dfull[l])[(long long)n * HW + i] = d;
+            if (do_stats) {
+                v[3 * l + 2] += d;
+                if (hx) v[3 * l + 0] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx + 1, gy)) * wx;
+                if (hy) v[3 * l + 1] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy + 1)) * wy;
+            }
         }
     }
+    if (!do_stats) return;
     block_sum<3 * LMAX>(v, red);
     if (threadIdx.x < 3 * LMAX) part[((long long)n * bpi + blockIdx.x) * (3 * LMAX) + threadIdx.x] = red[threadIdx.x * (blockDim.x >> 5)];
     __threadfence();
@@ -227,226 +200,134 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ Fused
     if (threadIdx.x == 0) counters[n] = 0u;
 }
 
-// ------------------------------------------------------------------------------------------
-// the fused tile kernel; the last block to finish reduces the partial sums and finalises the
-// loss and the pose gradients (fixed summation order => the loss is run-to-run deterministic)
-// ------------------------------------------------------------------------------------------
-template <int C, int S, bool BWD>
-__global__ void __launch_bounds__(FUSED_THREADS, BWD ? (C == 1 ? 5 : 3) : 4) fused_kernel(const __grid_constant__ FusedParams p) {
-    extern __shared__ float sm[];
-    using F = Fused<C, S, BWD>;
-    const int z = blockIdx.z, scale = z / p.N, n = z % p.N;
-    const int tx0 = blockIdx.x * F::TW, ty0 = blockIdx.y * F::TH;
-    const int tid = threadIdx.x;
-    const int tiles = gridDim.x * gridDim.y;
-    FusedAcc<S> acc;
-    acc.clear();
-    F::phase_load(p, sm, scale, n, tx0, ty0, tid);
-    __syncthreads();
-    F::phase_windows(p, sm, scale, n, tx0, ty0, tid, acc);
-    if (!BWD) {
-        F::phase_smooth_fwd(p, sm, tx0, ty0, tid, acc);
-    } else {
-        __syncthreads();
-        F::phase_pixel_bwd(p, sm, scale, n, tx0, ty0, tid, acc);
-        if (p.dw[scale] != p.W || p.dh[scale] != p.H) {
-            __syncthreads();
-            F::phase_down_a(p, sm, tid);
-            __syncthreads();
-            F::phase_down_b(p, sm, scale, n, tid);
-        }
-    }
-    __syncthreads();   // shared memory is re-used as reduction scratch from here on
-    constexpr int NP = F::NPART;
-    constexpr int NW = FUSED_THREADS / 32;
-    {
-        float v[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = 0.f;
-        v[0] = acc.warp_sum; v[1] = acc.sx; v[2] = acc.sy; v[3] = acc.dsum;
-        if (BWD) {
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-#pragma unroll
-                for (int k = 0; k < 12; ++k) v[NSTAT + 12 * s + k] = acc.pose[s][k];
-        }
-        const float tot = warp_reduce_32(v);
-        sm[(tid >> 5) * 32 + (tid & 31)] = tot;
-    }
-    __syncthreads();
-    const long long blk = ((long long)z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (tid < NP) {
-        float r = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) r += sm[w * 32 + tid];
-        p.partial[blk * NP + tid] = r;
-    }
-    // ---- last-block reductions ----
-    __shared__ int flag;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) flag = (atomicAdd(&p.counters[z], 1u) == (unsigned)(tiles - 1)) ? 1 : 0;
-    __syncthreads();
-    if (!flag) return;
-    __threadfence();
-    {   // this block finished image z last: reduce its tiles in a fixed order
-        const int k = tid & 31, chunk = tid >> 5;
-        float s = 0.f;
-        if (k < NP)
-            for (int b = chunk; b < tiles; b += NW) s += __ldcg(p.partial + ((long long)z * tiles + b) * NP + k);
-        sm[chunk * 32 + k] = s;
-        __syncthreads();
-        if (tid < NP) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) t += sm[w * 32 + tid];
-            p.sums[(long long)z * NP + tid] = t;
-        }
-    }
-    __threadfence();
-    __syncthreads();
-    const int LN = p.L * p.N;
-    if (tid == 0) {
-        p.counters[z] = 0u;
-        flag = (atomicAdd(&p.counters[LN], 1u) == (unsigned)(LN - 1)) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!flag) return;
-    __threadfence();
-    // ---- the very last block: loss, saved statistics, pose gradients ----
-    if (p.mode != 1) {
-        for (int zz = tid; zz < LN; zz += FUSED_THREADS) {
-            float* st = p.stats_out + (long long)zz * NSTAT;
-            st[0] = __ldcg(p.sums + (long long)zz * NP);
-            if (p.mode == 0) {
-                st[1] = __ldcg(p.sums + (long long)zz * NP + 1);
-                st[2] = __ldcg(p.sums + (long long)zz * NP + 2);
-                st[3] = __ldcg(p.sums + (long long)zz * NP + 3);
-            }
-            if (p.saved && p.saved != p.stats_out)
-                for (int k = 0; k < NSTAT; ++k) p.saved[(long long)zz * NSTAT + k] = st[k];
-        }
-        __syncthreads();
-        if (tid == 0 && p.loss)
-            *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
-    }
-    if (BWD) {
-        for (int i = tid; i < S * p.N; i += FUSED_THREADS) {
-            const int s = i / p.N, nn = i % p.N;
-            double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
-            for (int l = 0; l < p.L; ++l) {
-                const float* su = p.sums + ((long long)l * p.N + nn) * NP + NSTAT + 12 * s;
-                for (int k = 0; k < 9; ++k) G[k] += __ldcg(su + k);
-                for (int k = 0; k < 3; ++k) h[k] += __ldcg(su + 9 + k);
-            }
-            finalize_pose(p.pose, s, nn, G, h);
-        }
-    }
-    if (tid == 0) p.counters[LN] = 0u;
+// adjoint of the upsample for the low-res decoder scales (after the marching kernel): gather form,
+// one thread per low-res pixel, deterministic.  grid (x-blocks, low-res scale index, N)
+__global__ void __launch_bounds__(128) down_adjoint_kernel(const __grid_constant__ FusedParams p) {
+    int l = -1;
+    for (int k = 0, seen = -1; k < p.L; ++k)
+        if (p.dw[k] != p.W || p.dh[k] != p.H) { if (++seen == (int)blockIdx.y) { l = k; break; } }
+    if (l < 0) return;
+    const int w = p.dw[l], h = p.dh[l], n = blockIdx.z;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    p.gdisp[l][(long long)n * w * h + i] =
+        upsample_adjoint_at(p.gfull[l] + (long long)n * p.W * p.H, w, h, p.W, p.H, i % w, i / w);
 }
 
 // ------------------------------------------------------------------------------------------
-// the marching-warp kernel (md2_march.cuh): one warp per block, grid (strips, chunks, L*N).
-// The last warp of a (scale, image) reduces that group's partial sums in a fixed order, the
-// very last warp finalises the loss and the pose gradients (deterministic loss).
+// the marching-warp kernel (md2_march.cuh), persistent: one-warp blocks, as many as are resident
+// on the whole GPU; block b walks the work items (strip, chunk, scale, image) b, b + grid, ...  The last warp to finish an item of a (scale, image) reduces that group's
+// partial sums in a fixed order, the very last one finalises the loss and the pose gradients
+// (deterministic loss).
 // ------------------------------------------------------------------------------------------
 template <int C, int S, bool BWD>
-__global__ void __launch_bounds__(32, BWD ? (C == 1 ? 16 : 10) : 16) march_kernel(const __grid_constant__ FusedParams p) {
+struct MarchCfg {
+    // resident one-warp blocks per SM the kernel is compiled for, and the register budget that
+    // lets exactly that many fit (65536 / (WARPS * 32), rounded down to the allocation unit of 8)
+    static constexpr int WARPS = BWD ? (C == 1 ? 13 : 8) : 13;
+    static constexpr int MAXREG = (65536 / (WARPS * 32)) / 8 * 8;
+};
+
+template <int C, int S, bool BWD>
+__global__ void __maxnreg__((MarchCfg<C, S, BWD>::MAXREG))
+march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
     extern __shared__ __align__(16) float wsm[];
     using M = March<C, S, BWD>;
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x;
-    const int z = blockIdx.z;
-    const int ipg = gridDim.x * gridDim.y;
-    {
-        float v[32];
-        M::run(p, blockIdx.x, blockIdx.y, z, lane, wsm, v);
-        const float tot = warp_reduce_32(v);
-        const long long item = (long long)z * ipg + blockIdx.y * gridDim.x + blockIdx.x;
-        if (lane < NP) p.partial[item * NP + lane] = tot;
-    }
-    __threadfence();
-    __syncwarp();
-    int flag = 0;
-    if (lane == 0) flag = (atomicAdd(&p.counters[z], 1u) == (unsigned)(ipg - 1)) ? 1 : 0;
-    flag = __shfl_sync(0xffffffffu, flag, 0);
-    if (!flag) return;
-    __threadfence();
-    if (lane < NP) {   // this warp finished (scale, image) z last: reduce its items in a fixed order
-        float s0 = 0.f, s1 = 0.f;
-        const float* pp = p.partial + (long long)z * ipg * NP + lane;
-        int b = 0;
-        for (; b + 1 < ipg; b += 2) { s0 += __ldcg(pp + (long long)b * NP); s1 += __ldcg(pp + (long long)(b + 1) * NP); }
-        if (b < ipg) s0 += __ldcg(pp + (long long)b * NP);
-        p.sums[(long long)z * NP + lane] = s0 + s1;
-    }
-    __threadfence();
-    __syncwarp();
+    const int ipg = strips * chunks;
     const int LN = p.L * p.N;
-    if (lane == 0) {
-        p.counters[z] = 0u;
-        flag = (atomicAdd(&p.counters[LN], 1u) == (unsigned)(LN - 1)) ? 1 : 0;
-    }
-    flag = __shfl_sync(0xffffffffu, flag, 0);
-    if (!flag) return;
-    __threadfence();
-    // ---- the very last warp: loss, saved statistics, pose gradients ----
-    if (p.mode != 1) {
-        for (int zz = lane; zz < LN; zz += 32) {
-            float* st = p.stats_out + (long long)zz * NSTAT;
-            st[0] = __ldcg(p.sums + (long long)zz * NP);
-            if (p.mode == 0) {
-                st[1] = __ldcg(p.sums + (long long)zz * NP + 1);
-                st[2] = __ldcg(p.sums + (long long)zz * NP + 2);
-                st[3] = __ldcg(p.sums + (long long)zz * NP + 3);
-            }
-            if (p.saved && p.saved != p.stats_out)
-                for (int k = 0; k < NSTAT; ++k) p.saved[(long long)zz * NSTAT + k] = st[k];
+    const int items = ipg * LN;
+    // one warp per block so that everything derived from the item index is warp-uniform for the
+    // compiler (uniform registers / constant-bank operands); the grid is exactly the number of
+    // blocks resident on the whole GPU, so every SM gets the same number of items
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int z = it / ipg, rem = it - z * ipg;
+        const int cy = rem / strips, sx = rem - cy * strips;
+        {
+            float v[32];
+            M::run(p, sx, cy, z, lane, wsm, v);
+            const float tot = warp_reduce_32(v);
+            if (lane < NP) p.partial[(long long)it * NP + lane] = tot;
         }
-        __threadfence_block();
+        __threadfence();
         __syncwarp();
-        if (lane == 0 && p.loss)
-            *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
-    }
-    if (BWD) {
-        for (int i = lane; i < S * p.N; i += 32) {
-            const int s = i / p.N, nn = i % p.N;
-            double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
-            for (int l = 0; l < p.L; ++l) {
-                const float* su = p.sums + ((long long)l * p.N + nn) * NP + NSTAT + 12 * s;
-                for (int k = 0; k < 9; ++k) G[k] += __ldcg(su + k);
-                for (int k = 0; k < 3; ++k) h[k] += __ldcg(su + 9 + k);
-            }
-            finalize_pose(p.pose, s, nn, G, h);
+        int flag = 0;
+        if (lane == 0) flag = (atomicAdd(&p.counters[z], 1u) == (unsigned)(ipg - 1)) ? 1 : 0;
+        flag = __shfl_sync(0xffffffffu, flag, 0);
+        if (!flag) continue;
+        __threadfence();
+        if (lane < NP) {   // this warp finished (scale, image) z last: reduce its items in a fixed order
+            float s0 = 0.f, s1 = 0.f;
+            const float* pp = p.partial + (long long)z * ipg * NP + lane;
+            int b = 0;
+            for (; b + 1 < ipg; b += 2) { s0 += __ldcg(pp + (long long)b * NP); s1 += __ldcg(pp + (long long)(b + 1) * NP); }
+            if (b < ipg) s0 += __ldcg(pp + (long long)b * NP);
+            p.sums[(long long)z * NP + lane] = s0 + s1;
         }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            p.counters[z] = 0u;
+            flag = (atomicAdd(&p.counters[LN], 1u) == (unsigned)(LN - 1)) ? 1 : 0;
+        }
+        flag = __shfl_sync(0xffffffffu, flag, 0);
+        if (!flag) continue;
+        __threadfence();
+        // ---- the very last warp: loss, saved statistics, pose gradients ----
+        if (p.mode != 1) {
+            for (int zz = lane; zz < LN; zz += 32) {
+                float* st = p.stats_out + (long long)zz * NSTAT;
+                st[0] = __ldcg(p.sums + (long long)zz * NP);
+                if (p.mode == 0) {
+                    st[1] = __ldcg(p.sums + (long long)zz * NP + 1);
+                    st[2] = __ldcg(p.sums + (long long)zz * NP + 2);
+                    st[3] = __ldcg(p.sums + (long long)zz * NP + 3);
+                }
+                if (p.saved && p.saved != p.stats_out)
+                    for (int k = 0; k < NSTAT; ++k) p.saved[(long long)zz * NSTAT + k] = st[k];
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0 && p.loss)
+                *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
+        }
+        if (BWD) {
+            for (int i = lane; i < S * p.N; i += 32) {
+                const int s = i / p.N, nn = i % p.N;
+                double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
+                for (int l = 0; l < p.L; ++l) {
+                    const float* su = p.sums + ((long long)l * p.N + nn) * NP + NSTAT + 12 * s;
+                    for (int k = 0; k < 9; ++k) G[k] += __ldcg(su + k);
+                    for (int k = 0; k < 3; ++k) h[k] += __ldcg(su + 9 + k);
+                }
+                finalize_pose(p.pose, s, nn, G, h);
+            }
+        }
+        if (lane == 0) p.counters[LN] = 0u;
     }
-    if (lane == 0) p.counters[LN] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
 template <int C, int S, bool BWD>
-static int launch_fused(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
-    using F = Fused<C, S, BWD>;
-    static bool configured = false;
-    const size_t smem = sizeof(float) * (size_t)F::SMEM_FLOATS;
-    if (!configured) {
-        MD2_CHECK(cudaFuncSetAttribute(fused_kernel<C, S, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    dim3 grid(cdiv(p.W, F::TW), cdiv(p.H, F::TH), p.L * p.N);
-    fused_kernel<C, S, BWD><<<grid, FUSED_THREADS, smem, st>>>(p);
-    MD2_LAUNCH_CHECK(ctx);
-    return 0;
-}
-
-template <int C, int S, bool BWD>
 static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     using M = March<C, S, BWD>;
     const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
-    dim3 grid(cdiv(p.W, M::OW), cdiv(p.H, p.m_R), p.L * p.N);
-    march_kernel<C, S, BWD><<<grid, 32, smem, st>>>(p);
+    static int resident = 0;   // one-warp blocks resident per SM
+    if (!resident) {
+        MD2_CHECK(cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MD2_CHECK(cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int occ = 0;
+        MD2_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_kernel<C, S, BWD>, 32, smem));
+        resident = occ > 0 ? occ : 1;
+    }
+    const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R);
+    const long long items = (long long)strips * chunks * p.L * p.N;
+    const long long cap = (long long)ctx->sm_count * resident;
+    const int blocks = (int)(items < cap ? items : cap);
+    march_kernel<C, S, BWD><<<blocks, 32, smem, st>>>(p, strips, chunks);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -460,31 +341,28 @@ static int dispatch_march(md2_ctx* ctx, int C, int S, const FusedParams& p, cuda
     return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
 }
 
-// rows per chunk of the marching kernel: long chunks amortise the 2*HALO warm-up rows, short ones
-// give enough warps to fill 148 SMs x ~16 resident warps
-static int choose_march_rows(int W, int H, int LN, bool bwd) {
+// rows per chunk of the marching kernel.  Long chunks amortise the 2*HALO warm-up rows; the item
+// count should fill the resident warps of all SMs evenly (one block per SM, `warps` warps each):
+// time ~ max(throughput term, longest per-warp chain), both in row-iterations.
+static int choose_march_rows(int W, int H, int LN, bool bwd, int sms, int warps) {
     static const int env = [] { const char* e = getenv("MD2_MARCH_ROWS"); return e ? atoi(e) : 0; }();
     if (env > 0) return env < H ? env : H;
-    const int ow = bwd ? 28 : 30;
-    const long long strips = cdiv(W, ow);
-    int R = 32;
-    while (R > 8 && strips * cdiv(H, R) * LN < 148LL * 12) R -= 8;
-    return R < H ? R : H;
-}
-
-template <bool BWD>
-static int dispatch_fused(md2_ctx* ctx, int C, int S, const FusedParams& p, cudaStream_t st) {
-    if (C == 1 && S == 1) return launch_fused<1, 1, BWD>(ctx, p, st);
-    if (C == 1 && S == 2) return launch_fused<1, 2, BWD>(ctx, p, st);
-    if (C == 3 && S == 1) return launch_fused<3, 1, BWD>(ctx, p, st);
-    if (C == 3 && S == 2) return launch_fused<3, 2, BWD>(ctx, p, st);
-    return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
-}
-
-template <bool BWD>
-static int tiles_of(int C, int W, int H) {
-    const int tw = BWD ? 30 : 32, th = 16;
-    return cdiv(W, tw) * cdiv(H, th);
+    const int ow = bwd ? 28 : 30, halo = bwd ? 2 : 1;
+    const long long base = (long long)cdiv(W, ow) * LN;
+    int best_R = H;
+    double best = 1e30;
+    for (int chunks = 1; chunks <= H; ++chunks) {
+        const int R = cdiv(H, chunks);
+        if (R < 8 && chunks > 1) break;
+        if (cdiv(H, R) != chunks) continue;
+        const long long per_sm = (base * chunks + sms - 1) / sms;
+        const double rows = R + 2 * halo + 1.5;
+        const double thr = (double)per_sm * rows / warps;
+        const double chain = (double)((per_sm + warps - 1) / warps) * rows;
+        const double cost = thr > chain ? thr : chain;
+        if (cost < best - 1e-9) { best = cost; best_R = R; }
+    }
+    return best_R;
 }
 
 static int check_desc(const md2_vsl_desc* d, bool need_loss_inputs) {
@@ -557,13 +435,30 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
         const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
         p.depth_a = maxd - mind; p.depth_b = mind;
     }
-    bool any_low = false;
+    int n_low = 0, max_low = 0;
     for (int l = 0; l < L; ++l) {
         p.smooth_w[l] = d->smooth_weight[l];
         p.disp[l] = d->disparity[l]; p.dw[l] = d->disp_w[l]; p.dh[l] = d->disp_h[l];
         p.gdisp[l] = bwd ? d->grad_disparity[l] : nullptr;
         if (bwd) MD2_REQUIRE(d->grad_disparity[l] != nullptr, "null grad_disparity");
-        any_low = any_low || d->disp_w[l] != W || d->disp_h[l] != H;
+        if (d->disp_w[l] != W || d->disp_h[l] != H) {
+            ++n_low;
+            max_low = max(max_low, d->disp_w[l] * d->disp_h[l]);
+        }
+    }
+    {   // full-resolution views of every scale: the caller's buffers for native-size scales, L2-resident
+        // scratch (upsampled disparity; full-resolution gradient before its adjoint down-sampling) otherwise
+        const size_t img = (size_t)N * W * H;
+        float* dscr = n_low ? (float*)ws_get(ctx, MD2_WS_DISP, sizeof(float) * img * n_low) : nullptr;
+        float* gscr = (n_low && bwd) ? (float*)ws_get(ctx, MD2_WS_GDISP, sizeof(float) * img * n_low) : nullptr;
+        if (n_low && (!dscr || (bwd && !gscr))) return 1;
+        int k = 0;
+        for (int l = 0; l < L; ++l) {
+            const bool native = d->disp_w[l] == W && d->disp_h[l] == H;
+            p.dfull[l] = native ? d->disparity[l] : dscr + img * k;
+            p.gfull[l] = !bwd ? nullptr : (native ? d->grad_disparity[l] : gscr + img * k);
+            if (!native) ++k;
+        }
     }
     p.loss_scale = d->loss_scale;
     p.gloss = gloss;
@@ -571,10 +466,8 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     p.mode = mode;
     fill_pose_io(d, p.pose);
 
-    static const bool use_tiles = [] { const char* e = getenv("MD2_KERNEL"); return e && !strcmp(e, "tile"); }();
-    p.m_R = choose_march_rows(W, H, L * N, bwd);
-    const int tiles = use_tiles ? (bwd ? tiles_of<true>(C, W, H) : tiles_of<false>(C, W, H))
-                                : cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);
+    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, bwd ? (C == 1 ? 13 : 8) : 13);
+    const int tiles = cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
     const int NP = NSTAT + 12 * S;
     // this call's pose rows in the constant-memory table: a slot per ctx (re-entrant across ctxs)
     const int pose_floats = 12 * S * N;
@@ -594,19 +487,18 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     if (mode == MODE_BWD && d->saved) p.stats = d->saved;   // else the ctx holds the last forward's statistics
     p.loss = (mode == MODE_BWD) ? nullptr : d->loss;
 
-    {   // prep: poses (+ zero fill of low-res gradients, + statistics pre-pass for the fused fwd+bwd)
-        const int do_stats = mode == MODE_FWDBWD, do_zero = bwd && any_low;
-        dim3 g(bpi + 1, N);
+    {   // prep: poses, upsampled low-res disparities (+ statistics pre-pass for the fused fwd+bwd)
+        const int do_stats = mode == MODE_FWDBWD;
+        dim3 g((do_stats || n_low) ? bpi + 1 : 1, N);
         unsigned int* pc = counters + L * N + 1;
-#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 256, 0, st>>>(p, bpi, do_stats, do_zero, pose_ab, part2, stats, pc)
+#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 256, 0, st>>>(p, (int)g.x - 1, do_stats, pose_ab, part2, stats, pc)
         if (C == 1) { if (LMAX == 1) MD2_PREP(1, 1); else if (LMAX == 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
         else        { if (LMAX == 1) MD2_PREP(3, 1); else if (LMAX == 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
 #undef MD2_PREP
         MD2_LAUNCH_CHECK(ctx);
     }
-    if (!use_tiles)
-        MD2_CHECK(cudaMemcpyToSymbolAsync(c_pose, pose_ab, sizeof(float) * pose_floats, sizeof(float) * p.pose_slot,
-                                          cudaMemcpyDeviceToDevice, st));
+    MD2_CHECK(cudaMemcpyToSymbolAsync(c_pose, pose_ab, sizeof(float) * pose_floats, sizeof(float) * p.pose_slot,
+                                      cudaMemcpyDeviceToDevice, st));
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {
@@ -621,14 +513,14 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
         ctx->prof_used += 2;
         MD2_CHECK(cudaEventRecord(ev0, st));
     }
-    if (use_tiles) {
-        if (bwd) { if (dispatch_fused<true>(ctx, C, S, p, st)) return 1; }
-        else     { if (dispatch_fused<false>(ctx, C, S, p, st)) return 1; }
-    } else {
-        if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
-        else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
-    }
+    if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
+    else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
+    if (bwd && n_low) {   // low-res decoder scales: adjoint of the upsample, gather form (deterministic)
+        dim3 g(cdiv(max_low, 128), n_low, N);
+        down_adjoint_kernel<<<g, 128, 0, st>>>(p);
+        MD2_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 
@@ -660,7 +552,7 @@ __global__ void pose_final_kernel(PoseIO io, int S, int N, int NP, const float* 
 
 template <int C, int S>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const __grid_constant__ FusedParams p, WarpIO io) {
-    using F = Fused<C, S, false>;
+    using F = Sampler<C>;
     const long long HW = (long long)p.W * p.H;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= HW * p.N) return;
@@ -679,7 +571,7 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const __grid_constant__ F
 
 template <int C, int S>
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const __grid_constant__ FusedParams p, WarpIO io) {
-    using F = Fused<C, S, true>;
+    using F = Sampler<C>;
     __shared__ float scratch[(NSTAT + 12 * S) * 8];
     const long long HW = (long long)p.W * p.H;
     const int n = blockIdx.y;
@@ -818,6 +710,8 @@ int md2_create(int device, md2_ctx** out) {
     c->pose_slot = next_slot.fetch_add(1) % (md2::POSE_CONST_FLOATS / md2::POSE_SLOT_FLOATS);
     c->device = device;
     c->launches = 0;
+    c->sm_count = 148;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
     return 0;
 }

@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or shipped with the product.
-// Runs the __host__ __device__ tile phases of monodepth2.jl_b200/csrc/md2_fused.cuh sequentially
-// on the CPU (one "thread" at a time, phase by phase) so that the halo / reflect / fold / reduction
-// logic of the fused CUDA kernel can be checked against the oracle in a container without a GPU.
+// Runs the marching-warp kernel source (monodepth2.jl_b200/csrc/md2_march.cuh) on the CPU, every warp as
+// 32 lockstep fibers (warp_emu.h), plus the host versions of the prep / adjoint steps around it, so that
+// the halo / reflect / rolling-window / scatter logic of the fused CUDA kernel can be checked against the
+// oracle in a container without a GPU.
 // All pointers in the descriptor are HOST pointers here.
 #include <math.h>
 #include <stdint.h>
@@ -16,44 +17,6 @@
 #include "../../monodepth2.jl_b200/csrc/md2_march.cuh"
 
 using namespace md2;
-
-template <int C, int S, bool BWD>
-static void run_tiles(const FusedParams& p, std::vector<float>& sums) {
-    using F = Fused<C, S, BWD>;
-    const int NP = F::NPART;
-    const int tw = (p.W + F::TW - 1) / F::TW, th = (p.H + F::TH - 1) / F::TH;
-    sums.assign((size_t)p.L * p.N * NP, 0.f);
-    std::vector<float> sm(F::SMEM_FLOATS);
-    std::vector<FusedAcc<S>> acc(FUSED_THREADS);
-    for (int z = 0; z < p.L * p.N; ++z) {
-        const int scale = z / p.N, n = z % p.N;
-        const bool native = p.dw[scale] == p.W && p.dh[scale] == p.H;
-        for (int by = 0; by < th; ++by)
-            for (int bx = 0; bx < tw; ++bx) {
-                const int tx0 = bx * F::TW, ty0 = by * F::TH;
-                for (auto& v : sm) v = NAN;   // poison: catches reads of never-written shared memory
-                for (auto& a : acc) a.clear();
-                for (int t = 0; t < FUSED_THREADS; ++t) F::phase_load(p, sm.data(), scale, n, tx0, ty0, t);
-                for (int t = 0; t < FUSED_THREADS; ++t) F::phase_windows(p, sm.data(), scale, n, tx0, ty0, t, acc[t]);
-                if (!BWD) {
-                    for (int t = 0; t < FUSED_THREADS; ++t) F::phase_smooth_fwd(p, sm.data(), tx0, ty0, t, acc[t]);
-                } else {
-                    for (int t = 0; t < FUSED_THREADS; ++t) F::phase_pixel_bwd(p, sm.data(), scale, n, tx0, ty0, t, acc[t]);
-                    if (!native) {
-                        for (int t = 0; t < FUSED_THREADS; ++t) F::phase_down_a(p, sm.data(), t);
-                        for (int t = 0; t < FUSED_THREADS; ++t) F::phase_down_b(p, sm.data(), scale, n, t);
-                    }
-                }
-                float* su = sums.data() + (size_t)z * NP;
-                for (int t = 0; t < FUSED_THREADS; ++t) {
-                    su[0] += acc[t].warp_sum; su[1] += acc[t].sx; su[2] += acc[t].sy; su[3] += acc[t].dsum;
-                    if (BWD)
-                        for (int s = 0; s < S; ++s)
-                            for (int k = 0; k < 12; ++k) su[NSTAT + 12 * s + k] += acc[t].pose[s][k];
-                }
-            }
-    }
-}
 
 // marching-warp kernel (md2_march.cuh): every work item runs as 32 lockstep fibers
 template <int C, int S, bool BWD>
@@ -90,10 +53,6 @@ static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums
         if (C == 3 && S == 2) { run_march<3, 2, BWD>(p, sums); return 0; }
         return 1;
     }
-    if (C == 1 && S == 1) { run_tiles<1, 1, BWD>(p, sums); return 0; }
-    if (C == 1 && S == 2) { run_tiles<1, 2, BWD>(p, sums); return 0; }
-    if (C == 3 && S == 1) { run_tiles<3, 1, BWD>(p, sums); return 0; }
-    if (C == 3 && S == 2) { run_tiles<3, 2, BWD>(p, sums); return 0; }
     return 1;
 }
 
@@ -117,8 +76,22 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
         p.smooth_w[l] = d->smooth_weight[l];
         p.disp[l] = d->disparity[l]; p.dw[l] = d->disp_w[l]; p.dh[l] = d->disp_h[l];
         p.gdisp[l] = bwd ? d->grad_disparity[l] : nullptr;
-        if (bwd && (p.dw[l] != W || p.dh[l] != H))   // the prep kernel zero-fills the accumulated low-res gradients
-            memset(d->grad_disparity[l], 0, sizeof(float) * (size_t)N * p.dw[l] * p.dh[l]);
+    }
+    // full-resolution views of every scale (what the prep kernel / ctx scratch provide on the device)
+    std::vector<std::vector<float>> dscr(L), gscr(L);
+    for (int l = 0; l < L; ++l) {
+        const bool native = p.dw[l] == W && p.dh[l] == H;
+        if (native) { p.dfull[l] = p.disp[l]; p.gfull[l] = p.gdisp[l]; continue; }
+        dscr[l].resize((size_t)N * W * H);
+        gscr[l].assign((size_t)N * W * H, NAN);
+        const float usx = up_scale(p.dw[l], W), usy = up_scale(p.dh[l], H);
+        for (int n = 0; n < N; ++n)
+            for (int gy = 0; gy < H; ++gy)
+                for (int gx = 0; gx < W; ++gx)
+                    dscr[l][((size_t)n * H + gy) * W + gx] =
+                        disp_fullres(p.disp[l] + (size_t)n * p.dw[l] * p.dh[l], p.dw[l], p.dh[l], false, usx, usy, W, gx, gy);
+        p.dfull[l] = dscr[l].data();
+        p.gfull[l] = bwd ? gscr[l].data() : nullptr;
     }
     p.loss_scale = d->loss_scale; p.gloss = gloss; p.normalize_disp = d->normalize_disparity;
     p.mode = mode;
@@ -153,6 +126,14 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
     std::vector<float> sums;
     const int NP = NSTAT + 12 * S;
     if (bwd ? dispatch<true>(C, S, p, sums, variant) : dispatch<false>(C, S, p, sums, variant)) return 1;
+    if (bwd)   // adjoint of the upsample for the low-res scales (down_adjoint_kernel on the device)
+        for (int l = 0; l < L; ++l) {
+            if (p.dw[l] == W && p.dh[l] == H) continue;
+            const int w = p.dw[l], h = p.dh[l];
+            for (int n = 0; n < N; ++n)
+                for (int i = 0; i < w * h; ++i)
+                    p.gdisp[l][(size_t)n * w * h + i] = upsample_adjoint_at(p.gfull[l] + (size_t)n * W * H, w, h, W, H, i % w, i / w);
+        }
 
     if (mode != 1) {
         for (int z = 0; z < L * N; ++z) {

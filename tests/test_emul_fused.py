@@ -33,6 +33,27 @@ def test_fused_statistical_on_arbitrary_inputs(N, C, H, W, am):
     check_vsl_statistical(out, ref, tag=f"{N},{C},{H},{W},{am}")
 
 
+@pytest.mark.parametrize("R", [8, 32])
+def test_stress_poses_strict(R):
+    (x, disps, rv, tv, K, invK), seed = well_conditioned_batch(1, 3, 24, 40, True, pose_sigma=0.1)
+    ref = oracle_vsl(x, disps, rv, tv, K, invK, automask=True)
+    out = emul_vsl(x, disps, rv, tv, K, invK, mode=2, automask=ref["auto"].float().contiguous(), R=R)
+    out["loss"] = out["loss"].item()
+    check_vsl(out, ref, tag=f"stress strict seed={seed}")
+
+
+@pytest.mark.parametrize("R", [4, 12, 64])
+def test_chunk_height_does_not_change_results(R):
+    """rows per chunk only re-partitions the work: same loss / gradients for any R"""
+    x, disps, rv, tv = O.synthetic_batch(1, 1, 40, 70, seed=9)
+    K, invK = O.make_K(70, 40)
+    a = emul_vsl(x, disps, rv, tv, K, invK, mode=2, R=R)
+    b = emul_vsl(x, disps, rv, tv, K, invK, mode=2, R=32)
+    assert abs(a["loss"].item() - b["loss"].item()) <= 2e-6 * abs(b["loss"].item())
+    for u, v in zip(a["gdisp"] + a["grvec"] + a["gtvec"] + [a["gx"]], b["gdisp"] + b["grvec"] + b["gtvec"] + [b["gx"]]):
+        assert rel_l2(u, v) < 2e-2     # (a tie flip would show up as ~1e-2 on a 70x40 image; rounding alone is ~1e-6)
+
+
 def test_fwd_then_bwd_equals_fused():
     x, disps, rv, tv = O.synthetic_batch(1, 3, 32, 64, seed=5)
     K, invK = O.make_K(64, 32)
