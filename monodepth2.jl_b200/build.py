@@ -22,7 +22,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + SOURCES
+    extra = os.environ.get("MD2_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DMD2_PREFETCH=0
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc build of libmd2_b200.so failed:\n" + r.stdout + r.stderr)

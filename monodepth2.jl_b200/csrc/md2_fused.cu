@@ -121,97 +121,177 @@ __device__ __forceinline__ float warp_reduce_32(float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// prep kernel (one launch before the marching kernel):
-//   blockIdx.x <  bpi : a grid-stride pass over the pixels of image blockIdx.y that (a) writes the
-//                       align-corners bilinear upsample (A17) of every low-res disparity into its
-//                       full-resolution scratch and (b) for the fused fwd+bwd call accumulates the
-//                       smoothness / mean-disparity statistics of every scale (needed before the
-//                       backward because d / mean(d) couples all pixels of an image, SURVEY.md
-//                       appendix A.6); the last block of an image reduces the per-block partials in
-//                       a fixed order (deterministic)
-//   blockIdx.x == bpi : [composeT +] pose pre-composition of image blockIdx.y
+// prep kernel (one launch before the marching kernel), grid (warp groups + 1, N):
+//   blockIdx.x <  gridDim.x-1 : four warps, each marching down a 31-column strip chunk of image
+//       blockIdx.y (lane = column, lane 31 = right-hand halo): (a) writes the align-corners
+//       bilinear upsample (A17) of every low-res disparity into its full-resolution scratch and
+//       (b) for the fused fwd+bwd call accumulates the smoothness / mean-disparity statistics of
+//       every scale (needed before the backward because d / mean(d) couples all pixels of an
+//       image; the edge weights exp(-|dT|) are shared by the scales).
+//       Right neighbours come from the next lane, lower neighbours from the next row of the
+//       march, so every disparity is interpolated once.  The last warp of an image reduces the
+//       per-warp partials in a fixed order (deterministic).
+//   blockIdx.x == gridDim.x-1 : [composeT +] pose pre-composition of image blockIdx.y
 // ------------------------------------------------------------------------------------------
+constexpr int PREP_COLS = 31;
+
 template <int C, int LMAX>
-__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ FusedParams p, int bpi, int do_stats,
-                                                   float* __restrict__ pose_ab, float* __restrict__ part,
+__global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int R,
+                                                   int do_stats, float* __restrict__ pose_ab, float* __restrict__ part,
                                                    float* __restrict__ stats, unsigned int* __restrict__ counters) {
     const int n = blockIdx.y;
-    if ((int)blockIdx.x == bpi) {
+    if (blockIdx.x == gridDim.x - 1) {
         if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
         return;
     }
-    __shared__ float red[3 * LMAX * 8];
-    __shared__ bool last;
-    const int HW = p.W * p.H;
-    float v[3 * LMAX];
+    const int lane = threadIdx.x & 31;
+    const int wpi = strips * chunks;                         // warps (work items) per image
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= wpi) return;
+    const int W = p.W, H = p.H, HW = W * H;
+    const int cy = w / strips, sx = w - cy * strips;
+    const int gx = sx * PREP_COLS + lane;
+    const int gxc = gx < W ? gx : W - 1;
+    const bool own_col = lane < PREP_COLS && gx < W;
+    const bool has_right = own_col && gx + 1 < W;
+    const int Y0 = cy * R, Y1 = min(Y0 + R, H);
+    const float* tg = p.tgt + (long long)n * p.tgt_ns + gxc;
+    // per-lane horizontal taps of every low-res scale
+    int xa0[LMAX], xa1[LMAX];
+    float fxu[LMAX], usy[LMAX];
+    bool native[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+        xa0[l] = xa1[l] = 0; fxu[l] = 0.f; usy[l] = 0.f; native[l] = true;
+        if (l < p.L) {
+            native[l] = (p.dw[l] == W && p.dh[l] == H);
+            usy[l] = up_scale(p.dh[l], H);
+            if (!native[l]) up_taps(gxc, up_scale(p.dw[l], W), p.dw[l], xa0[l], xa1[l], fxu[l]);
+        }
+    }
+    float v[3 * LMAX], dprev[LMAX], tprev[C];
 #pragma unroll
     for (int k = 0; k < 3 * LMAX; ++k) v[k] = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += bpi * blockDim.x) {
-        const int gx = i % p.W, gy = i / p.W;
-        const bool hx = gx + 1 < p.W, hy = gy + 1 < p.H;
-        float wx = 0.f, wy = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) dprev[l] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) tprev[c] = 0.f;
+    const int ylast = Y1 < H ? Y1 : H - 1;                   // one extra row below the chunk as lower neighbour
+    for (int y = Y0; y <= ylast; ++y) {
+        const bool own_row = y < Y1;
+        float t[C], wy = 0.f, wx = 0.f;
         if (do_stats) {
-            const float* t = p.tgt + (long long)n * p.tgt_ns + i;
-            if (hx) {
-                float g = 0.f;
+            float gyv = 0.f, gxv = 0.f;
 #pragma unroll
-                for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + 1]);
-                wx = __expf(-g * (1.0f / C));
+            for (int c = 0; c < C; ++c) {
+                t[c] = tg[(long long)c * HW + y * W];
+                gyv += fabsf(tprev[c] - t[c]);
+                gxv += fabsf(t[c] - __shfl_down_sync(0xffffffffu, t[c], 1));
+                tprev[c] = t[c];
             }
-            if (hy) {
-                float g = 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) g += fabsf(t[(long long)c * HW] - t[(long long)c * HW + p.W]);
-                wy = __expf(-g * (1.0f / C));
-            }
+            wy = __expf(-gyv * (1.0f / C));                  // edge between rows y-1 and y
+            wx = __expf(-gxv * (1.0f / C));                  // edge between columns gx and gx+1
         }
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) {
             if (l >= p.L) break;
-            const int dw = p.dw[l], dh = p.dh[l];
-            const bool native = (dw == p.W && dh == p.H);
-            if (native && !do_stats) continue;
-            const float* dp = p.disp[l] + (long long)n * dw * dh;
-            const float usx = up_scale(dw, p.W), usy = up_scale(dh, p.H);
-            const float d = disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy);
-            if (!native) const_cast<float*>(p.dfull[l])[(long long)n * HW + i] = d;
+            if (native[l] && !do_stats) continue;
+            float d;
+            if (native[l]) {
+                d = p.disp[l][(long long)n * HW + y * W + gxc];
+            } else {
+                const int dw = p.dw[l], dh = p.dh[l];
+                const float* dp = p.disp[l] + (long long)n * dw * dh;
+                int ya0, ya1; float fyu;
+                up_taps(y, usy[l], dh, ya0, ya1, fyu);
+                d = bilerp(dp[ya0 * dw + xa0[l]], dp[ya0 * dw + xa1[l]], dp[ya1 * dw + xa0[l]], dp[ya1 * dw + xa1[l]], fxu[l], fyu);
+                if (own_row && own_col) const_cast<float*>(p.dfull[l])[(long long)n * HW + y * W + gx] = d;
+            }
             if (do_stats) {
-                v[3 * l + 2] += d;
-                if (hx) v[3 * l + 0] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx + 1, gy)) * wx;
-                if (hy) v[3 * l + 1] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy + 1)) * wy;
+                const float dr = __shfl_down_sync(0xffffffffu, d, 1);
+                if (own_col) {
+                    if (y > Y0) v[3 * l + 1] += fabsf(dprev[l] - d) * wy;          // row y-1 (owned) to row y
+                    if (own_row) {
+                        v[3 * l + 2] += d;
+                        if (has_right) v[3 * l + 0] += fabsf(d - dr) * wx;
+                    }
+                }
+                dprev[l] = d;
             }
         }
     }
     if (!do_stats) return;
-    block_sum<3 * LMAX>(v, red);
-    if (threadIdx.x < 3 * LMAX) part[((long long)n * bpi + blockIdx.x) * (3 * LMAX) + threadIdx.x] = red[threadIdx.x * (blockDim.x >> 5)];
+#pragma unroll
+    for (int k = 0; k < 3 * LMAX; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3 * LMAX; ++k) part[((long long)n * wpi + w) * (3 * LMAX) + k] = v[k];
+    }
     __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(&counters[n], 1u) == (unsigned)(bpi - 1));
-    __syncthreads();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&counters[n], 1u) == (unsigned)(wpi - 1)) ? 1 : 0;
+    last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     __threadfence();
-    if ((int)threadIdx.x < 3 * p.L) {
-        float s = 0.f;
-        for (int b = 0; b < bpi; ++b) s += __ldcg(part + ((long long)n * bpi + b) * (3 * LMAX) + threadIdx.x);
-        const int l = threadIdx.x / 3, k = threadIdx.x % 3;
-        stats[((long long)l * p.N + n) * NSTAT + 1 + k] = s;
+    if (lane < 3 * p.L) {
+        float s0 = 0.f, s1 = 0.f;
+        const float* pp = part + (long long)n * wpi * (3 * LMAX) + lane;
+        int b = 0;
+        for (; b + 1 < wpi; b += 2) { s0 += __ldcg(pp + (long long)b * (3 * LMAX)); s1 += __ldcg(pp + (long long)(b + 1) * (3 * LMAX)); }
+        if (b < wpi) s0 += __ldcg(pp + (long long)b * (3 * LMAX));
+        const int l = lane / 3, k = lane % 3;
+        stats[((long long)l * p.N + n) * NSTAT + 1 + k] = s0 + s1;
     }
-    if (threadIdx.x == 0) counters[n] = 0u;
+    if (lane == 0) counters[n] = 0u;
 }
 
-// adjoint of the upsample for the low-res decoder scales (after the marching kernel): gather form,
-// one thread per low-res pixel, deterministic.  grid (x-blocks, low-res scale index, N)
-__global__ void __launch_bounds__(128) down_adjoint_kernel(const __grid_constant__ FusedParams p) {
+// adjoint of the upsample for the low-res decoder scales (after the marching kernel), gather form,
+// deterministic, separable: one block per low-res output row.  Phase A sums the contributing
+// full-resolution rows with their vertical weights into shared memory (coalesced), phase B sums
+// the contributing columns per low-res pixel.  grid (max low-res height, low-res scale index, N)
+__global__ void __launch_bounds__(256) down_adjoint_kernel(const __grid_constant__ FusedParams p) {
+    extern __shared__ float vrow[];   // [W]
     int l = -1;
     for (int k = 0, seen = -1; k < p.L; ++k)
         if (p.dw[k] != p.W || p.dh[k] != p.H) { if (++seen == (int)blockIdx.y) { l = k; break; } }
     if (l < 0) return;
-    const int w = p.dw[l], h = p.dh[l], n = blockIdx.z;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * h) return;
-    p.gdisp[l][(long long)n * w * h + i] =
-        upsample_adjoint_at(p.gfull[l] + (long long)n * p.W * p.H, w, h, p.W, p.H, i % w, i / w);
+    const int w = p.dw[l], h = p.dh[l], n = blockIdx.z, yi = blockIdx.x;
+    if (yi >= h) return;
+    const int W = p.W, H = p.H;
+    const float sx = up_scale(w, W), sy = up_scale(h, H);
+    const float* g = p.gfull[l] + (long long)n * W * H;
+    int ylo = 0, yhi = H - 1;
+    if (sy > 0.f) {
+        ylo = max(0, (int)floorf((float)(yi - 1) / sy) - 1);
+        yhi = min(H - 1, (int)ceilf((float)(yi + 1) / sy) + 1);
+    }
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        float acc = 0.f;
+        for (int y = ylo; y <= yhi; ++y) {
+            int y0, y1; float fy;
+            up_taps(y, sy, h, y0, y1, fy);
+            const float wy = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
+            acc = fmaf(wy, g[y * W + x], acc);
+        }
+        vrow[x] = acc;
+    }
+    __syncthreads();
+    for (int xi = threadIdx.x; xi < w; xi += blockDim.x) {
+        int xlo = 0, xhi = W - 1;
+        if (sx > 0.f) {
+            xlo = max(0, (int)floorf((float)(xi - 1) / sx) - 1);
+            xhi = min(W - 1, (int)ceilf((float)(xi + 1) / sx) + 1);
+        }
+        float acc = 0.f;
+        for (int x = xlo; x <= xhi; ++x) {
+            int x0, x1; float fx;
+            up_taps(x, sx, w, x0, x1, fx);
+            const float wx = (x0 == xi ? 1.f - fx : 0.f) + (x1 == xi ? fx : 0.f);
+            acc = fmaf(wx, vrow[x], acc);
+        }
+        p.gdisp[l][((long long)n * h + yi) * w + xi] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -222,10 +302,9 @@ __global__ void __launch_bounds__(128) down_adjoint_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------
 template <int C, int S, bool BWD>
 struct MarchCfg {
-    // resident one-warp blocks per SM the kernel is compiled for, and the register budget that
-    // lets exactly that many fit (65536 / (WARPS * 32), rounded down to the allocation unit of 8)
-    static constexpr int WARPS = BWD ? (C == 1 ? 13 : 8) : 13;
-    static constexpr int MAXREG = (65536 / (WARPS * 32)) / 8 * 8;
+    // register budget per thread; registers are allocated per warp in units of 512, so the useful
+    // tiers are 128 (16 resident one-warp blocks per SM), 144 (14), 160 (12), 176 (11), 192 (10)
+    static constexpr int MAXREG = BWD ? (C == 1 ? 160 : 208) : 128;
 };
 
 template <int C, int S, bool BWD>
@@ -311,25 +390,40 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
+// one-warp blocks of march_kernel<C,S,BWD> resident per SM (occupancy API, cached)
+template <int C, int S, bool BWD>
+static int march_resident() {
+    using M = March<C, S, BWD>;
+    static int resident = 0;
+    if (!resident) {
+        const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_kernel<C, S, BWD>, 32, smem) != cudaSuccess) occ = 0;
+        resident = occ > 0 ? occ : 8;
+    }
+    return resident;
+}
+
 template <int C, int S, bool BWD>
 static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     using M = March<C, S, BWD>;
     const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
-    static int resident = 0;   // one-warp blocks resident per SM
-    if (!resident) {
-        MD2_CHECK(cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MD2_CHECK(cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        int occ = 0;
-        MD2_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_kernel<C, S, BWD>, 32, smem));
-        resident = occ > 0 ? occ : 1;
-    }
     const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R);
     const long long items = (long long)strips * chunks * p.L * p.N;
-    const long long cap = (long long)ctx->sm_count * resident;
+    const long long cap = (long long)ctx->sm_count * march_resident<C, S, BWD>();
     const int blocks = (int)(items < cap ? items : cap);
     march_kernel<C, S, BWD><<<blocks, 32, smem, st>>>(p, strips, chunks);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+static int march_resident_of(int C, int S, bool bwd) {
+    if (bwd) {
+        if (C == 1) return S == 1 ? march_resident<1, 1, true>() : march_resident<1, 2, true>();
+        return S == 1 ? march_resident<3, 1, true>() : march_resident<3, 2, true>();
+    }
+    if (C == 1) return S == 1 ? march_resident<1, 1, false>() : march_resident<1, 2, false>();
+    return S == 1 ? march_resident<3, 1, false>() : march_resident<3, 2, false>();
 }
 
 template <bool BWD>
@@ -369,6 +463,7 @@ static int check_desc(const md2_vsl_desc* d, bool need_loss_inputs) {
     MD2_REQUIRE(d != nullptr, "null descriptor");
     MD2_REQUIRE(d->W >= 2 && d->H >= 2 && d->W <= 65535 && d->H <= 32767, "W, H must be in 2..65535 / 2..32767");
     MD2_REQUIRE((long long)d->W * d->H * d->C < (1LL << 31), "one image must have fewer than 2^31 elements");
+    MD2_REQUIRE(d->W <= 12288, "W must be <= 12288 (one image row is staged in shared memory)");
     MD2_REQUIRE(d->N >= 1, "N must be >= 1");
     MD2_REQUIRE(d->C == 1 || d->C == 3, "C must be 1 or 3");
     MD2_REQUIRE(d->S >= 1 && d->S <= MAX_S, "S must be 1 or 2");
@@ -435,7 +530,7 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
         const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
         p.depth_a = maxd - mind; p.depth_b = mind;
     }
-    int n_low = 0, max_low = 0;
+    int n_low = 0, max_low_h = 0;
     for (int l = 0; l < L; ++l) {
         p.smooth_w[l] = d->smooth_weight[l];
         p.disp[l] = d->disparity[l]; p.dw[l] = d->disp_w[l]; p.dh[l] = d->disp_h[l];
@@ -443,7 +538,7 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
         if (bwd) MD2_REQUIRE(d->grad_disparity[l] != nullptr, "null grad_disparity");
         if (d->disp_w[l] != W || d->disp_h[l] != H) {
             ++n_low;
-            max_low = max(max_low, d->disp_w[l] * d->disp_h[l]);
+            max_low_h = max(max_low_h, d->disp_h[l]);
         }
     }
     {   // full-resolution views of every scale: the caller's buffers for native-size scales, L2-resident
@@ -466,20 +561,25 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     p.mode = mode;
     fill_pose_io(d, p.pose);
 
-    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, bwd ? (C == 1 ? 13 : 8) : 13);
+    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, march_resident_of(C, S, bwd));
     const int tiles = cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
     const int NP = NSTAT + 12 * S;
     // this call's pose rows in the constant-memory table: a slot per ctx (re-entrant across ctxs)
     const int pose_floats = 12 * S * N;
     MD2_REQUIRE(pose_floats <= POSE_CONST_FLOATS, "S*N too large for one call (max 1024 source-image pairs)");
     p.pose_slot = pose_floats <= POSE_SLOT_FLOATS ? ctx->pose_slot * POSE_SLOT_FLOATS : 0;
-    const int bpi = max(1, min(256, cdiv((long long)W * H, 512)));
     const int LMAX = L == 1 ? 1 : (L <= 4 ? 4 : 8);
+    // prep kernel partition: 31-column strips x chunks of rows, one warp each
+    const int prep_strips = cdiv(W, PREP_COLS);
+    int prep_R = 16;
+    while (prep_R < H && (long long)prep_strips * cdiv(H, prep_R) * N > 8LL * ctx->sm_count * 4) prep_R *= 2;
+    const int prep_chunks = cdiv(H, prep_R);
+    const int prep_wpi = prep_strips * prep_chunks;
     float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
     float* sums = (float*)ws_get(ctx, MD2_WS_SUMS, sizeof(float) * (size_t)L * N * NP);
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
-    float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)bpi * N * 3 * LMAX);
+    float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)prep_wpi * N * 3 * LMAX);
     unsigned int* counters = get_counters(ctx, L * N + 1 + N, st);
     if (!pose_ab || !partial || !sums || !stats || !part2 || !counters) return 1;
     p.pose_ab = pose_ab; p.partial = partial; p.sums = sums; p.counters = counters;
@@ -489,9 +589,9 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
 
     {   // prep: poses, upsampled low-res disparities (+ statistics pre-pass for the fused fwd+bwd)
         const int do_stats = mode == MODE_FWDBWD;
-        dim3 g((do_stats || n_low) ? bpi + 1 : 1, N);
+        dim3 g((do_stats || n_low) ? cdiv(prep_wpi, 4) + 1 : 1, N);
         unsigned int* pc = counters + L * N + 1;
-#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 256, 0, st>>>(p, (int)g.x - 1, do_stats, pose_ab, part2, stats, pc)
+#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 128, 0, st>>>(p, prep_strips, prep_chunks, prep_R, do_stats, pose_ab, part2, stats, pc)
         if (C == 1) { if (LMAX == 1) MD2_PREP(1, 1); else if (LMAX == 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
         else        { if (LMAX == 1) MD2_PREP(3, 1); else if (LMAX == 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
 #undef MD2_PREP
@@ -517,8 +617,8 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
     if (bwd && n_low) {   // low-res decoder scales: adjoint of the upsample, gather form (deterministic)
-        dim3 g(cdiv(max_low, 128), n_low, N);
-        down_adjoint_kernel<<<g, 128, 0, st>>>(p);
+        dim3 g(max_low_h, n_low, N);
+        down_adjoint_kernel<<<g, 256, sizeof(float) * W, st>>>(p);
         MD2_LAUNCH_CHECK(ctx);
     }
     return 0;

@@ -57,6 +57,7 @@ inline float g_ld1(const float* q) { return q[1]; }
 inline void g_st(float* q, float v) { *q = v; }
 inline void g_red(float* q, float v) { *q += v; }
 inline void g_red1(float* q, float v) { q[1] += v; }
+inline void g_pf(const float*) {}
 #define MD2_POSE(p, idx) ((p).pose_ab[(idx)])
 #else
 #define MD2_DEV __device__ __forceinline__
@@ -93,6 +94,18 @@ MD2_DEV float g_ld1(const float* q) { float v; asm("ld.global.nc.f32 %0, [%1+4];
 MD2_DEV void g_st(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v)); }
 MD2_DEV void g_red(float* q, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v)); }
 MD2_DEV void g_red1(float* q, float v) { asm volatile("red.global.add.f32 [%0+4], %1;" ::"l"(q), "f"(v)); }
+// pull a line into L1 one row ahead of its use (every row of the march touches new lines)
+#ifndef MD2_PREFETCH
+#define MD2_PREFETCH 1
+#endif
+MD2_DEV void g_pf(const float* q) {
+#if MD2_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+#elif MD2_PREFETCH == 2
+    float dummy;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dummy) : "l"(q));
+#endif
+}
 #endif
 
 // c * sign(d), 0 at d == 0  (abs'(0) = 0 as in ChainRules)
@@ -134,7 +147,7 @@ struct March {
         const float* dp;             // full-resolution disparity of this (scale, image)
         float* gd;                   // its gradient
         const float* am;             // automask of this image or null
-        float rc[C], rc9[C];
+        float rc[C];
         float apx[S][3];
         int pb[S];
         float px, Wf, Hf;
@@ -163,6 +176,11 @@ struct March {
         const float py = (float)(gym + 1);
         const int toff = gym * c.W;
         const float d = g_ld(c.dp + (toff + c.gxm));
+        if (gym + 1 < c.H) {   // next row's disparity / target lines
+            g_pf(c.dp + (toff + c.W + c.gxm));
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) g_pf(c.tg + (ch * c.HW + toff + c.W));
+        }
         cur.D = d;
         const float zv = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
         float Tc[C], Xc[S][C];
@@ -189,6 +207,10 @@ struct March {
             const int off = y0 * c.W + x0;
             const float* r0 = c.sb[s] + off;
             const float* r1 = r0 + c.W;
+            if (y0 + 2 < c.H) {   // the source row the next image row will need
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) g_pf(r1 + (ch * c.HW + c.W));
+            }
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
                 const float v00 = g_ld(r0 + ch * c.HW), v01 = g_ld1(r0 + ch * c.HW), v10 = g_ld(r1 + ch * c.HW), v11 = g_ld1(r1 + ch * c.HW);
@@ -256,7 +278,7 @@ struct March {
         for (int ch = 0; ch < C; ++ch) {
             sy[ch] = a.hy[ch] + b.hy[ch] + cur.hy[ch];
             const float syy = a.hyy[ch] + b.hyy[ch] + cur.hyy[ch];
-            my9[ch] = c.rc9[ch] + sy[ch];
+            my9[ch] = fmaf(9.0f, c.rc[ch], sy[ch]);
             Y2[ch] = fmaf(my9[ch], my9[ch], C1);
             VY[ch] = fmaf(-sy[ch], sy[ch], fmaf(9.0f, syy, C2));
         }
@@ -269,7 +291,7 @@ struct March {
                 const float sx = a.hx[s][ch] + b.hx[s][ch] + cur.hx[s][ch];
                 const float sxx = a.hxx[s][ch] + b.hxx[s][ch] + cur.hxx[s][ch];
                 const float sxy = a.hxy[s][ch] + b.hxy[s][ch] + cur.hxy[s][ch];
-                const float mx9 = c.rc9[ch] + sx;
+                const float mx9 = fmaf(9.0f, c.rc[ch], sx);
                 const float A = fmaf(2.0f * mx9, my9[ch], C1);
                 const float Cc = fmaf(mx9, mx9, Y2[ch]);
                 const float B = fmaf(-2.0f * sx, sy[ch], fmaf(18.0f, sxy, C2));
@@ -311,14 +333,14 @@ struct March {
         const bool own = row_own && c.pcol;
         acc.warp_sum += own ? wlv : 0.f;
         if (c.do_viz && own) {
-            const long long o = (long long)c.n * c.HW + q * c.W + c.gxr;
+            const long long o = (long long)c.n * c.HW + q * c.W + c.gxm;
             if (p.viz_loss) p.viz_loss[o] = wlv;
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 if (p.viz_warped[s]) {
 #pragma unroll
                     for (int ch = 0; ch < C; ++ch)
-                        p.viz_warped[s][((long long)c.n * C + ch) * c.HW + q * c.W + c.gxr] = b.xm[s][ch] + c.rc[ch];
+                        p.viz_warped[s][((long long)c.n * C + ch) * c.HW + q * c.W + c.gxm] = b.xm[s][ch] + c.rc[ch];
                 }
         }
         if (!BWD) {
@@ -496,7 +518,7 @@ struct March {
                 gd += fmaf(c.sA, gh, -c.sB);
             }
             gd *= c.mp;
-            if (c.pcol) g_st(c.gd + (r * c.W + c.gxr), gd);
+            if (c.pcol) g_st(c.gd + (r * c.W + c.gxm), gd);   // (gxm == gxr on the output columns)
         }
         acc.ey_prev = ey;
     }
@@ -548,7 +570,7 @@ struct March {
             const int ym = (c.Y0 + c.Y1) >> 1;
             const int xm = X0 + OW / 2 < c.W ? X0 + OW / 2 : c.W - 1;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) { c.rc[ch] = tgn[ch * c.HW + ym * c.W + xm]; c.rc9[ch] = 9.0f * c.rc[ch]; }
+            for (int ch = 0; ch < C; ++ch) c.rc[ch] = tgn[ch * c.HW + ym * c.W + xm];
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -579,7 +601,7 @@ struct March {
         }
         c.ring = reinterpret_cast<Vec4*>(wsm);
         // pin the per-lane invariants in registers (otherwise they are re-derived in every row)
-        keep(c.gxm); keep(c.gxr); keep(c.tg); keep(c.px);
+        keep(c.gxm); keep(c.tg);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.sb[s]);
@@ -590,7 +612,7 @@ struct March {
         keep(c.dp);
         if (BWD) { keep(c.gd); keep(c.kq); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); }
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) { keep(c.rc[ch]); keep(c.rc9[ch]); }
+        for (int ch = 0; ch < C; ++ch) keep(c.rc[ch]);
 
         Acc acc;
         acc.warp_sum = acc.ssx = acc.ssy = acc.dsum = 0.f;
@@ -646,7 +668,7 @@ struct March {
             for (int s = 0; s < S; ++s)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {   // G = sum cbar (z p)^T, p = (px, py, 1); h = sum cbar
-                    v[NSTAT + 12 * s + 3 * k + 0] = c.px * acc.P0[s][k];
+                    v[NSTAT + 12 * s + 3 * k + 0] = (float)(c.gxm + 1) * acc.P0[s][k];
                     v[NSTAT + 12 * s + 3 * k + 1] = acc.P1[s][k];
                     v[NSTAT + 12 * s + 3 * k + 2] = acc.P0[s][k];
                     v[NSTAT + 12 * s + 9 + k] = acc.Ph[s][k];
