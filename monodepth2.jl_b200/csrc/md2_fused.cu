@@ -246,17 +246,133 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ Fused
     if (lane == 0) counters[n] = 0u;
 }
 
-// adjoint of the upsample for the low-res decoder scales (after the marching kernel), gather form,
-// deterministic, separable: one block per low-res output row.  Phase A sums the contributing
-// full-resolution rows with their vertical weights into shared memory (coalesced), phase B sums
-// the contributing columns per low-res pixel.  grid (max low-res height, low-res scale index, N)
-__global__ void __launch_bounds__(256) down_adjoint_kernel(const __grid_constant__ FusedParams p) {
-    extern __shared__ float vrow[];   // [W]
+// ------------------------------------------------------------------------------------------
+// the marching-warp kernel (md2_march.cuh), persistent: one-warp blocks, as many as are resident
+// on the whole GPU; block b walks the work items (strip, chunk, scale, image) b, b + grid, ...  The last warp to finish an item of a (scale, image) reduces that group's
+// partial sums in a fixed order, the very last one finalises the loss and the pose gradients
+// (deterministic loss).
+// ------------------------------------------------------------------------------------------
+template <int C, int S, bool BWD>
+struct MarchCfg {
+    // register budget per thread; registers are allocated per warp in units of 512, so the useful
+    // tiers are 96 (20 resident warps per SM), 112 (18), 128 (16), 144 (14), 160 (12), 192 (10)
+    static constexpr int MAXREG = C == 1 ? 128 : 192;
+};
+
+template <int C, int S, bool BWD>
+__global__ void __maxnreg__((MarchCfg<C, S, BWD>::MAXREG))
+march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
+    extern __shared__ __align__(16) float wsm[];
+    using M = March<C, S, BWD>;
+    constexpr int NP = M::NPART;
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;      // 0: warp F (forward), 1: warp B (backward)
+    const int ipg = strips * chunks;
+    const int LN = p.L * p.N;
+    const int items = ipg * LN;
+    int gslot = 0;
+    if (BWD) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int b = 0; b < MARCH_NBAR; ++b) mb_init(reinterpret_cast<mbar_t*>(wsm + M::RING_FLOATS), b, 32);
+        }
+        __syncthreads();
+    }
+    // one warp pair per block, item index from blockIdx only, so that everything derived from it is
+    // warp-uniform for the compiler (uniform registers / constant-bank operands); the grid is
+    // exactly the number of blocks resident on the whole GPU
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int z = it / ipg, rem = it - z * ipg;
+        const int cy = rem / strips, sx = rem - cy * strips;
+        {
+            float v[32];
+            if (role == 0) M::run_forward(p, sx, cy, z, lane, wsm, gslot, v);
+            else M::run_backward(p, sx, cy, z, lane, wsm, gslot, v);
+            const float tot = warp_reduce_32(v);
+            // warp F owns the loss sums [0, NSTAT), warp B the pose sums [NSTAT, NP)
+            if (role == 0 ? lane < (BWD ? NSTAT : NP) : (lane >= NSTAT && lane < NP)) p.partial[(long long)it * NP + lane] = tot;
+        }
+        if (BWD) __syncthreads();   // both warps are done with the ring before the next item reuses it
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finish kernel (one launch after the marching kernel); every block is independent, all sums
+// are taken in a fixed order (deterministic), nothing is atomic:
+//   block 0             per-(scale, image) loss sums from the per-item partials -> statistics,
+//                       saved statistics, loss scalar
+//   blocks 1 .. S*N     (backward) pose gradient of one (source, image): G | h summed over all
+//                       scales and items in double, then the K / composeT / so3 adjoints
+//   remaining blocks    (backward, low-res decoder scales) adjoint of the upsample, gather form,
+//                       separable: one block per low-res output row.  Phase A sums the
+//                       contributing full-resolution rows with their vertical weights into
+//                       shared memory (coalesced), phase B the contributing columns per pixel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd,
+                                                     int n_low, int max_low_h) {
+    extern __shared__ float vrow[];   // [W] (adjoint blocks)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LN = p.L * p.N;
+    int b = blockIdx.x;
+    if (b == 0) {
+        if (p.mode != 1) {
+            for (int z = warp; z < LN; z += 8) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* pp = p.partial + (long long)z * ipg * NP;
+                for (int it = lane; it < ipg; it += 32) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] += pp[(long long)it * NP + k];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+                if (lane == 0) {
+                    float* st = p.stats_out + (long long)z * NSTAT;
+                    st[0] = v[0];
+                    if (p.mode == 0) { st[1] = v[1]; st[2] = v[2]; st[3] = v[3]; }
+                    if (p.saved && p.saved != p.stats_out)
+                        for (int k = 0; k < NSTAT; ++k) p.saved[(long long)z * NSTAT + k] = st[k];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && p.loss)
+                *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
+        }
+        return;
+    }
+    b -= 1;
+    if (!bwd) return;
+    if (b < p.S * p.N) {
+        if (warp != 0) return;
+        const int s = b / p.N, nn = b % p.N;
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+        for (int l = 0; l < p.L; ++l) {
+            const float* pp = p.partial + ((long long)l * p.N + nn) * ipg * NP + NSTAT + 12 * s;
+            for (int it = lane; it < ipg; it += 32) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) acc[k] += (double)pp[(long long)it * NP + k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = warp_sum_d(acc[k]);
+        if (lane == 0) finalize_pose(p.pose, s, nn, acc, acc + 9);
+        return;
+    }
+    b -= p.S * p.N;
+    if (b >= n_low * max_low_h * p.N) return;
+    const int yi = b % max_low_h, li = (b / max_low_h) % n_low, n = b / (max_low_h * n_low);
     int l = -1;
     for (int k = 0, seen = -1; k < p.L; ++k)
-        if (p.dw[k] != p.W || p.dh[k] != p.H) { if (++seen == (int)blockIdx.y) { l = k; break; } }
+        if (p.dw[k] != p.W || p.dh[k] != p.H) { if (++seen == li) { l = k; break; } }
     if (l < 0) return;
-    const int w = p.dw[l], h = p.dh[l], n = blockIdx.z, yi = blockIdx.x;
+    const int w = p.dw[l], h = p.dh[l];
     if (yi >= h) return;
     const int W = p.W, H = p.H;
     const float sx = up_scale(w, W), sy = up_scale(h, H);
@@ -266,15 +382,29 @@ __global__ void __launch_bounds__(256) down_adjoint_kernel(const __grid_constant
         ylo = max(0, (int)floorf((float)(yi - 1) / sy) - 1);
         yhi = min(H - 1, (int)ceilf((float)(yi + 1) / sy) + 1);
     }
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
-        float acc = 0.f;
-        for (int y = ylo; y <= yhi; ++y) {
+    __shared__ float wys[64];
+    const int ny = yhi - ylo + 1;   // <= 2/sy + 5
+    for (int base = 0; base < ny; base += 64) {
+        __syncthreads();
+        if ((int)threadIdx.x < 64 && base + (int)threadIdx.x < ny) {
             int y0, y1; float fy;
-            up_taps(y, sy, h, y0, y1, fy);
-            const float wy = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
-            acc = fmaf(wy, g[y * W + x], acc);
+            up_taps(ylo + base + threadIdx.x, sy, h, y0, y1, fy);
+            wys[threadIdx.x] = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
         }
-        vrow[x] = acc;
+        __syncthreads();
+        const int cnt = min(64, ny - base);
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            float acc = base ? vrow[x] : 0.f;
+            const float* gp = g + (long long)(ylo + base) * W + x;
+            int k = 0;
+            for (; k + 4 <= cnt; k += 4) {
+                const float g0 = gp[(long long)k * W], g1 = gp[(long long)(k + 1) * W], g2 = gp[(long long)(k + 2) * W], g3 = gp[(long long)(k + 3) * W];
+                acc = fmaf(wys[k], g0, acc); acc = fmaf(wys[k + 1], g1, acc);
+                acc = fmaf(wys[k + 2], g2, acc); acc = fmaf(wys[k + 3], g3, acc);
+            }
+            for (; k < cnt; ++k) acc = fmaf(wys[k], gp[(long long)k * W], acc);
+            vrow[x] = acc;
+        }
     }
     __syncthreads();
     for (int xi = threadIdx.x; xi < w; xi += blockDim.x) {
@@ -295,102 +425,9 @@ __global__ void __launch_bounds__(256) down_adjoint_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// the marching-warp kernel (md2_march.cuh), persistent: one-warp blocks, as many as are resident
-// on the whole GPU; block b walks the work items (strip, chunk, scale, image) b, b + grid, ...  The last warp to finish an item of a (scale, image) reduces that group's
-// partial sums in a fixed order, the very last one finalises the loss and the pose gradients
-// (deterministic loss).
-// ------------------------------------------------------------------------------------------
-template <int C, int S, bool BWD>
-struct MarchCfg {
-    // register budget per thread; registers are allocated per warp in units of 512, so the useful
-    // tiers are 128 (16 resident one-warp blocks per SM), 144 (14), 160 (12), 176 (11), 192 (10)
-    static constexpr int MAXREG = BWD ? (C == 1 ? 160 : 208) : 128;
-};
-
-template <int C, int S, bool BWD>
-__global__ void __maxnreg__((MarchCfg<C, S, BWD>::MAXREG))
-march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
-    extern __shared__ __align__(16) float wsm[];
-    using M = March<C, S, BWD>;
-    constexpr int NP = M::NPART;
-    const int lane = threadIdx.x;
-    const int ipg = strips * chunks;
-    const int LN = p.L * p.N;
-    const int items = ipg * LN;
-    // one warp per block so that everything derived from the item index is warp-uniform for the
-    // compiler (uniform registers / constant-bank operands); the grid is exactly the number of
-    // blocks resident on the whole GPU, so every SM gets the same number of items
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int z = it / ipg, rem = it - z * ipg;
-        const int cy = rem / strips, sx = rem - cy * strips;
-        {
-            float v[32];
-            M::run(p, sx, cy, z, lane, wsm, v);
-            const float tot = warp_reduce_32(v);
-            if (lane < NP) p.partial[(long long)it * NP + lane] = tot;
-        }
-        __threadfence();
-        __syncwarp();
-        int flag = 0;
-        if (lane == 0) flag = (atomicAdd(&p.counters[z], 1u) == (unsigned)(ipg - 1)) ? 1 : 0;
-        flag = __shfl_sync(0xffffffffu, flag, 0);
-        if (!flag) continue;
-        __threadfence();
-        if (lane < NP) {   // this warp finished (scale, image) z last: reduce its items in a fixed order
-            float s0 = 0.f, s1 = 0.f;
-            const float* pp = p.partial + (long long)z * ipg * NP + lane;
-            int b = 0;
-            for (; b + 1 < ipg; b += 2) { s0 += __ldcg(pp + (long long)b * NP); s1 += __ldcg(pp + (long long)(b + 1) * NP); }
-            if (b < ipg) s0 += __ldcg(pp + (long long)b * NP);
-            p.sums[(long long)z * NP + lane] = s0 + s1;
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            p.counters[z] = 0u;
-            flag = (atomicAdd(&p.counters[LN], 1u) == (unsigned)(LN - 1)) ? 1 : 0;
-        }
-        flag = __shfl_sync(0xffffffffu, flag, 0);
-        if (!flag) continue;
-        __threadfence();
-        // ---- the very last warp: loss, saved statistics, pose gradients ----
-        if (p.mode != 1) {
-            for (int zz = lane; zz < LN; zz += 32) {
-                float* st = p.stats_out + (long long)zz * NSTAT;
-                st[0] = __ldcg(p.sums + (long long)zz * NP);
-                if (p.mode == 0) {
-                    st[1] = __ldcg(p.sums + (long long)zz * NP + 1);
-                    st[2] = __ldcg(p.sums + (long long)zz * NP + 2);
-                    st[3] = __ldcg(p.sums + (long long)zz * NP + 3);
-                }
-                if (p.saved && p.saved != p.stats_out)
-                    for (int k = 0; k < NSTAT; ++k) p.saved[(long long)zz * NSTAT + k] = st[k];
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0 && p.loss)
-                *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
-        }
-        if (BWD) {
-            for (int i = lane; i < S * p.N; i += 32) {
-                const int s = i / p.N, nn = i % p.N;
-                double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
-                for (int l = 0; l < p.L; ++l) {
-                    const float* su = p.sums + ((long long)l * p.N + nn) * NP + NSTAT + 12 * s;
-                    for (int k = 0; k < 9; ++k) G[k] += __ldcg(su + k);
-                    for (int k = 0; k < 3; ++k) h[k] += __ldcg(su + 9 + k);
-                }
-                finalize_pose(p.pose, s, nn, G, h);
-            }
-        }
-        if (lane == 0) p.counters[LN] = 0u;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
-// one-warp blocks of march_kernel<C,S,BWD> resident per SM (occupancy API, cached)
+// blocks (warp F [+ warp B]) of march_kernel<C,S,BWD> resident per SM (occupancy API, cached)
 template <int C, int S, bool BWD>
 static int march_resident() {
     using M = March<C, S, BWD>;
@@ -398,8 +435,10 @@ static int march_resident() {
     if (!resident) {
         const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_kernel<C, S, BWD>, 32, smem) != cudaSuccess) occ = 0;
+        if (cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_kernel<C, S, BWD>, M::THREADS, smem) != cudaSuccess) occ = 0;
         resident = occ > 0 ? occ : 8;
+        if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] march_kernel<%d,%d,%d>: %d resident blocks/SM, %zu B smem/block\n", C, S, (int)BWD, resident, smem);
     }
     return resident;
 }
@@ -412,7 +451,7 @@ static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     const long long items = (long long)strips * chunks * p.L * p.N;
     const long long cap = (long long)ctx->sm_count * march_resident<C, S, BWD>();
     const int blocks = (int)(items < cap ? items : cap);
-    march_kernel<C, S, BWD><<<blocks, 32, smem, st>>>(p, strips, chunks);
+    march_kernel<C, S, BWD><<<blocks, M::THREADS, smem, st>>>(p, strips, chunks);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -571,18 +610,17 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     const int LMAX = L == 1 ? 1 : (L <= 4 ? 4 : 8);
     // prep kernel partition: 31-column strips x chunks of rows, one warp each
     const int prep_strips = cdiv(W, PREP_COLS);
-    int prep_R = 16;
+    int prep_R = 4;   // short chains: every row of the march waits for one memory round trip
     while (prep_R < H && (long long)prep_strips * cdiv(H, prep_R) * N > 8LL * ctx->sm_count * 4) prep_R *= 2;
     const int prep_chunks = cdiv(H, prep_R);
     const int prep_wpi = prep_strips * prep_chunks;
     float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
-    float* sums = (float*)ws_get(ctx, MD2_WS_SUMS, sizeof(float) * (size_t)L * N * NP);
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
     float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)prep_wpi * N * 3 * LMAX);
-    unsigned int* counters = get_counters(ctx, L * N + 1 + N, st);
-    if (!pose_ab || !partial || !sums || !stats || !part2 || !counters) return 1;
-    p.pose_ab = pose_ab; p.partial = partial; p.sums = sums; p.counters = counters;
+    unsigned int* counters = get_counters(ctx, N, st);   // prep kernel: last warp of an image
+    if (!pose_ab || !partial || !stats || !part2 || !counters) return 1;
+    p.pose_ab = pose_ab; p.partial = partial; p.sums = nullptr; p.counters = nullptr;
     p.stats = stats; p.stats_out = stats; p.saved = (mode == MODE_BWD) ? nullptr : d->saved;
     if (mode == MODE_BWD && d->saved) p.stats = d->saved;   // else the ctx holds the last forward's statistics
     p.loss = (mode == MODE_BWD) ? nullptr : d->loss;
@@ -590,7 +628,7 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     {   // prep: poses, upsampled low-res disparities (+ statistics pre-pass for the fused fwd+bwd)
         const int do_stats = mode == MODE_FWDBWD;
         dim3 g((do_stats || n_low) ? cdiv(prep_wpi, 4) + 1 : 1, N);
-        unsigned int* pc = counters + L * N + 1;
+        unsigned int* pc = counters;
 #define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 128, 0, st>>>(p, prep_strips, prep_chunks, prep_R, do_stats, pose_ab, part2, stats, pc)
         if (C == 1) { if (LMAX == 1) MD2_PREP(1, 1); else if (LMAX == 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
         else        { if (LMAX == 1) MD2_PREP(3, 1); else if (LMAX == 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
@@ -616,9 +654,9 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
     else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
-    if (bwd && n_low) {   // low-res decoder scales: adjoint of the upsample, gather form (deterministic)
-        dim3 g(max_low_h, n_low, N);
-        down_adjoint_kernel<<<g, 256, sizeof(float) * W, st>>>(p);
+    {   // loss / statistics, pose gradients, adjoint of the upsample for the low-res decoder scales
+        const int blocks = 1 + (bwd ? S * N + n_low * max_low_h * N : 0);
+        finish_kernel<<<blocks, 256, sizeof(float) * W, st>>>(p, NP, tiles, bwd ? 1 : 0, n_low, max_low_h);
         MD2_LAUNCH_CHECK(ctx);
     }
     return 0;

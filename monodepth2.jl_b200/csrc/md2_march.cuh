@@ -1,29 +1,35 @@
 // Fused view-synthesis loss, "marching warp" pipeline (the hot path).
 //
-// Same maths as md2_fused.cuh (src/training.jl:42-70 and its Zygote pullback), different mapping:
-// ONE WARP owns a 32-column strip of one (scale, image) and marches down a chunk of rows; lane =
-// image column.  Per row the warp runs three pipelined stages, all rolling state in registers:
-//   L(i)    disparity -> depth -> backproject/pose/project -> 4-tap border
-//           gather of the S source frames; horizontal 3-sums for the SSIM windows come from the
-//           neighbouring lanes by warp shuffle
-//   W(i-1)  vertical rolling 3-sums -> SSIM + L1 photometric error, arg-min over sources, automask,
-//           loss partial sums; (backward) the per-window SSIM gradient coefficients and their
-//           horizontal adjoint 3-sums (shuffles)
-//   P(i-2)  (backward) vertical adjoint sums -> d loss / d warped, sampler / projection / depth
-//           adjoints, pose accumulators, source-image scatter (lower tap pair carried to the next
-//           row, right tap merged into the right-hand lane), smoothness gradient, disparity
-//           gradient
-// The disparity of every scale arrives at full resolution (low-res decoder scales are upsampled by
-// the prep kernel into an L2-resident scratch, and their gradient is brought back by a gather-form
-// adjoint kernel afterwards: md2_fused.cu), so all work items run the same code.
-// Nothing is shared between warps: no block barriers, the halo is 2 columns each side (28 of 32
-// lanes produce outputs) and 2 rows at the chunk ends.  The only shared memory is a per-lane
-// 3-row ring holding what P(i-2) needs from L(i-2) (sampler taps, slopes, projection factors).
-// The row loop is unrolled by 3 with rotating roles, so rolling the 3-row state costs no moves.
+// Same maths as src/training.jl:42-70 and its Zygote pullback.  A work item is a 32-column strip
+// of one (scale, image), a chunk of rows tall; lane = image column, the warps march down the rows
+// with all rolling state in registers.  The backward runs as a two-warp producer / consumer pair:
 //
-// The code is written against a tiny warp interface (w_up / w_dn / w_shfl / w_ballot / w_sync) so
-// that tests/emul can run the very same source on the CPU with 32 cooperative fibers per warp
-// (MD2_WARP_EMU, test infrastructure only).
+//   warp F (forward)   per row i:
+//     L(i)    disparity -> depth -> backproject/pose/project -> 4-tap border gather of the S source
+//             frames; horizontal 3-sums for the SSIM windows come from the neighbouring lanes by
+//             warp shuffle
+//     W(i-1)  vertical rolling 3-sums -> SSIM + L1 photometric error, arg-min over sources,
+//             automask, loss partial sums; the per-window SSIM gradient coefficients and their
+//             horizontal adjoint 3-sums (shuffles)
+//     -> writes one slot of a shared-memory ring: the pixel packet of row i (sampler taps, slopes,
+//        projection factors, own values) and the window packet of row i-1
+//   warp B (backward)  per pixel row r, once slot r+2 is full:
+//     P(r)    vertical adjoint sums -> d loss / d warped, sampler / projection / depth adjoints,
+//             pose accumulators, source-image scatter (lower tap pair carried to the next row,
+//             right tap merged into the right-hand lane), smoothness gradient, disparity gradient
+//   The two warps are coupled only by full/empty mbarriers per ring slot, so the gather
+//   latency of F overlaps the arithmetic of B, and each warp carries half of the register state
+//   (twice the resident warps per SM of a single-warp formulation).
+//
+// Forward-only calls run warp F alone.  The halo is 2 columns each side (28 of 32 lanes produce
+// outputs) and 2 rows at the chunk ends; F's row loop is unrolled by 3 with rotating roles, so
+// rolling the 3-row state costs no moves.  The disparity of every scale arrives at full resolution
+// (low-res decoder scales are upsampled by the prep kernel into an L2-resident scratch, and their
+// gradient is brought back by a gather-form adjoint kernel afterwards: md2_fused.cu).
+//
+// The code is written against a tiny warp/block interface (w_up / w_dn / w_shfl / w_any /
+// mb_wait / mb_arrive) so that tests/emul can run the very same source on the CPU with 32
+// cooperative fibers per warp (MD2_WARP_EMU, test infrastructure only).
 #pragma once
 #include <string.h>
 
@@ -35,17 +41,17 @@ struct alignas(16) Vec4 { float x, y, z, w; };
 
 #if defined(MD2_WARP_EMU)
 #define MD2_DEV inline
-// emu_xchg / emu_ballot: tests/emul/warp_emu.h, included before this file
+// emu_xchg / emu_ballot / emu_bar: tests/emul/warp_emu.h, included before this file
 inline float w_shfl(float v, int src, int) { unsigned int u; memcpy(&u, &v, 4); u = emu_xchg(u, src); float r; memcpy(&r, &u, 4); return r; }
 inline int w_shfl(int v, int src, int) { return (int)emu_xchg((unsigned int)v, src); }
 inline float w_up(float v, int lane) { return w_shfl(v, lane > 0 ? lane - 1 : 0, lane); }
 inline float w_dn(float v, int lane) { return w_shfl(v, lane < 31 ? lane + 1 : 31, lane); }
 inline int w_up(int v, int lane) { return w_shfl(v, lane > 0 ? lane - 1 : 0, lane); }
 inline int w_dn(int v, int lane) { return w_shfl(v, lane < 31 ? lane + 1 : 31, lane); }
-inline unsigned int w_ballot(bool p) { return emu_ballot(p ? 1 : 0); }
 inline bool w_any(bool p) { return emu_ballot(p ? 1 : 0) != 0u; }
-inline void w_sync() { emu_ballot(0); }
-inline int w_popc(unsigned int m) { return __builtin_popcount(m); }
+typedef unsigned long long mbar_t;
+inline void mb_arrive(mbar_t* bars, int idx) { emu_mb_arrive(bars, idx); }
+inline void mb_wait(mbar_t* bars, int idx, int parity) { emu_mb_wait(bars, idx, parity); }
 inline float f_sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 inline float f_rcp(float x) { return 1.0f / x; }
 inline float f_ex2(float x) { return exp2f(x); }
@@ -73,10 +79,29 @@ MD2_DEV float w_up(float v, int) { return __shfl_up_sync(0xffffffffu, v, 1); }
 MD2_DEV float w_dn(float v, int) { return __shfl_down_sync(0xffffffffu, v, 1); }
 MD2_DEV int w_up(int v, int) { return __shfl_up_sync(0xffffffffu, v, 1); }
 MD2_DEV int w_dn(int v, int) { return __shfl_down_sync(0xffffffffu, v, 1); }
-MD2_DEV unsigned int w_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 MD2_DEV bool w_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
-MD2_DEV void w_sync() { __syncwarp(); }
-MD2_DEV int w_popc(unsigned int m) { return __popc(m); }
+// shared-memory mbarriers (32 arrivals per phase: every lane of the signalling warp arrives).
+// Named bar.sync/bar.arrive barriers would also do, but 2 x depth of them per block cap the
+// resident blocks per SM at 4 (16 hardware barriers per block are reserved).
+typedef unsigned long long mbar_t;
+MD2_DEV unsigned int smem_u32(const void* q) { return (unsigned int)__cvta_generic_to_shared(q); }
+MD2_DEV void mb_init(mbar_t* bars, int idx, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + idx)), "r"(count) : "memory");
+}
+MD2_DEV void mb_arrive(mbar_t* bars, int idx) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bars + idx)) : "memory");
+}
+MD2_DEV void mb_wait(mbar_t* bars, int idx, int parity) {   // returns once the phase of that parity has completed
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MB_DONE_%=;\n"
+        "bra MB_WAIT_%=;\n"
+        "MB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bars + idx)), "r"(parity) : "memory");
+}
 MD2_DEV float f_sat(float x) { return __saturatef(x); }
 MD2_DEV float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 MD2_DEV float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -113,17 +138,32 @@ MD2_DEV float sgn_scaled(float d, float c) {
     return d != 0.0f ? i_as_float(f_as_int(c) ^ (f_as_int(d) & (int)0x80000000)) : 0.0f;
 }
 
+constexpr int MARCH_DEPTH = 4;       // ring slots between warp F and warp B (B holds 3, F fills the 4th)
+constexpr int BAR_FULL = 0;          // mbarrier indices: full[s] = BAR_FULL + s, empty[s] = BAR_EMPTY + s
+constexpr int BAR_EMPTY = MARCH_DEPTH;
+constexpr int MARCH_NBAR = 2 * MARCH_DEPTH;
+constexpr int SLOT_WRAP = 4 * MARCH_DEPTH;   // the running slot counters live in [0, SLOT_WRAP)
+
 template <int C, int S, bool BWD>
 struct March {
     static constexpr int HALO = BWD ? 2 : 1;
     static constexpr int OW = 32 - 2 * HALO;             // output columns per strip
     static constexpr int NPART = NSTAT + 12 * S;
-    // what P(i-2) needs from L(i-2), per source: A = mx q, B = my q, u, v, fx, fy, gather offset,
-    // C slopes d/dix, C slopes d/diy; plus the depth z
+    // ---- ring slot layout (floats per lane) ----
+    // pixel packet of row i: own target values ym[C], disparity D, own warped values xm[S][C], depth z,
+    // then per source: A = mx q, B = my q, u, v, fx, fy, gather offset, C slopes d/dix, C slopes d/diy
+    static constexpr int O_YM = 0, O_D = C, O_XM = C + 1, O_Z = C + 1 + S * C, O_SRC = O_Z + 1;
     static constexpr int SRCF = 7 + 2 * C;
-    static constexpr int NSTF = S * SRCF + 1;
-    static constexpr int NST4 = (NSTF + 3) / 4;
-    static constexpr int SMEM_FLOATS = BWD ? (3 * NST4 * 32 * 4) : 4;   // the ring
+    static constexpr int NPPF = O_SRC + S * SRCF;
+    static constexpr int NPP4 = (NPPF + 3) / 4;
+    static constexpr int NYD4 = (C + 1 + 3) / 4;         // Vec4s holding ym[C], D
+    // window packet of row i-1: t[3C], s0[3C], selected source
+    static constexpr int NWPF = 6 * C + 1;
+    static constexpr int NWP4 = (NWPF + 3) / 4;
+    static constexpr int SLOT4 = NPP4 + NWP4;            // Vec4 per lane and slot
+    static constexpr int RING_FLOATS = BWD ? (MARCH_DEPTH * SLOT4 * 32 * 4) : 0;
+    static constexpr int SMEM_FLOATS = RING_FLOATS + 2 * MARCH_NBAR + 4;   // ring, then the mbarriers (8 B each)
+    static constexpr int THREADS = BWD ? 64 : 32;
     static_assert(NPART <= 32, "one lane per partial sum");
 
     struct Row {           // one pixel row: horizontal 3-sums (window column centred on this lane) + own values
@@ -131,62 +171,68 @@ struct March {
         float xm[S][C], ym[C];   // this lane's own (centred) warped / target values
         float D;                 // this lane's disparity
     };
-    struct Coef {          // one window row: horizontal adjoint 3-sums of the coefficient maps
-        float t[3 * C];    // all windows
-        float s0[3 * C];   // windows whose selected source is 0
-        int sel;           // this lane's selected source (-1: automask)
+
+    struct Geo {           // what both warps need to know about the work item
+        int W, H, HW, Y0, Y1, n, scale, lane, gxm, gxr;
+        bool col_img, pcol, has_right;
     };
 
-    struct Ctx {           // loop invariants of one work item
-        int W, H, HW, Y0, Y1, n, scale, lane;
-        int gxm, gxr;
-        bool col_img, pcol, has_right, do_viz;
+    static MD2_DEV void geometry(const FusedParams& p, int sx, int cy, int z, int lane, Geo& g) {
+        g.lane = lane;
+        g.W = p.W; g.H = p.H; g.HW = p.W * p.H;
+        g.scale = z / p.N; g.n = z - g.scale * p.N;
+        g.Y0 = cy * p.m_R;
+        g.Y1 = (g.Y0 + p.m_R < g.H) ? g.Y0 + p.m_R : g.H;
+        // this lane's column (reflect-pad(1): only -1 and W are ever used by an in-image window)
+        g.gxr = sx * OW - HALO + lane;
+        int gxm = g.gxr == -1 ? 1 : (g.gxr == g.W ? g.W - 2 : g.gxr);
+        g.gxm = gxm < 0 ? 0 : (gxm > g.W - 1 ? g.W - 1 : gxm);
+        g.col_img = g.gxr >= 0 && g.gxr < g.W;
+        g.pcol = g.col_img && lane >= HALO && lane < 32 - HALO;             // output pixel column
+        g.has_right = g.col_img && g.gxr + 1 < g.W;
+    }
+
+    // =====================================================================================
+    // warp F
+    // =====================================================================================
+    struct CtxF {
+        Geo g;
+        bool do_viz;
         const float* tg;             // target image + this lane's column
         const float* sb[S];
-        float* gb[S];
         const float* dp;             // full-resolution disparity of this (scale, image)
-        float* gd;                   // its gradient
         const float* am;             // automask of this image or null
         float rc[C];
         float apx[S][3];
         int pb[S];
-        float px, Wf, Hf;
+        float Wf, Hf;
         float kq;                    // wcol ? up_photo * alpha/C * (-1/2) : 0
-        float cl1;                   // up_photo * (1-alpha)/C
-        float mp;                    // pcol ? 1 : 0
         float wl, wr;                // horizontal reflect-pad adjoint weights of this pixel column
-        float cxn, cyn, sA, sB, nega;
         Vec4* ring;
+        mbar_t* bars;
+        int gslot;                   // running slot counter (continues across work items)
     };
-
-    struct Acc {           // per-lane accumulators of one work item
-        float warp_sum, ssx, ssy, dsum;
-        float P0[S][3], P1[S][3], Ph[S][3];
-        float car0[S][C], car1[S][C];
-        int coff[S];
-        float ey_prev;
-    };
+    struct AccF { float warp_sum, ssx, ssy, dsum; };
 
     // ---- L(i) ----
-    template <int SLOT>
-    static MD2_DEV void stage_load(const FusedParams& p, const Ctx& c, Acc& acc, Row& cur, int i) {
-        const int lane = c.lane;
-        int gym = i == -1 ? 1 : (i == c.H ? c.H - 2 : i);
-        gym = gym < 0 ? 0 : (gym > c.H - 1 ? c.H - 1 : gym);
+    static MD2_DEV void stage_load(const FusedParams& p, const CtxF& c, Row& cur, int i, float (&pk)[NPP4 * 4]) {
+        const Geo& g = c.g;
+        const int lane = g.lane;
+        int gym = i == -1 ? 1 : (i == g.H ? g.H - 2 : i);
+        gym = gym < 0 ? 0 : (gym > g.H - 1 ? g.H - 1 : gym);
         const float py = (float)(gym + 1);
-        const int toff = gym * c.W;
-        const float d = g_ld(c.dp + (toff + c.gxm));
-        if (gym + 1 < c.H) {   // next row's disparity / target lines
-            g_pf(c.dp + (toff + c.W + c.gxm));
+        const int toff = gym * g.W;
+        const float d = g_ld(c.dp + (toff + g.gxm));
+        if (gym + 1 < g.H) {   // next row's disparity / target lines
+            g_pf(c.dp + (toff + g.W + g.gxm));
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) g_pf(c.tg + (ch * c.HW + toff + c.W));
+            for (int ch = 0; ch < C; ++ch) g_pf(c.tg + (ch * g.HW + toff + g.W));
         }
         cur.D = d;
         const float zv = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
         float Tc[C], Xc[S][C];
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) Tc[ch] = g_ld(c.tg + (ch * c.HW + toff)) - c.rc[ch];
-        float st[NST4 * 4];
+        for (int ch = 0; ch < C; ++ch) Tc[ch] = g_ld(c.tg + (ch * g.HW + toff)) - c.rc[ch];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const float ap0 = fmaf(MD2_POSE(p, c.pb[s] + 1), py, c.apx[s][0]);
@@ -201,44 +247,45 @@ struct March {
             const float cu = fminf(fmaxf(u, 1.0f), c.Wf) - 1.0f;
             const float cv = fminf(fmaxf(vv, 1.0f), c.Hf) - 1.0f;
             int x0 = (int)cu, y0 = (int)cv;
-            x0 = x0 < c.W - 2 ? x0 : c.W - 2;
-            y0 = y0 < c.H - 2 ? y0 : c.H - 2;
+            x0 = x0 < g.W - 2 ? x0 : g.W - 2;
+            y0 = y0 < g.H - 2 ? y0 : g.H - 2;
             const float fx = cu - (float)x0, fy = cv - (float)y0;
-            const int off = y0 * c.W + x0;
+            const int off = y0 * g.W + x0;
             const float* r0 = c.sb[s] + off;
-            const float* r1 = r0 + c.W;
-            if (y0 + 2 < c.H) {   // the source row the next image row will need
+            const float* r1 = r0 + g.W;
+            if (y0 + 2 < g.H) {   // the source row the next image row will need
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) g_pf(r1 + (ch * c.HW + c.W));
+                for (int ch = 0; ch < C; ++ch) g_pf(r1 + (ch * g.HW + g.W));
             }
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-                const float v00 = g_ld(r0 + ch * c.HW), v01 = g_ld1(r0 + ch * c.HW), v10 = g_ld(r1 + ch * c.HW), v11 = g_ld1(r1 + ch * c.HW);
+                const float v00 = g_ld(r0 + ch * g.HW), v01 = g_ld1(r0 + ch * g.HW), v10 = g_ld(r1 + ch * g.HW), v11 = g_ld1(r1 + ch * g.HW);
                 const float dtop = v01 - v00, dbot = v11 - v10, dl = v10 - v00;
                 const float dd = dbot - dtop;
                 const float dix = fmaf(fy, dd, dtop);          // d value / d ix
                 const float diy = fmaf(fx, dd, dl);            // d value / d iy
                 Xc[s][ch] = fmaf(fy, diy, fmaf(fx, dtop, v00)) - c.rc[ch];
-                if (BWD) { st[s * SRCF + 7 + ch] = dix; st[s * SRCF + 7 + C + ch] = diy; }
+                if (BWD) { pk[O_SRC + s * SRCF + 7 + ch] = dix; pk[O_SRC + s * SRCF + 7 + C + ch] = diy; }
             }
             if (BWD) {
                 // clip-gradient masks (0 where the un-clipped coordinate is <= 1 or >= size), folded into q
-                st[s * SRCF + 0] = (u > 1.0f && u < c.Wf) ? q : 0.0f;
-                st[s * SRCF + 1] = (vv > 1.0f && vv < c.Hf) ? q : 0.0f;
-                st[s * SRCF + 2] = u; st[s * SRCF + 3] = vv;
-                st[s * SRCF + 4] = fx; st[s * SRCF + 5] = fy;
-                st[s * SRCF + 6] = i_as_float(off);
+                pk[O_SRC + s * SRCF + 0] = (u > 1.0f && u < c.Wf) ? q : 0.0f;
+                pk[O_SRC + s * SRCF + 1] = (vv > 1.0f && vv < c.Hf) ? q : 0.0f;
+                pk[O_SRC + s * SRCF + 2] = u; pk[O_SRC + s * SRCF + 3] = vv;
+                pk[O_SRC + s * SRCF + 4] = fx; pk[O_SRC + s * SRCF + 5] = fy;
+                pk[O_SRC + s * SRCF + 6] = i_as_float(off);
             }
         }
         if (BWD) {
-            st[S * SRCF] = zv;
+            pk[O_Z] = zv; pk[O_D] = d;
 #pragma unroll
-            for (int k = NSTF; k < NST4 * 4; ++k) st[k] = 0.f;
+            for (int ch = 0; ch < C; ++ch) {
+                pk[O_YM + ch] = Tc[ch];
 #pragma unroll
-            for (int k = 0; k < NST4; ++k) {
-                Vec4 s4; s4.x = st[4 * k]; s4.y = st[4 * k + 1]; s4.z = st[4 * k + 2]; s4.w = st[4 * k + 3];
-                c.ring[(SLOT * NST4 + k) * 32 + lane] = s4;
+                for (int s = 0; s < S; ++s) pk[O_XM + s * C + ch] = Xc[s][ch];
             }
+#pragma unroll
+            for (int k = NPPF; k < NPP4 * 4; ++k) pk[k] = 0.f;
         }
         // horizontal 3-sums (window column centred on this lane)
 #pragma unroll
@@ -259,12 +306,13 @@ struct March {
     }
 
     // ---- W(i-1): windows centred on row q = i-1; rows a = i-2, b = i-1, cur = i ----
-    static MD2_DEV void stage_windows(const FusedParams& p, const Ctx& c, Acc& acc, const Row& a, const Row& b,
-                                      const Row& cur, Coef& out, int i) {
-        const int lane = c.lane;
+    static MD2_DEV void stage_windows(const FusedParams& p, const CtxF& c, AccF& acc, const Row& a, const Row& b,
+                                      const Row& cur, int i, float (&wp)[NWP4 * 4]) {
+        const Geo& g = c.g;
+        const int lane = g.lane;
         const int q = i - 1;
-        const bool row_in = q >= 0 && q < c.H;
-        const bool row_own = q >= c.Y0 && q < c.Y1;
+        const bool row_in = q >= 0 && q < g.H;
+        const bool row_own = q >= g.Y0 && q < g.Y1;
         // SSIM from 9-sample sums centred on rc, everything scaled by 81 (mu9 = 9 mu, ...):
         //   S = A B / (Cc D), A = 2 mux muy + c1, B = 2 sxy + c2, Cc = mux^2 + muy^2 + c1, D = sx + sy + c2
         constexpr float C1 = 81.0f * SSIM_C1, C2 = 81.0f * SSIM_C2;
@@ -326,21 +374,21 @@ struct March {
         }
         float wlv = pe_best;
         if (c.am) {
-            const int qc = q < 0 ? 0 : (q > c.H - 1 ? c.H - 1 : q);
-            const float am = g_ld(c.am + (qc * c.W + c.gxm));
+            const int qc = q < 0 ? 0 : (q > g.H - 1 ? g.H - 1 : q);
+            const float am = g_ld(c.am + (qc * g.W + g.gxm));
             if (am <= wlv) { wlv = am; sel = -1; }   // mask is first in the cat: wins ties
         }
-        const bool own = row_own && c.pcol;
+        const bool own = row_own && g.pcol;
         acc.warp_sum += own ? wlv : 0.f;
         if (c.do_viz && own) {
-            const long long o = (long long)c.n * c.HW + q * c.W + c.gxm;
+            const long long o = (long long)g.n * g.HW + q * g.W + g.gxm;   // (gxm == gxr on the output columns)
             if (p.viz_loss) p.viz_loss[o] = wlv;
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 if (p.viz_warped[s]) {
 #pragma unroll
                     for (int ch = 0; ch < C; ++ch)
-                        p.viz_warped[s][((long long)c.n * C + ch) * c.HW + q * c.W + c.gxm] = b.xm[s][ch] + c.rc[ch];
+                        p.viz_warped[s][((long long)g.n * C + ch) * g.HW + q * g.W + g.gxm] = b.xm[s][ch] + c.rc[ch];
                 }
         }
         if (!BWD) {
@@ -353,269 +401,367 @@ struct March {
                 gy_ += fabsf(b.ym[ch] - cur.ym[ch]);
             }
             if (own) {
-                if (c.has_right) acc.ssx += fabsf(b.D - Dr) * MD2_EXP(-gx_ * (1.0f / C));
-                if (q + 1 < c.H) acc.ssy += fabsf(b.D - cur.D) * MD2_EXP(-gy_ * (1.0f / C));
+                if (g.has_right) acc.ssx += fabsf(b.D - Dr) * MD2_EXP(-gx_ * (1.0f / C));
+                if (q + 1 < g.H) acc.ssy += fabsf(b.D - cur.D) * MD2_EXP(-gy_ * (1.0f / C));
                 acc.dsum += b.D;
             }
         }
         if (BWD) {
             // scale by the upstream cotangent of this window (0 outside the image / where the automask won)
             const float k = (row_in && sel >= 0) ? c.kq : 0.f;
-            out.sel = sel;
             const int e0 = w_up(sel, lane), e2 = w_dn(sel, lane);
             const float m0 = (e0 == 0) ? c.wl : 0.f, m1 = (sel == 0) ? 1.f : 0.f, m2 = (e2 == 0) ? c.wr : 0.f;
 #pragma unroll
             for (int j = 0; j < 3 * C; ++j) {
                 const float c1 = cf[j] * k;
                 const float c0 = w_up(c1, lane), c2 = w_dn(c1, lane);
-                out.t[j] = fmaf(c.wl, c0, fmaf(c.wr, c2, c1));
-                out.s0[j] = (S > 1) ? fmaf(m0, c0, fmaf(m2, c2, m1 * c1)) : 0.f;
+                wp[j] = fmaf(c.wl, c0, fmaf(c.wr, c2, c1));
+                wp[3 * C + j] = (S > 1) ? fmaf(m0, c0, fmaf(m2, c2, m1 * c1)) : 0.f;
             }
+            wp[6 * C] = i_as_float(sel);
+#pragma unroll
+            for (int k2 = NWPF; k2 < NWP4 * 4; ++k2) wp[k2] = 0.f;
         }
     }
 
-    // ---- P(i-2): backward of pixel row r = i-2; rows a = i-2, b = i-1; window rows ra = r-1, rb = r, rc = r+1 ----
-    template <int RSLOT>
-    static MD2_DEV void stage_pixels(const FusedParams& p, const Ctx& c, Acc& acc, const Row& a, const Row& b,
-                                     const Coef& ra, const Coef& rb, const Coef& rcf, int i) {
-        const int lane = c.lane;
-        const int r = i - 2;
-        // vertical smoothness edge of row r (towards r+1); it is also the "up" edge of row r+1
-        float ey = 0.f;
-        {
-            float g = 0.f;
+    // hand one ring slot to warp B: wait until it is empty, store the packets, signal full
+    static MD2_DEV void publish(CtxF& c, const float (&pk)[NPP4 * 4], const float (&wp)[NWP4 * 4]) {
+        const int slot = c.gslot % MARCH_DEPTH, fill = c.gslot / MARCH_DEPTH;
+        mb_wait(c.bars, BAR_EMPTY + slot, (fill & 1) ^ 1);   // the previous fill of this slot has been consumed
+        Vec4* dst = c.ring + slot * (SLOT4 * 32) + c.g.lane;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) g += fabsf(a.ym[ch] - b.ym[ch]);
-            const float w = f_ex2(g * (-1.4426950408889634f / C)) * c.cyn;
-            if (r >= 0 && r + 1 < c.H) ey = sgn_scaled(a.D - b.D, w);
+        for (int k = 0; k < NPP4; ++k) {
+            Vec4 s4; s4.x = pk[4 * k]; s4.y = pk[4 * k + 1]; s4.z = pk[4 * k + 2]; s4.w = pk[4 * k + 3];
+            dst[k * 32] = s4;
         }
-        if (i >= c.Y0 + 2) {
-            const float wu = (r == 1) ? 2.f : 1.f, wd = (r == c.H - 2) ? 2.f : 1.f;
-            const float pyr = (float)(r + 1);
-            float st[NST4 * 4];
 #pragma unroll
-            for (int k = 0; k < NST4; ++k) {
-                const Vec4 s4 = c.ring[(RSLOT * NST4 + k) * 32 + lane];
-                st[4 * k] = s4.x; st[4 * k + 1] = s4.y; st[4 * k + 2] = s4.z; st[4 * k + 3] = s4.w;
-            }
-            const float zr = st[S * SRCF];
-            float dbar_z = 0.f;
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                // d loss / d warped_s at this pixel
-                float ibar[C];
-                bool act = false;
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    float sa, sb_, sg;
-                    const float ta = fmaf(wu, ra.t[3 * ch], fmaf(wd, rcf.t[3 * ch], rb.t[3 * ch]));
-                    const float tb = fmaf(wu, ra.t[3 * ch + 1], fmaf(wd, rcf.t[3 * ch + 1], rb.t[3 * ch + 1]));
-                    const float tgm = fmaf(wu, ra.t[3 * ch + 2], fmaf(wd, rcf.t[3 * ch + 2], rb.t[3 * ch + 2]));
-                    if (S == 1) { sa = ta; sb_ = tb; sg = tgm; }
-                    else {
-                        const float za = fmaf(wu, ra.s0[3 * ch], fmaf(wd, rcf.s0[3 * ch], rb.s0[3 * ch]));
-                        const float zb = fmaf(wu, ra.s0[3 * ch + 1], fmaf(wd, rcf.s0[3 * ch + 1], rb.s0[3 * ch + 1]));
-                        const float zg = fmaf(wu, ra.s0[3 * ch + 2], fmaf(wd, rcf.s0[3 * ch + 2], rb.s0[3 * ch + 2]));
-                        if (s == 0) { sa = za; sb_ = zb; sg = zg; }
-                        else { sa = ta - za; sb_ = tb - zb; sg = tgm - zg; }
-                    }
-                    const float xj = a.xm[s][ch], yj = a.ym[ch];
-                    float g = fmaf(xj, sb_, fmaf(yj, sg, sa));
-                    if (rb.sel == s) g += sgn_scaled(xj - yj, c.cl1);
-                    ibar[ch] = g * c.mp;
-                    act = act || (ibar[ch] != 0.f);
-                }
-                // sources not selected anywhere in the 3x3 neighbourhood of any lane skip all of this
-                if (w_any(act)) {
-                    const float qa = st[s * SRCF + 0], qb = st[s * SRCF + 1], u = st[s * SRCF + 2], vv = st[s * SRCF + 3];
-                    const float fx = st[s * SRCF + 4], fy = st[s * SRCF + 5];
-                    const int off = f_as_int(st[s * SRCF + 6]);
-                    float du = 0.f, dv = 0.f;
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        du = fmaf(ibar[ch], st[s * SRCF + 7 + ch], du);
-                        dv = fmaf(ibar[ch], st[s * SRCF + 7 + C + ch], dv);
-                    }
-                    const float cb0 = du * qa, cb1 = dv * qb;
-                    const float cb2 = -fmaf(cb0, u, cb1 * vv);
-                    const float ap0 = fmaf(MD2_POSE(p, c.pb[s] + 1), pyr, c.apx[s][0]);
-                    const float ap1 = fmaf(MD2_POSE(p, c.pb[s] + 4), pyr, c.apx[s][1]);
-                    const float ap2 = fmaf(MD2_POSE(p, c.pb[s] + 7), pyr, c.apx[s][2]);
-                    dbar_z = fmaf(cb0, ap0, fmaf(cb1, ap1, fmaf(cb2, ap2, dbar_z)));
-                    const float t0 = cb0 * zr, t1 = cb1 * zr, t2 = cb2 * zr;
-                    acc.P0[s][0] += t0; acc.P0[s][1] += t1; acc.P0[s][2] += t2;
-                    acc.P1[s][0] = fmaf(t0, pyr, acc.P1[s][0]); acc.P1[s][1] = fmaf(t1, pyr, acc.P1[s][1]);
-                    acc.P1[s][2] = fmaf(t2, pyr, acc.P1[s][2]);
-                    acc.Ph[s][0] += cb0; acc.Ph[s][1] += cb1; acc.Ph[s][2] += cb2;
-                    // source-image gradient: scatter with vertical carry + merge with the right-hand lane
-                    if (c.gb[s]) {
-                        const bool sval = act;     // (ibar is already 0 outside the output columns)
-                        const float gx1 = 1.f - fx, gy1 = 1.f - fy;
-                        float tq0[C], tq1[C];
-#pragma unroll
-                        for (int ch = 0; ch < C; ++ch) { tq0[ch] = gx1 * gy1 * ibar[ch]; tq1[ch] = fx * gy1 * ibar[ch]; }
-                        const int key = sval ? off : -2;
-                        const bool have = acc.coff[s] >= 0;
-                        const bool aligned = have && key == acc.coff[s] + c.W;
-                        if (aligned) {
-#pragma unroll
-                            for (int ch = 0; ch < C; ++ch) { tq0[ch] += acc.car0[s][ch]; tq1[ch] += acc.car1[s][ch]; }
-                        } else if (have) {
-                            float* o = c.gb[s] + (acc.coff[s] + c.W);
-#pragma unroll
-                            for (int ch = 0; ch < C; ++ch) {
-                                g_red(o + ch * c.HW, acc.car0[s][ch]);
-                                g_red1(o + ch * c.HW, acc.car1[s][ch]);
-                            }
-                        }
-                        // my right tap is the right lane's left tap
-                        const int key_r = w_dn(key, lane), key_l = w_up(key, lane);
-                        const bool absorbed = sval && lane < 31 && key_r == key + 1;
-                        const bool absorb = sval && lane > 0 && key_l >= 0 && key_l + 1 == key;
-#pragma unroll
-                        for (int ch = 0; ch < C; ++ch) {
-                            const float fl = w_up(tq1[ch], lane);
-                            if (absorb) tq0[ch] += fl;
-                        }
-                        if (sval) {
-                            float* o = c.gb[s] + off;
-#pragma unroll
-                            for (int ch = 0; ch < C; ++ch) {
-                                g_red(o + ch * c.HW, tq0[ch]);
-                                if (!absorbed) g_red1(o + ch * c.HW, tq1[ch]);
-                                acc.car0[s][ch] = gx1 * fy * ibar[ch];
-                                acc.car1[s][ch] = fx * fy * ibar[ch];
-                            }
-                        }
-                        acc.coff[s] = sval ? off : -1;
-                    }
-                } else if (c.gb[s]) {
-                    // nobody scatters into source s on this row: flush what the previous row carried
-                    if (acc.coff[s] >= 0) {
-                        float* o = c.gb[s] + (acc.coff[s] + c.W);
-#pragma unroll
-                        for (int ch = 0; ch < C; ++ch) {
-                            g_red(o + ch * c.HW, acc.car0[s][ch]);
-                            g_red1(o + ch * c.HW, acc.car1[s][ch]);
-                        }
-                    }
-                    acc.coff[s] = -1;
-                }
-            }
-            // depth -> disparity:  dz/dd = -a z^2
-            float gd = c.nega * zr * zr * dbar_z;
-            // smoothness gradient (src/utils.jl:159-173 with the mean-normalisation of
-            // src/training.jl:64-65 folded in):  A ghat_j - B
-            {
-                const float Dr = w_dn(a.D, lane);
-                float g = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) g += fabsf(a.ym[ch] - w_dn(a.ym[ch], lane));
-                const float w = f_ex2(g * (-1.4426950408889634f / C)) * c.cxn;
-                const float ex = c.has_right ? sgn_scaled(a.D - Dr, w) : 0.f;
-                const float exl = w_up(ex, lane);
-                const float gh = (ex - exl) + (ey - acc.ey_prev);
-                gd += fmaf(c.sA, gh, -c.sB);
-            }
-            gd *= c.mp;
-            if (c.pcol) g_st(c.gd + (r * c.W + c.gxm), gd);   // (gxm == gxr on the output columns)
+        for (int k = 0; k < NWP4; ++k) {
+            Vec4 s4; s4.x = wp[4 * k]; s4.y = wp[4 * k + 1]; s4.z = wp[4 * k + 2]; s4.w = wp[4 * k + 3];
+            dst[(NPP4 + k) * 32] = s4;
         }
-        acc.ey_prev = ey;
+        mb_arrive(c.bars, BAR_FULL + slot);
+        c.gslot = c.gslot + 1 == SLOT_WRAP ? 0 : c.gslot + 1;
     }
 
-    template <int PH>
-    static MD2_DEV void step(const FusedParams& p, const Ctx& c, Acc& acc, Row& a, Row& b, Row& cur, Coef& ra, Coef& rb,
-                             Coef& rcf, int i) {
-        stage_load<PH>(p, c, acc, cur, i);
-        stage_windows(p, c, acc, a, b, cur, rcf, i);
-        if (BWD) stage_pixels<(PH + 1) % 3>(p, c, acc, a, b, ra, rb, rcf, i);
+    static MD2_DEV void stepF(const FusedParams& p, CtxF& c, AccF& acc, Row& a, Row& b, Row& cur, int i) {
+        float pk[NPP4 * 4], wp[NWP4 * 4];
+        stage_load(p, c, cur, i, pk);
+        stage_windows(p, c, acc, a, b, cur, i, wp);
+        if (BWD) publish(c, pk, wp);
     }
 
-    // one warp, one (strip sx, chunk cy, scale*N+n = z) work item; on return lane-local partial
-    // sums are in v[0..NPART)
-    static MD2_DEV void run(const FusedParams& p, int sx, int cy, int z, int lane, float* wsm, float (&v)[32]) {
-        Ctx c;
-        c.lane = lane;
-        c.W = p.W; c.H = p.H; c.HW = p.W * p.H;
-        c.scale = z / p.N; c.n = z - c.scale * p.N;
-        const int X0 = sx * OW;
-        c.Y0 = cy * p.m_R;
-        c.Y1 = (c.Y0 + p.m_R < c.H) ? c.Y0 + p.m_R : c.H;
-        // this lane's column (reflect-pad(1): only -1 and W are ever used by an in-image window)
-        c.gxr = X0 - HALO + lane;
-        int gxm = c.gxr == -1 ? 1 : (c.gxr == c.W ? c.W - 2 : c.gxr);
-        c.gxm = gxm < 0 ? 0 : (gxm > c.W - 1 ? c.W - 1 : gxm);
-        c.col_img = c.gxr >= 0 && c.gxr < c.W;
-        const bool wcol = c.col_img && lane >= 1 && lane <= 30;             // window column
-        c.pcol = c.col_img && lane >= HALO && lane < 32 - HALO;             // output pixel column
-        c.has_right = c.col_img && c.gxr + 1 < c.W;
-        c.px = (float)(c.gxm + 1);
-        c.Wf = (float)c.W; c.Hf = (float)c.H;
-        c.do_viz = c.scale == p.L - 1 && (p.viz_loss != nullptr || p.viz_warped[0] != nullptr || (S > 1 && p.viz_warped[S - 1] != nullptr));
-
-        const float* tgn = p.tgt + (long long)c.n * p.tgt_ns;
-        c.tg = tgn + c.gxm;
+    // warp F of one work item; gslot: running ring-slot counter of this warp
+    static MD2_DEV void run_forward(const FusedParams& p, int sx, int cy, int z, int lane, float* wsm, int& gslot, float (&v)[32]) {
+        CtxF c;
+        geometry(p, sx, cy, z, lane, c.g);
+        const Geo& g = c.g;
+        const bool wcol = g.col_img && lane >= 1 && lane <= 30;             // window column
+        c.Wf = (float)g.W; c.Hf = (float)g.H;
+        c.do_viz = g.scale == p.L - 1 && (p.viz_loss != nullptr || p.viz_warped[0] != nullptr || (S > 1 && p.viz_warped[S - 1] != nullptr));
+        const float* tgn = p.tgt + (long long)g.n * p.tgt_ns;
+        c.tg = tgn + g.gxm;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            c.sb[s] = p.src[s] + (long long)c.n * p.src_ns[s];
-            c.gb[s] = (BWD && p.gsrc[s]) ? p.gsrc[s] + (long long)c.n * p.src_ns[s] : nullptr;
-        }
-        c.dp = p.dfull[c.scale] + (long long)c.n * c.HW;
-        c.gd = BWD ? p.gfull[c.scale] + (long long)c.n * c.HW : nullptr;
-        c.am = p.automask ? p.automask + (long long)c.n * c.HW : nullptr;
-
+        for (int s = 0; s < S; ++s) c.sb[s] = p.src[s] + (long long)g.n * p.src_ns[s];
+        c.dp = p.dfull[g.scale] + (long long)g.n * g.HW;
+        c.am = p.automask ? p.automask + (long long)g.n * g.HW : nullptr;
         // centring constant of the window sums (any constant is exact; a local value keeps the
         // centred squares small): the target at the middle of the strip chunk
         {
-            const int ym = (c.Y0 + c.Y1) >> 1;
-            const int xm = X0 + OW / 2 < c.W ? X0 + OW / 2 : c.W - 1;
+            const int ym = (g.Y0 + g.Y1) >> 1;
+            const int xm = sx * OW + OW / 2 < g.W ? sx * OW + OW / 2 : g.W - 1;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) c.rc[ch] = tgn[ch * c.HW + ym * c.W + xm];
+            for (int ch = 0; ch < C; ++ch) c.rc[ch] = tgn[ch * g.HW + ym * g.W + xm];
         }
+        const float px = (float)(g.gxm + 1);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            c.pb[s] = p.pose_slot + (s * p.N + c.n) * 12;
+            c.pb[s] = p.pose_slot + (s * p.N + g.n) * 12;
 #pragma unroll
             for (int k = 0; k < 3; ++k)   // A[:,0] px + A[:,2]: the lane-constant part of A p
-                c.apx[s][k] = fmaf(MD2_POSE(p, c.pb[s] + 3 * k), c.px, MD2_POSE(p, c.pb[s] + 3 * k + 2));
+                c.apx[s][k] = fmaf(MD2_POSE(p, c.pb[s] + 3 * k), px, MD2_POSE(p, c.pb[s] + 3 * k + 2));
         }
-        const float up_photo = p.gloss * p.loss_scale / ((float)c.W * (float)c.H * (float)p.N);
+        const float up_photo = p.gloss * p.loss_scale / ((float)g.W * (float)g.H * (float)p.N);
         c.kq = wcol ? up_photo * (PHOTO_ALPHA / C) * (-0.5f) : 0.f;
-        c.cl1 = up_photo * ((1.0f - PHOTO_ALPHA) / C);
-        c.mp = c.pcol ? 1.f : 0.f;
-        c.wl = (c.gxr == 1) ? 2.f : 1.f;
-        c.wr = (c.gxr == c.W - 2) ? 2.f : 1.f;
-        c.cxn = 1.0f / ((float)(c.W - 1) * (float)c.H * (float)p.N);
-        c.cyn = 1.0f / ((float)c.W * (float)(c.H - 1) * (float)p.N);
-        c.nega = -p.depth_a;
-        c.sA = 0.f; c.sB = 0.f;
-        if (BWD) {
-            const float* st = p.stats + ((long long)c.scale * p.N + c.n) * NSTAT;
-            const float up_s = p.gloss * p.loss_scale * p.smooth_w[c.scale];
-            c.sA = up_s;
-            if (p.normalize_disp) {
-                const float m = st[3] / (float)c.HW + 1e-7f;
-                c.sA = up_s / m;
-                c.sB = up_s * (c.cxn * st[1] + c.cyn * st[2]) / (m * m * (float)c.HW);
-            }
-        }
+        c.wl = (g.gxr == 1) ? 2.f : 1.f;
+        c.wr = (g.gxr == g.W - 2) ? 2.f : 1.f;
         c.ring = reinterpret_cast<Vec4*>(wsm);
+        c.bars = reinterpret_cast<mbar_t*>(wsm + RING_FLOATS);
+        c.gslot = gslot;
         // pin the per-lane invariants in registers (otherwise they are re-derived in every row)
-        keep(c.gxm); keep(c.tg);
+        keep(c.g.gxm); keep(c.tg); keep(c.dp);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.sb[s]);
-            if (BWD) keep(c.gb[s]);
 #pragma unroll
             for (int k = 0; k < 3; ++k) keep(c.apx[s][k]);
         }
-        keep(c.dp);
-        if (BWD) { keep(c.gd); keep(c.kq); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); }
+        if (BWD) keep(c.kq);
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) keep(c.rc[ch]);
 
-        Acc acc;
+        AccF acc;
         acc.warp_sum = acc.ssx = acc.ssy = acc.dsum = 0.f;
+        Row r0, r1, r2;
+        // rows i0, i0+1: load only (their ring slots carry pixel packets, no window packet yet); then
+        // every row runs L(i), W(i-1); the loop is unrolled by 3 so that the three row registers
+        // rotate roles without moves
+        const int i0 = g.Y0 - HALO, iend = g.Y1 + HALO;
+        {
+            float pk[NPP4 * 4], wp[NWP4 * 4];
+#pragma unroll
+            for (int k = 0; k < NWP4 * 4; ++k) wp[k] = 0.f;
+            stage_load(p, c, r0, i0, pk);
+            if (BWD) publish(c, pk, wp);
+            stage_load(p, c, r1, i0 + 1, pk);
+            if (BWD) publish(c, pk, wp);
+        }
+        int i = i0 + 2;
+        for (; i + 2 < iend; i += 3) {
+            stepF(p, c, acc, r0, r1, r2, i);
+            stepF(p, c, acc, r1, r2, r0, i + 1);
+            stepF(p, c, acc, r2, r0, r1, i + 2);
+        }
+        if (i < iend) {
+            stepF(p, c, acc, r0, r1, r2, i);
+            if (i + 1 < iend) stepF(p, c, acc, r1, r2, r0, i + 1);
+        }
+        gslot = c.gslot;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.f;
+        v[0] = acc.warp_sum; v[1] = acc.ssx; v[2] = acc.ssy; v[3] = acc.dsum;
+    }
+
+    // =====================================================================================
+    // warp B
+    // =====================================================================================
+    struct CtxB {
+        Geo g;
+        float* gb[S];
+        float* gd;                   // full-resolution disparity gradient of this (scale, image)
+        float apx[S][3];
+        int pb[S];
+        float cl1;                   // up_photo * (1-alpha)/C
+        float mp;                    // pcol ? 1 : 0
+        float cxn, cyn, sA, sB, nega;
+        const Vec4* ring;
+        mbar_t* bars;
+    };
+    struct AccB {
+        float P0[S][3], P1[S][3], Ph[S][3];
+        float car0[S][C], car1[S][C];
+        int coff[S];
+        float ey_prev;
+    };
+
+    static MD2_DEV const Vec4* slot_ptr(const CtxB& c, int gs) { return c.ring + (gs % MARCH_DEPTH) * (SLOT4 * 32) + c.g.lane; }
+    // acquire = wait until warp F has filled the slot, release = hand it back
+    static MD2_DEV void acquire(const CtxB& c, int gs) { mb_wait(c.bars, BAR_FULL + gs % MARCH_DEPTH, (gs / MARCH_DEPTH) & 1); }
+    static MD2_DEV void release(const CtxB& c, int gs) { mb_arrive(c.bars, BAR_EMPTY + gs % MARCH_DEPTH); }
+
+    // vertical smoothness edge between rows y and y+1 (own target values / disparities of both rows)
+    static MD2_DEV float edge_y(const CtxB& c, int y, const float* ymA, float DA, const float* ymB, float DB) {
+        float gsum = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gsum += fabsf(ymA[ch] - ymB[ch]);
+        const float w = f_ex2(gsum * (-1.4426950408889634f / C)) * c.cyn;
+        return (y >= 0 && y + 1 < c.g.H) ? sgn_scaled(DA - DB, w) : 0.f;
+    }
+
+    // ---- P(r): slot s0 = row r (pixel packet, window packet r-1), s1 = row r+1 (window r), s2 = row r+2 (window r+1) ----
+    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, const Vec4* s0, const Vec4* s1,
+                                     const Vec4* s2) {
+        const Geo& g = c.g;
+        const int lane = g.lane;
+        float pk[NPP4 * 4], wa[NWP4 * 4], wb[NWP4 * 4], wc[NWP4 * 4], nx[NYD4 * 4];
+#pragma unroll
+        for (int k = 0; k < NPP4; ++k) {
+            const Vec4 t = s0[k * 32];
+            pk[4 * k] = t.x; pk[4 * k + 1] = t.y; pk[4 * k + 2] = t.z; pk[4 * k + 3] = t.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NWP4; ++k) {
+            const Vec4 ta = s0[(NPP4 + k) * 32], tb = s1[(NPP4 + k) * 32], tc = s2[(NPP4 + k) * 32];
+            wa[4 * k] = ta.x; wa[4 * k + 1] = ta.y; wa[4 * k + 2] = ta.z; wa[4 * k + 3] = ta.w;
+            wb[4 * k] = tb.x; wb[4 * k + 1] = tb.y; wb[4 * k + 2] = tb.z; wb[4 * k + 3] = tb.w;
+            wc[4 * k] = tc.x; wc[4 * k + 1] = tc.y; wc[4 * k + 2] = tc.z; wc[4 * k + 3] = tc.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NYD4; ++k) {   // ym[C], D of row r+1
+            const Vec4 t = s1[k * 32];
+            nx[4 * k] = t.x; nx[4 * k + 1] = t.y; nx[4 * k + 2] = t.z; nx[4 * k + 3] = t.w;
+        }
+        const float Da = pk[O_D];
+        const float ey = edge_y(c, r, pk + O_YM, Da, nx + O_YM, nx[O_D]);
+        const float wu = (r == 1) ? 2.f : 1.f, wd = (r == g.H - 2) ? 2.f : 1.f;
+        const float pyr = (float)(r + 1);
+        const int selr = f_as_int(wb[6 * C]);
+        const float zr = pk[O_Z];
+        float dbar_z = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float* st = pk + O_SRC + s * SRCF;
+            // d loss / d warped_s at this pixel
+            float ibar[C];
+            bool act = false;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                float sa, sb_, sg;
+                const float ta = fmaf(wu, wa[3 * ch], fmaf(wd, wc[3 * ch], wb[3 * ch]));
+                const float tb = fmaf(wu, wa[3 * ch + 1], fmaf(wd, wc[3 * ch + 1], wb[3 * ch + 1]));
+                const float tgm = fmaf(wu, wa[3 * ch + 2], fmaf(wd, wc[3 * ch + 2], wb[3 * ch + 2]));
+                if (S == 1) { sa = ta; sb_ = tb; sg = tgm; }
+                else {
+                    const float za = fmaf(wu, wa[3 * C + 3 * ch], fmaf(wd, wc[3 * C + 3 * ch], wb[3 * C + 3 * ch]));
+                    const float zb = fmaf(wu, wa[3 * C + 3 * ch + 1], fmaf(wd, wc[3 * C + 3 * ch + 1], wb[3 * C + 3 * ch + 1]));
+                    const float zg = fmaf(wu, wa[3 * C + 3 * ch + 2], fmaf(wd, wc[3 * C + 3 * ch + 2], wb[3 * C + 3 * ch + 2]));
+                    if (s == 0) { sa = za; sb_ = zb; sg = zg; }
+                    else { sa = ta - za; sb_ = tb - zb; sg = tgm - zg; }
+                }
+                const float xj = pk[O_XM + s * C + ch], yj = pk[O_YM + ch];
+                float gv = fmaf(xj, sb_, fmaf(yj, sg, sa));
+                if (selr == s) gv += sgn_scaled(xj - yj, c.cl1);
+                ibar[ch] = gv * c.mp;
+                act = act || (ibar[ch] != 0.f);
+            }
+            // sources not selected anywhere in the 3x3 neighbourhood of any lane skip all of this
+            if (w_any(act)) {
+                const float qa = st[0], qb = st[1], u = st[2], vv = st[3];
+                const float fx = st[4], fy = st[5];
+                const int off = f_as_int(st[6]);
+                float du = 0.f, dv = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    du = fmaf(ibar[ch], st[7 + ch], du);
+                    dv = fmaf(ibar[ch], st[7 + C + ch], dv);
+                }
+                const float cb0 = du * qa, cb1 = dv * qb;
+                const float cb2 = -fmaf(cb0, u, cb1 * vv);
+                const float ap0 = fmaf(MD2_POSE(p, c.pb[s] + 1), pyr, c.apx[s][0]);
+                const float ap1 = fmaf(MD2_POSE(p, c.pb[s] + 4), pyr, c.apx[s][1]);
+                const float ap2 = fmaf(MD2_POSE(p, c.pb[s] + 7), pyr, c.apx[s][2]);
+                dbar_z = fmaf(cb0, ap0, fmaf(cb1, ap1, fmaf(cb2, ap2, dbar_z)));
+                const float t0 = cb0 * zr, t1 = cb1 * zr, t2 = cb2 * zr;
+                acc.P0[s][0] += t0; acc.P0[s][1] += t1; acc.P0[s][2] += t2;
+                acc.P1[s][0] = fmaf(t0, pyr, acc.P1[s][0]); acc.P1[s][1] = fmaf(t1, pyr, acc.P1[s][1]);
+                acc.P1[s][2] = fmaf(t2, pyr, acc.P1[s][2]);
+                acc.Ph[s][0] += cb0; acc.Ph[s][1] += cb1; acc.Ph[s][2] += cb2;
+                // source-image gradient: scatter with vertical carry + merge with the right-hand lane
+                if (c.gb[s]) {
+                    const bool sval = act;     // (ibar is already 0 outside the output columns)
+                    const float gx1 = 1.f - fx, gy1 = 1.f - fy;
+                    float tq0[C], tq1[C];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) { tq0[ch] = gx1 * gy1 * ibar[ch]; tq1[ch] = fx * gy1 * ibar[ch]; }
+                    const int key = sval ? off : -2;
+                    const bool have = acc.coff[s] >= 0;
+                    const bool aligned = have && key == acc.coff[s] + g.W;
+                    if (aligned) {
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) { tq0[ch] += acc.car0[s][ch]; tq1[ch] += acc.car1[s][ch]; }
+                    } else if (have) {
+                        float* o = c.gb[s] + (acc.coff[s] + g.W);
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) {
+                            g_red(o + ch * g.HW, acc.car0[s][ch]);
+                            g_red1(o + ch * g.HW, acc.car1[s][ch]);
+                        }
+                    }
+                    // my right tap is the right lane's left tap
+                    const int key_r = w_dn(key, lane), key_l = w_up(key, lane);
+                    const bool absorbed = sval && lane < 31 && key_r == key + 1;
+                    const bool absorb = sval && lane > 0 && key_l >= 0 && key_l + 1 == key;
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        const float fl = w_up(tq1[ch], lane);
+                        if (absorb) tq0[ch] += fl;
+                    }
+                    if (sval) {
+                        float* o = c.gb[s] + off;
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) {
+                            g_red(o + ch * g.HW, tq0[ch]);
+                            if (!absorbed) g_red1(o + ch * g.HW, tq1[ch]);
+                            acc.car0[s][ch] = gx1 * fy * ibar[ch];
+                            acc.car1[s][ch] = fx * fy * ibar[ch];
+                        }
+                    }
+                    acc.coff[s] = sval ? off : -1;
+                }
+            } else if (c.gb[s]) {
+                // nobody scatters into source s on this row: flush what the previous row carried
+                if (acc.coff[s] >= 0) {
+                    float* o = c.gb[s] + (acc.coff[s] + g.W);
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        g_red(o + ch * g.HW, acc.car0[s][ch]);
+                        g_red1(o + ch * g.HW, acc.car1[s][ch]);
+                    }
+                }
+                acc.coff[s] = -1;
+            }
+        }
+        // depth -> disparity:  dz/dd = -a z^2
+        float gd = c.nega * zr * zr * dbar_z;
+        // smoothness gradient (src/utils.jl:159-173 with the mean-normalisation of
+        // src/training.jl:64-65 folded in):  A ghat_j - B
+        {
+            const float Dr = w_dn(Da, lane);
+            float gsum = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) gsum += fabsf(pk[O_YM + ch] - w_dn(pk[O_YM + ch], lane));
+            const float w = f_ex2(gsum * (-1.4426950408889634f / C)) * c.cxn;
+            const float ex = g.has_right ? sgn_scaled(Da - Dr, w) : 0.f;
+            const float exl = w_up(ex, lane);
+            const float gh = (ex - exl) + (ey - acc.ey_prev);
+            gd += fmaf(c.sA, gh, -c.sB);
+        }
+        if (g.pcol) g_st(c.gd + (r * g.W + g.gxm), gd);   // (gxm == gxr on the output columns)
+        acc.ey_prev = ey;
+    }
+
+    // warp B of one work item; gslot: running ring-slot counter of this warp
+    static MD2_DEV void run_backward(const FusedParams& p, int sx, int cy, int z, int lane, float* wsm, int& gslot, float (&v)[32]) {
+        CtxB c;
+        geometry(p, sx, cy, z, lane, c.g);
+        const Geo& g = c.g;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            c.gb[s] = p.gsrc[s] ? p.gsrc[s] + (long long)g.n * p.src_ns[s] : nullptr;
+            c.pb[s] = p.pose_slot + (s * p.N + g.n) * 12;
+        }
+        c.gd = p.gfull[g.scale] + (long long)g.n * g.HW;
+        const float px = (float)(g.gxm + 1);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                c.apx[s][k] = fmaf(MD2_POSE(p, c.pb[s] + 3 * k), px, MD2_POSE(p, c.pb[s] + 3 * k + 2));
+        const float up_photo = p.gloss * p.loss_scale / ((float)g.W * (float)g.H * (float)p.N);
+        c.cl1 = up_photo * ((1.0f - PHOTO_ALPHA) / C);
+        c.mp = g.pcol ? 1.f : 0.f;
+        c.cxn = 1.0f / ((float)(g.W - 1) * (float)g.H * (float)p.N);
+        c.cyn = 1.0f / ((float)g.W * (float)(g.H - 1) * (float)p.N);
+        c.nega = -p.depth_a;
+        {
+            const float* st = p.stats + ((long long)g.scale * p.N + g.n) * NSTAT;
+            const float up_s = p.gloss * p.loss_scale * p.smooth_w[g.scale];
+            c.sA = up_s; c.sB = 0.f;
+            if (p.normalize_disp) {
+                const float m = st[3] / (float)g.HW + 1e-7f;
+                c.sA = up_s / m;
+                c.sB = up_s * (c.cxn * st[1] + c.cyn * st[2]) / (m * m * (float)g.HW);
+            }
+        }
+        c.ring = reinterpret_cast<const Vec4*>(wsm);
+        c.bars = reinterpret_cast<mbar_t*>(wsm + RING_FLOATS);
+        keep(c.g.gxm); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            keep(c.gb[s]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) keep(c.apx[s][k]);
+        }
+        AccB acc;
         acc.ey_prev = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -625,55 +771,59 @@ struct March {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) acc.car0[s][ch] = acc.car1[s][ch] = 0.f;
         }
-        Row r0, r1, r2;
-        Coef k0, k1, k2;
+        // ring slot gslot + j holds row Y0 - 2 + j of this item
+        int gs = gslot;
+        acquire(c, gs);                                            // row Y0-2: nothing to read
+        release(c, gs);
+        acquire(c, gs + 1);                                        // row Y0-1
+        acquire(c, gs + 2);                                        // row Y0
+        {   // the "up" edge of the first row
+            float ya[NYD4 * 4], yb[NYD4 * 4];
+            const Vec4* sa = slot_ptr(c, gs + 1);
+            const Vec4* sb = slot_ptr(c, gs + 2);
 #pragma unroll
-        for (int j = 0; j < 3 * C; ++j) k0.t[j] = k0.s0[j] = k1.t[j] = k1.s0[j] = k2.t[j] = k2.s0[j] = 0.f;
-        k0.sel = k1.sel = k2.sel = -1;
-
-        // rows i0, i0+1: load only; then every row runs L(i), W(i-1) [, P(i-2)]; the loop is unrolled
-        // by 3 so that the three row / coefficient registers rotate roles without moves
-        const int i0 = c.Y0 - HALO, iend = c.Y1 + HALO;
-        stage_load<0>(p, c, acc, r0, i0);
-        stage_load<1>(p, c, acc, r1, i0 + 1);
-        int i = i0 + 2;
-        for (; i + 2 < iend; i += 3) {
-            step<2>(p, c, acc, r0, r1, r2, k0, k1, k2, i);
-            step<0>(p, c, acc, r1, r2, r0, k1, k2, k0, i + 1);
-            step<1>(p, c, acc, r2, r0, r1, k2, k0, k1, i + 2);
+            for (int k = 0; k < NYD4; ++k) {
+                const Vec4 ta = sa[k * 32], tb = sb[k * 32];
+                ya[4 * k] = ta.x; ya[4 * k + 1] = ta.y; ya[4 * k + 2] = ta.z; ya[4 * k + 3] = ta.w;
+                yb[4 * k] = tb.x; yb[4 * k + 1] = tb.y; yb[4 * k + 2] = tb.z; yb[4 * k + 3] = tb.w;
+            }
+            acc.ey_prev = edge_y(c, g.Y0 - 1, ya + O_YM, ya[O_D], yb + O_YM, yb[O_D]);
         }
-        if (i < iend) {
-            step<2>(p, c, acc, r0, r1, r2, k0, k1, k2, i);
-            if (i + 1 < iend) step<0>(p, c, acc, r1, r2, r0, k1, k2, k0, i + 1);
+        release(c, gs + 1);
+        acquire(c, gs + 3);                                        // row Y0+1
+        gs += 2;                                                   // gs = slot of row r
+        for (int r = g.Y0; r < g.Y1; ++r) {
+            acquire(c, gs + 2);                                    // row r+2 (carries window row r+1)
+            stage_pixels(p, c, acc, r, slot_ptr(c, gs), slot_ptr(c, gs + 1), slot_ptr(c, gs + 2));
+            release(c, gs);
+            ++gs;
+            if (gs >= 2 * SLOT_WRAP) gs -= SLOT_WRAP;              // keep the counter small (slot and parity are periodic)
         }
-
-        if (BWD) {
-            // flush the carried lower tap pairs of the last row
+        release(c, gs);                                            // rows Y1, Y1+1
+        release(c, gs + 1);
+        gslot = (gs + 2) % SLOT_WRAP;
+        // flush the carried lower tap pairs of the last row
 #pragma unroll
-            for (int s = 0; s < S; ++s)
-                if (c.gb[s] && acc.coff[s] >= 0) {
-                    float* o = c.gb[s] + (acc.coff[s] + c.W);
+        for (int s = 0; s < S; ++s)
+            if (c.gb[s] && acc.coff[s] >= 0) {
+                float* o = c.gb[s] + (acc.coff[s] + g.W);
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        g_red(o + ch * c.HW, acc.car0[s][ch]);
-                        g_red1(o + ch * c.HW, acc.car1[s][ch]);
-                    }
+                for (int ch = 0; ch < C; ++ch) {
+                    g_red(o + ch * g.HW, acc.car0[s][ch]);
+                    g_red1(o + ch * g.HW, acc.car1[s][ch]);
                 }
-        }
+            }
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = 0.f;
-        v[0] = acc.warp_sum; v[1] = acc.ssx; v[2] = acc.ssy; v[3] = acc.dsum;
-        if (BWD) {
 #pragma unroll
-            for (int s = 0; s < S; ++s)
+        for (int s = 0; s < S; ++s)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {   // G = sum cbar (z p)^T, p = (px, py, 1); h = sum cbar
-                    v[NSTAT + 12 * s + 3 * k + 0] = (float)(c.gxm + 1) * acc.P0[s][k];
-                    v[NSTAT + 12 * s + 3 * k + 1] = acc.P1[s][k];
-                    v[NSTAT + 12 * s + 3 * k + 2] = acc.P0[s][k];
-                    v[NSTAT + 12 * s + 9 + k] = acc.Ph[s][k];
-                }
-        }
+            for (int k = 0; k < 3; ++k) {   // G = sum cbar (z p)^T, p = (px, py, 1); h = sum cbar
+                v[NSTAT + 12 * s + 3 * k + 0] = px * acc.P0[s][k];
+                v[NSTAT + 12 * s + 3 * k + 1] = acc.P1[s][k];
+                v[NSTAT + 12 * s + 3 * k + 2] = acc.P0[s][k];
+                v[NSTAT + 12 * s + 9 + k] = acc.Ph[s][k];
+            }
     }
 };
 

@@ -174,14 +174,34 @@ MD2_HD void hat3(const double* r, double* k) {
     k[6] = -r[1]; k[7] = r[0];  k[8] = 0;
 }
 
+// f1 = sin(th)/max(th,1e-4), f2 = (1-cos(th))/max(th,1e-4)^2 and sin, cos, th themselves from th^2.
+// For 1e-8 < th^2 < 1/4 (every realistic pose: the clamp is inactive there) the even power series
+// are used -- no sqrt / sin / cos calls, whose double-precision slow paths dominated the serial
+// pose blocks of the prep and finish kernels; otherwise the library functions.
+MD2_HD void so3_factors(double t2, double& th, double& s, double& c, double& f1, double& f2) {
+    if (t2 > 1e-8 && t2 < 0.25) {
+        f1 = 1.0 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880 + t2 * (-1.0 / 39916800 +
+             t2 * (1.0 / 6227020800.0 + t2 * (-1.0 / 1307674368000.0 + t2 * (1.0 / 355687428096000.0))))))));
+        f2 = 0.5 + t2 * (-1.0 / 24 + t2 * (1.0 / 720 + t2 * (-1.0 / 40320 + t2 * (1.0 / 3628800 + t2 * (-1.0 / 479001600 +
+             t2 * (1.0 / 87178291200.0 + t2 * (-1.0 / 20922789888000.0 + t2 * (1.0 / 6402373705728000.0))))))));
+        th = sqrt(t2);
+        s = th * f1;
+        c = 1.0 - t2 * f2;
+    } else {
+        th = sqrt(t2);
+        const double ti = 1.0 / fmax(th, 1e-4);
+        s = sin(th); c = cos(th);
+        f1 = ti * s; f2 = ti * ti * (1.0 - c);
+    }
+}
+
 // R = I + f1 K + f2 K^2, theta_inv = 1/max(theta, 1e-4)   (src/utils.jl:102-117)
 MD2_HD void so3_exp(const double* r, double* R) {
     double K[9], K2[9];
     hat3(r, K);
     mat3_mul(K, K, K2);
-    const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    const double ti = 1.0 / fmax(th, 1e-4);
-    const double f1 = ti * sin(th), f2 = ti * ti * (1.0 - cos(th));
+    double th, s, c, f1, f2;
+    so3_factors(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], th, s, c, f1, f2);
     for (int i = 0; i < 9; ++i) R[i] = f1 * K[i] + f2 * K2[i] + ((i % 4 == 0) ? 1.0 : 0.0);
 }
 
@@ -193,11 +213,10 @@ MD2_HD void so3_exp_bwd(const double* r, const double* Rb, double* rb) {
     hat3(r, K);
     mat3_mul(K, K, K2);
     mat3_t(K, Kt);
-    const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    double th, s, c, f1, f2;
+    so3_factors(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], th, s, c, f1, f2);
     const double tc = fmax(th, 1e-4);
     const double ti = 1.0 / tc;
-    const double s = sin(th), c = cos(th);
-    const double f1 = ti * s, f2 = ti * ti * (1.0 - c);
     mat3_mul(Rb, Kt, T1);
     mat3_mul(Kt, Rb, T2);
     double Kb[9], f1b = 0, f2b = 0;

@@ -18,7 +18,9 @@
 
 using namespace md2;
 
-// marching-warp kernel (md2_march.cuh): every work item runs as 32 lockstep fibers
+// marching-warp kernel (md2_march.cuh): a block of one (forward-only) or two (forward + backward
+// producer/consumer pair) warps of lockstep fibers walks all work items of one (scale, image), like
+// a persistent block of the CUDA kernel does
 template <int C, int S, bool BWD>
 static void run_march(const FusedParams& p, std::vector<float>& sums) {
     using M = March<C, S, BWD>;
@@ -28,20 +30,30 @@ static void run_march(const FusedParams& p, std::vector<float>& sums) {
     std::vector<float> wsm(M::SMEM_FLOATS + 4);
     float* wsm_al = (float*)(((uintptr_t)wsm.data() + 15) & ~(uintptr_t)15);
     WarpEmu emu;
-    std::vector<float> lane_v(32 * 32);
-    for (int z = 0; z < p.L * p.N; ++z)
-        for (int cy = 0; cy < chunks; ++cy)
-            for (int sx = 0; sx < strips; ++sx) {
-                for (int k = 0; k < M::SMEM_FLOATS; ++k) wsm_al[k] = NAN;
-                emu.run([&](int lane) {
+    std::vector<float> lane_v((size_t)M::THREADS * 32);
+    for (int z = 0; z < p.L * p.N; ++z) {
+        for (int k = 0; k < M::SMEM_FLOATS; ++k) wsm_al[k] = NAN;   // poison: catches reads of never-written slots
+        float* su = sums.data() + (size_t)z * NP;
+        emu.run(M::THREADS, [&](int tid) {
+            const int warp = tid >> 5, lane = tid & 31;
+            int gslot = 0;
+            if (tid == 0)
+                for (int b = 0; b < MARCH_NBAR; ++b) emu_mb_init(reinterpret_cast<mbar_t*>(wsm_al + M::RING_FLOATS), b);
+            if (BWD) emu_bar(0, 64, 1); else emu_ballot(0);
+            for (int cy = 0; cy < chunks; ++cy)
+                for (int sx = 0; sx < strips; ++sx) {
                     float v[32];
-                    M::run(p, sx, cy, z, lane, wsm_al, v);
-                    for (int k = 0; k < 32; ++k) lane_v[lane * 32 + k] = v[k];
-                });
-                float* su = sums.data() + (size_t)z * NP;
-                for (int lane = 0; lane < 32; ++lane)
-                    for (int k = 0; k < NP; ++k) su[k] += lane_v[lane * 32 + k];
-            }
+                    if (warp == 0) M::run_forward(p, sx, cy, z, lane, wsm_al, gslot, v);
+                    else M::run_backward(p, sx, cy, z, lane, wsm_al, gslot, v);
+                    for (int k = 0; k < 32; ++k) lane_v[(size_t)tid * 32 + k] = v[k];
+                    if (BWD) emu_bar(0, 64, 1); else emu_ballot(0);
+                    if (tid == 0)
+                        for (int t = 0; t < M::THREADS; ++t)
+                            for (int k = 0; k < NP; ++k) su[k] += lane_v[(size_t)t * 32 + k];
+                    if (BWD) emu_bar(0, 64, 1); else emu_ballot(0);
+                }
+        });
+    }
 }
 
 template <bool BWD>
