@@ -88,11 +88,11 @@ class ClockSampler(threading.Thread):
 
 
 def make_sets(n_sets, dev, seed0):
-    """ring of independent input + gradient-output sets, each built from the seeded synthetic
-    generator shared with the tests (oracle/torch_oracle.synthetic_batch is only used to MAKE
-    data here, never to compute)."""
-    from oracle import torch_oracle as O
-    base = O.synthetic_batch(NB, CH, H_, W_, seed=seed0)
+    """ring of independent input + gradient-output sets, each built from the package's seeded
+    synthetic generator (monodepth2_jl_b200.synthetic; the tests check that it produces exactly
+    the data of the oracle-side generator)."""
+    from monodepth2_jl_b200 import synthetic as SY
+    base = SY.synthetic_batch(NB, CH, H_, W_, seed=seed0)
     sets = []
     g = torch.Generator().manual_seed(seed0 + 1)
     for i in range(n_sets):
@@ -111,7 +111,7 @@ def make_sets(n_sets, dev, seed0):
 def run_ours(args):
     import monodepth2_jl_b200 as M
     from monodepth2_jl_b200 import _lib as L
-    from oracle import torch_oracle as O
+    from monodepth2_jl_b200 import synthetic as SY
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -125,7 +125,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     ctx = M.Context.get(dev)
-    K, invK = O.make_K(W_, H_)
+    K, invK = SY.make_K(W_, H_)
     K_cm, invK_cm = K.t().contiguous().to(dev), invK.t().contiguous().to(dev)
     sw = [1e-3 * s for s in SCALES]
 

@@ -81,3 +81,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".jl", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower().replace("# oracle", ""), f
+
+
+def test_package_synthetic_data_equals_test_side_generator():
+    """bench.py's CUDA arm builds its inputs with the package's generator, the CPU arm and the
+    parity tests with the oracle-side one: both must produce identical data."""
+    from monodepth2_jl_b200 import synthetic as SY
+    from oracle import torch_oracle as O
+    for kw in (dict(N=2, C=1, H=24, W=40, seed=42), dict(N=1, C=3, H=16, W=32, seed=7, full_res_disp=True, pose_sigma=0.1)):
+        a, b = SY.synthetic_batch(**kw), O.synthetic_batch(**kw)
+        assert torch.equal(a[0], b[0])
+        for k in (1, 2, 3):
+            assert all(torch.equal(u, v) for u, v in zip(a[k], b[k]))
+    for u, v in zip(SY.make_K(416, 128), O.make_K(416, 128)):
+        assert torch.equal(u, v)
