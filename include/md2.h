@@ -159,6 +159,7 @@ typedef struct md2_vsl_desc {
     float* viz_warped[MD2_MAX_SOURCES];     /* nullable (W,H,C,N): warped sources, last scale */
     float* viz_loss;                        /* nullable (W,H,1,N): warp-loss map, last scale */
     float* saved;                           /* nullable (4,N,L): fwd -> bwd statistics */
+    int32_t zero_grad_source;               /* != 0: the library zero-fills grad_source first (no caller memset) */
 } md2_vsl_desc;
 
 int md2_view_synthesis_loss_fwd(md2_ctx*, const md2_vsl_desc*, md2_stream);

@@ -121,129 +121,177 @@ __device__ __forceinline__ float warp_reduce_32(float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// prep kernel (one launch before the marching kernel), grid (warp groups + 1, N):
-//   blockIdx.x <  gridDim.x-1 : four warps, each marching down a 31-column strip chunk of image
-//       blockIdx.y (lane = column, lane 31 = right-hand halo): (a) writes the align-corners
-//       bilinear upsample (A17) of every low-res disparity into its full-resolution scratch and
-//       (b) for the fused fwd+bwd call accumulates the smoothness / mean-disparity statistics of
-//       every scale (needed before the backward because d / mean(d) couples all pixels of an
-//       image; the edge weights exp(-|dT|) are shared by the scales).
-//       Right neighbours come from the next lane, lower neighbours from the next row of the
-//       march, so every disparity is interpolated once.  The last warp of an image reduces the
-//       per-warp partials in a fixed order (deterministic).
-//   blockIdx.x == gridDim.x-1 : [composeT +] pose pre-composition of image blockIdx.y
+// prep kernel (one launch before the marching kernel), grid (1 + nblk + S * zero_blocks, N):
+//   blockIdx.x == 0 : [composeT +] pose pre-composition of image blockIdx.y (scheduled first, so
+//       the serial double-precision pose maths overlaps the rest of the grid)
+//   1 <= blockIdx.x <= nblk : eight warps, each owning a 31-column x 4-row patch of image
+//       blockIdx.y (lane = column, lane 31 = right-hand halo; one extra row below as lower
+//       neighbour), for all decoder scales.  Rows are unrolled and the loads of a scale are issued
+//       up front.  (a) writes the align-corners bilinear upsample (A17) of every low-res
+//       disparity into its full-resolution scratch -- separable: the (at most 4) low-res rows a
+//       patch touches are interpolated horizontally once per lane, the vertical weights are
+//       warp-uniform -- and (b) for the fused fwd+bwd call accumulates the smoothness /
+//       mean-disparity sums of every scale (needed before the backward because d / mean(d) couples
+//       all pixels of an image; the edge weights exp(-|dT|) are computed
+//       once and shared by the scales).  Right neighbours come from the next lane, lower
+//       neighbours from the next row, so every disparity is interpolated once.  One partial
+//       (Sx, Sy, sum d) per block and scale; the consumers (warp B of the marching kernel, the
+//       finish kernel) add the partials of a (scale, image) in a fixed order (deterministic).
+//   blockIdx.x > nblk : zero-fill of one slice of a grad_source image (desc.zero_grad_source)
 // ------------------------------------------------------------------------------------------
 constexpr int PREP_COLS = 31;
+constexpr int PREP_ROWS = 4;
+constexpr int PREP_WARPS = 8;
+
+__device__ __forceinline__ float sel4(const float (&h)[4], int k) {   // k is warp-uniform
+    return k == 0 ? h[0] : (k == 1 ? h[1] : (k == 2 ? h[2] : h[3]));
+}
 
 template <int C, int LMAX>
-__global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int R,
-                                                   int do_stats, float* __restrict__ pose_ab, float* __restrict__ part,
-                                                   float* __restrict__ stats, unsigned int* __restrict__ counters) {
+__global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_constant__ FusedParams p, int strips, int chunks,
+                                                               int nblk, int do_stats, float* __restrict__ pose_ab,
+                                                               float* __restrict__ part, int zero_blocks) {
     const int n = blockIdx.y;
-    if (blockIdx.x == gridDim.x - 1) {
+    if (blockIdx.x == 0) {
         if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
         return;
     }
-    const int lane = threadIdx.x & 31;
-    const int wpi = strips * chunks;                         // warps (work items) per image
-    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (w >= wpi) return;
     const int W = p.W, H = p.H, HW = W * H;
+    if ((int)blockIdx.x > nblk) {                            // zero-fill of one slice of a source-gradient image
+        const int zb = blockIdx.x - nblk - 1, s = zb / zero_blocks, sl = zb - s * zero_blocks;
+        if (!p.gsrc[s]) return;
+        float* g = p.gsrc[s] + (long long)n * p.src_ns[s];
+        const int total = C * HW;
+        const int per = ((total + zero_blocks - 1) / zero_blocks + 3) & ~3;
+        const int i0 = sl * per, i1 = min(i0 + per, total);
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            for (int i = i0 + 4 * (int)threadIdx.x; i + 3 < i1; i += 4 * (int)blockDim.x) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = i0 + ((i1 - i0) & ~3) + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
+        } else {
+            for (int i = i0 + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
+        }
+        return;
+    }
+    __shared__ float red[PREP_WARPS][3 * LMAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = (blockIdx.x - 1) * PREP_WARPS + warp;
+    const bool active = w < strips * chunks;
     const int cy = w / strips, sx = w - cy * strips;
     const int gx = sx * PREP_COLS + lane;
     const int gxc = gx < W ? gx : W - 1;
-    const bool own_col = lane < PREP_COLS && gx < W;
+    const bool own_col = active && lane < PREP_COLS && gx < W;
     const bool has_right = own_col && gx + 1 < W;
-    const int Y0 = cy * R, Y1 = min(Y0 + R, H);
-    const float* tg = p.tgt + (long long)n * p.tgt_ns + gxc;
-    // per-lane horizontal taps of every low-res scale
-    int xa0[LMAX], xa1[LMAX];
-    float fxu[LMAX], usy[LMAX];
-    bool native[LMAX];
+    const int Y0 = active ? cy * PREP_ROWS : 0;
+    int yo[PREP_ROWS + 1];                                   // clamped row offsets
+#pragma unroll
+    for (int r = 0; r <= PREP_ROWS; ++r) yo[r] = min(Y0 + r, H - 1) * W;
+
+    // ---- phase 1: every load of the patch (target rows, the disparity taps of all scales) ----
+    float t[PREP_ROWS + 1][C];
+    if (do_stats) {
+        const float* tg = p.tgt + (long long)n * p.tgt_ns + gxc;
+#pragma unroll
+        for (int r = 0; r <= PREP_ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) t[r][c] = __ldg(tg + c * HW + yo[r]);
+    }
+    // native scale: q[l][r] = disparity of row r; low-res scale: q[l][2k], q[l][2k+1] = the two horizontal
+    // taps of low-res row yb + k (k = 0..3: a 5-row patch touches at most 4 rows at scale <= 1/2)
+    float q[LMAX][8], fxu[LMAX];
+    int yb[LMAX];
+    bool native[LMAX], use[LMAX];
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
-        xa0[l] = xa1[l] = 0; fxu[l] = 0.f; usy[l] = 0.f; native[l] = true;
+        native[l] = true; use[l] = false; fxu[l] = 0.f; yb[l] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[l][k] = 0.f;
         if (l < p.L) {
-            native[l] = (p.dw[l] == W && p.dh[l] == H);
-            usy[l] = up_scale(p.dh[l], H);
-            if (!native[l]) up_taps(gxc, up_scale(p.dw[l], W), p.dw[l], xa0[l], xa1[l], fxu[l]);
+            const int dw = p.dw[l], dh = p.dh[l];
+            native[l] = (dw == W && dh == H);
+            use[l] = !native[l] || do_stats;
+            if (native[l]) {
+                if (do_stats) {
+                    const float* dp = p.disp[l] + (long long)n * HW + gxc;
+#pragma unroll
+                    for (int r = 0; r <= PREP_ROWS; ++r) q[l][r] = __ldg(dp + yo[r]);
+                }
+            } else {
+                int xa0, xa1, yb1; float fy0;
+                up_taps(gxc, p.usx[l], dw, xa0, xa1, fxu[l]);
+                up_taps(min(Y0, H - 1), p.usy[l], dh, yb[l], yb1, fy0);
+                const float* dp = p.disp[l] + (long long)n * dw * dh;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float* rw = dp + min(yb[l] + k, dh - 1) * dw;
+                    q[l][2 * k] = __ldg(rw + xa0); q[l][2 * k + 1] = __ldg(rw + xa1);
+                }
+            }
         }
     }
-    float v[3 * LMAX], dprev[LMAX], tprev[C];
+
+    // ---- phase 2: edge weights of the patch (shared by the scales): wx[r] between columns gx, gx+1 of
+    // row r, wy[r] between rows r-1 and r; the ownership masks are folded into the weights ----
+    float wx[PREP_ROWS], wy[PREP_ROWS + 1];
+    if (do_stats) {
 #pragma unroll
-    for (int k = 0; k < 3 * LMAX; ++k) v[k] = 0.f;
-#pragma unroll
-    for (int l = 0; l < LMAX; ++l) dprev[l] = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) tprev[c] = 0.f;
-    const int ylast = Y1 < H ? Y1 : H - 1;                   // one extra row below the chunk as lower neighbour
-    for (int y = Y0; y <= ylast; ++y) {
-        const bool own_row = y < Y1;
-        float t[C], wy = 0.f, wx = 0.f;
-        if (do_stats) {
-            float gyv = 0.f, gxv = 0.f;
+        for (int r = 0; r <= PREP_ROWS; ++r) {
+            float gxv = 0.f, gyv = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                t[c] = tg[(long long)c * HW + y * W];
-                gyv += fabsf(tprev[c] - t[c]);
-                gxv += fabsf(t[c] - __shfl_down_sync(0xffffffffu, t[c], 1));
-                tprev[c] = t[c];
+                if (r < PREP_ROWS) gxv += fabsf(t[r][c] - __shfl_down_sync(0xffffffffu, t[r][c], 1));
+                if (r > 0) gyv += fabsf(t[r - 1][c] - t[r][c]);
             }
-            wy = __expf(-gyv * (1.0f / C));                  // edge between rows y-1 and y
-            wx = __expf(-gxv * (1.0f / C));                  // edge between columns gx and gx+1
+            if (r < PREP_ROWS) wx[r] = (has_right && Y0 + r < H) ? __expf(-gxv * (1.0f / C)) : 0.f;
+            wy[r] = (r > 0 && own_col && Y0 + r < H) ? __expf(-gyv * (1.0f / C)) : 0.f;
         }
+    }
 #pragma unroll
-        for (int l = 0; l < LMAX; ++l) {
-            if (l >= p.L) break;
-            if (native[l] && !do_stats) continue;
-            float d;
-            if (native[l]) {
-                d = p.disp[l][(long long)n * HW + y * W + gxc];
-            } else {
-                const int dw = p.dw[l], dh = p.dh[l];
-                const float* dp = p.disp[l] + (long long)n * dw * dh;
+    for (int l = 0; l < LMAX; ++l) {
+        if (!use[l]) continue;
+        float d[PREP_ROWS + 1];
+        if (native[l]) {
+#pragma unroll
+            for (int r = 0; r <= PREP_ROWS; ++r) d[r] = q[l][r];
+        } else {
+            const int dh = p.dh[l];
+            const float usy = p.usy[l];
+            float h[4];                                      // low-res rows yb .. yb+3, interpolated horizontally
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = fmaf(fxu[l], q[l][2 * k + 1] - q[l][2 * k], q[l][2 * k]);
+            float* out = const_cast<float*>(p.dfull[l]) + (long long)n * HW + gx;
+#pragma unroll
+            for (int r = 0; r <= PREP_ROWS; ++r) {
                 int ya0, ya1; float fyu;
-                up_taps(y, usy[l], dh, ya0, ya1, fyu);
-                d = bilerp(dp[ya0 * dw + xa0[l]], dp[ya0 * dw + xa1[l]], dp[ya1 * dw + xa0[l]], dp[ya1 * dw + xa1[l]], fxu[l], fyu);
-                if (own_row && own_col) const_cast<float*>(p.dfull[l])[(long long)n * HW + y * W + gx] = d;
+                up_taps(min(Y0 + r, H - 1), usy, dh, ya0, ya1, fyu);
+                const float top = sel4(h, ya0 - yb[l]), bot = sel4(h, ya1 - yb[l]);
+                d[r] = fmaf(fyu, bot - top, top);
+                if (r < PREP_ROWS && Y0 + r < H && own_col) out[yo[r]] = d[r];
             }
-            if (do_stats) {
-                const float dr = __shfl_down_sync(0xffffffffu, d, 1);
-                if (own_col) {
-                    if (y > Y0) v[3 * l + 1] += fabsf(dprev[l] - d) * wy;          // row y-1 (owned) to row y
-                    if (own_row) {
-                        v[3 * l + 2] += d;
-                        if (has_right) v[3 * l + 0] += fabsf(d - dr) * wx;
-                    }
+        }
+        if (do_stats) {
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+            for (int r = 0; r <= PREP_ROWS; ++r) {
+                if (r < PREP_ROWS) {
+                    const float dr = __shfl_down_sync(0xffffffffu, d[r], 1);
+                    v0 = fmaf(fabsf(d[r] - dr), wx[r], v0);
+                    v2 += (own_col && Y0 + r < H) ? d[r] : 0.f;
                 }
-                dprev[l] = d;
+                if (r > 0) v1 = fmaf(fabsf(d[r - 1] - d[r]), wy[r], v1);   // rows r-1 (owned) and r
             }
+            v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+            if (lane == 0) { red[warp][3 * l] = v0; red[warp][3 * l + 1] = v1; red[warp][3 * l + 2] = v2; }
         }
     }
     if (!do_stats) return;
+    __syncthreads();
+    if ((int)threadIdx.x < 3 * p.L) {
+        float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 3 * LMAX; ++k) v[k] = warp_sum(v[k]);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 3 * LMAX; ++k) part[((long long)n * wpi + w) * (3 * LMAX) + k] = v[k];
+        for (int k = 0; k < PREP_WARPS; ++k) s += red[k][threadIdx.x];
+        const int l = threadIdx.x / 3, k = threadIdx.x - 3 * l;
+        part[(((long long)l * p.N + n) * nblk + (blockIdx.x - 1)) * 4 + k] = s;
     }
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = (atomicAdd(&counters[n], 1u) == (unsigned)(wpi - 1)) ? 1 : 0;
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence();
-    if (lane < 3 * p.L) {
-        float s0 = 0.f, s1 = 0.f;
-        const float* pp = part + (long long)n * wpi * (3 * LMAX) + lane;
-        int b = 0;
-        for (; b + 1 < wpi; b += 2) { s0 += __ldcg(pp + (long long)b * (3 * LMAX)); s1 += __ldcg(pp + (long long)(b + 1) * (3 * LMAX)); }
-        if (b < wpi) s0 += __ldcg(pp + (long long)b * (3 * LMAX));
-        const int l = lane / 3, k = lane % 3;
-        stats[((long long)l * p.N + n) * NSTAT + 1 + k] = s0 + s1;
-    }
-    if (lane == 0) counters[n] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -274,7 +322,7 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
     if (BWD) {
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int b = 0; b < MARCH_NBAR; ++b) mb_init(reinterpret_cast<mbar_t*>(wsm + M::RING_FLOATS), b, 32);
+            for (int b = 0; b < MARCH_NBAR; ++b) mb_init(bar_ref_of(wsm + M::RING_FLOATS), b, 32);
         }
         __syncthreads();
     }
@@ -299,14 +347,16 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
 // ------------------------------------------------------------------------------------------
 // finish kernel (one launch after the marching kernel); every block is independent, all sums
 // are taken in a fixed order (deterministic), nothing is atomic:
-//   block 0             per-(scale, image) loss sums from the per-item partials -> statistics,
-//                       saved statistics, loss scalar
+//   block 0             per-(scale, image) loss sums from the per-item partials (and, for the fused
+//                       fwd+bwd call, the smoothness sums from the prep kernel's partials) ->
+//                       statistics, saved statistics, loss scalar
 //   blocks 1 .. S*N     (backward) pose gradient of one (source, image): G | h summed over all
 //                       scales and items in double, then the K / composeT / so3 adjoints
 //   remaining blocks    (backward, low-res decoder scales) adjoint of the upsample, gather form,
-//                       separable: one block per low-res output row.  Phase A sums the
-//                       contributing full-resolution rows with their vertical weights into
-//                       shared memory (coalesced), phase B the contributing columns per pixel.
+//                       separable: one block per low-res output row (low_rows = sum of the low-res
+//                       heights, per image).  Phase A sums the contributing full-resolution rows
+//                       with their vertical weights into shared memory (128-bit coalesced loads),
+//                       phase B the contributing columns per low-res pixel.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -314,104 +364,162 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd,
-                                                     int n_low, int max_low_h) {
-    extern __shared__ float vrow[];   // [W] (adjoint blocks)
+constexpr int FIN_MAXROWS = 64;   // contributing full-resolution rows handled per pass of phase A
+constexpr int FIN_THREADS = 128;  // small blocks: the whole grid is resident at once (one latency chain, no waves)
+constexpr int FIN_PJ = FIN_THREADS / 12;
+
+__global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd, int low_rows) {
+    extern __shared__ __align__(16) float vrow[];   // [W rounded up to 4] (adjoint blocks)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int LN = p.L * p.N;
     int b = blockIdx.x;
     if (b == 0) {
-        if (p.mode != 1) {
-            for (int z = warp; z < LN; z += 8) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.mode == 1) return;
+        // eight lanes per (scale, image) group: strided partial sums (all loads in flight at once),
+        // then a fixed-order butterfly over the eight lanes
+        const int sub = threadIdx.x & 7;
+        for (int z0 = 0; z0 < LN; z0 += FIN_THREADS / 8) {
+            const int z = z0 + (threadIdx.x >> 3);
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (z < LN) {
                 const float* pp = p.partial + (long long)z * ipg * NP;
-                for (int it = lane; it < ipg; it += 32) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[k] += pp[(long long)it * NP + k];
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
-                if (lane == 0) {
-                    float* st = p.stats_out + (long long)z * NSTAT;
-                    st[0] = v[0];
-                    if (p.mode == 0) { st[1] = v[1]; st[2] = v[2]; st[3] = v[3]; }
-                    if (p.saved && p.saved != p.stats_out)
-                        for (int k = 0; k < NSTAT; ++k) p.saved[(long long)z * NSTAT + k] = st[k];
+                const int nv = p.mode == 0 ? 4 : 1;          // forward-only: warp F also carries the smoothness sums
+                for (int it = sub; it < ipg; it += 8)
+                    for (int k = 0; k < nv; ++k) v[k] += __ldcg(pp + (long long)it * NP + k);
+                if (p.mode == 2) {
+                    const float4* q = reinterpret_cast<const float4*>(p.prep_part) + (long long)z * p.prep_nblk;
+                    for (int it = sub; it < p.prep_nblk; it += 8) {
+                        const float4 t = __ldcg(q + it);
+                        v[1] += t.x; v[2] += t.y; v[3] += t.z;
+                    }
                 }
             }
-            __syncthreads();
-            if (threadIdx.x == 0 && p.loss)
-                *p.loss = loss_from_stats(p.stats_out, p.W, p.H, p.N, p.L, p.smooth_w, p.loss_scale, p.normalize_disp);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            if (z < LN && sub == 0) {
+                float* st = p.stats_out + (long long)z * NSTAT;
+#pragma unroll
+                for (int k = 0; k < NSTAT; ++k) st[k] = v[k];
+                if (p.saved && p.saved != p.stats_out)
+#pragma unroll
+                    for (int k = 0; k < NSTAT; ++k) p.saved[(long long)z * NSTAT + k] = v[k];
+            }
+        }
+        __syncthreads();
+        // loss = loss_scale * sum_i [ mean(warp_loss_i) + smooth_w_i * smooth_loss(dhat_i, target) ]
+        // (src/training.jl:64-69,77; same terms as loss_from_stats): one lane per (scale, image), double
+        if (warp == 0 && p.loss) {
+            const double P = (double)p.W * p.H;
+            const double cx = 1.0 / ((double)(p.W - 1) * p.H * p.N), cy = 1.0 / ((double)p.W * (p.H - 1) * p.N);
+            const double rPN = 1.0 / (P * p.N);
+            double acc = 0.0;
+            for (int z = lane; z < LN; z += 32) {
+                const float* st = p.stats_out + (long long)z * NSTAT;
+                const double m = p.normalize_disp ? ((double)st[3] / P + 1e-7) : 1.0;
+                acc += (double)st[0] * rPN + (double)p.smooth_w[z / p.N] * (cx * st[1] + cy * st[2]) / m;
+            }
+            acc = warp_sum_d(acc);
+            if (lane == 0) *p.loss = (float)(acc * p.loss_scale);
         }
         return;
     }
     b -= 1;
     if (!bwd) return;
     if (b < p.S * p.N) {
-        if (warp != 0) return;
+        // pose gradient of (source s, image nn): 12 sums over all scales and items; thread (j, k) adds
+        // every FIN_PJ-th row of column k in double, then 12 threads add the partials in order
+        __shared__ double pacc[FIN_PJ][12];
         const int s = b / p.N, nn = b % p.N;
-        double acc[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-        for (int l = 0; l < p.L; ++l) {
-            const float* pp = p.partial + ((long long)l * p.N + nn) * ipg * NP + NSTAT + 12 * s;
-            for (int it = lane; it < ipg; it += 32) {
-#pragma unroll
-                for (int k = 0; k < 12; ++k) acc[k] += (double)pp[(long long)it * NP + k];
+        const int k = threadIdx.x % 12, j = threadIdx.x / 12;
+        if (j < FIN_PJ) {
+            double a = 0.0;
+            const int rows = p.L * ipg;
+            for (int r = j; r < rows; r += FIN_PJ) {
+                const int l = r / ipg, it = r - l * ipg;
+                a += (double)__ldcg(p.partial + (((long long)l * p.N + nn) * ipg + it) * NP + NSTAT + 12 * s + k);
             }
+            pacc[j][k] = a;
         }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) acc[k] = warp_sum_d(acc[k]);
-        if (lane == 0) finalize_pose(p.pose, s, nn, acc, acc + 9);
+            for (int q = 0; q < FIN_PJ; ++q) a += pacc[q][threadIdx.x];
+            pacc[0][threadIdx.x] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) finalize_pose(p.pose, s, nn, &pacc[0][0], &pacc[0][0] + 9);
         return;
     }
     b -= p.S * p.N;
-    if (b >= n_low * max_low_h * p.N) return;
-    const int yi = b % max_low_h, li = (b / max_low_h) % n_low, n = b / (max_low_h * n_low);
-    int l = -1;
-    for (int k = 0, seen = -1; k < p.L; ++k)
-        if (p.dw[k] != p.W || p.dh[k] != p.H) { if (++seen == li) { l = k; break; } }
-    if (l < 0) return;
+    // (image, low-res scale, low-res row) of this block: block-uniform scalar code
+    const int n = b / low_rows;
+    int yi = b - n * low_rows, l = -1;
+    for (int k = 0; k < p.L; ++k) {
+        if (p.dw[k] == p.W && p.dh[k] == p.H) continue;
+        if (yi < p.dh[k]) { l = k; break; }
+        yi -= p.dh[k];
+    }
+    if (l < 0 || n >= p.N) return;
     const int w = p.dw[l], h = p.dh[l];
-    if (yi >= h) return;
     const int W = p.W, H = p.H;
-    const float sx = up_scale(w, W), sy = up_scale(h, H);
+    const float sx = p.usx[l], sy = p.usy[l];
     const float* g = p.gfull[l] + (long long)n * W * H;
     int ylo = 0, yhi = H - 1;
     if (sy > 0.f) {
         ylo = max(0, (int)floorf((float)(yi - 1) / sy) - 1);
         yhi = min(H - 1, (int)ceilf((float)(yi + 1) / sy) + 1);
     }
-    __shared__ float wys[64];
-    const int ny = yhi - ylo + 1;   // <= 2/sy + 5
-    for (int base = 0; base < ny; base += 64) {
+    __shared__ float wys[FIN_MAXROWS];
+    // trim the conservative row range to the rows that really contribute (weight != 0)
+    {
+        int y0, y1; float fy;
+        while (ylo < yhi) { up_taps(ylo, sy, h, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; ++ylo; }
+        while (yhi > ylo) { up_taps(yhi, sy, h, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; --yhi; }
+    }
+    const int ny = yhi - ylo + 1;
+    const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+    for (int base = 0; base < ny; base += FIN_MAXROWS) {
         __syncthreads();
-        if ((int)threadIdx.x < 64 && base + (int)threadIdx.x < ny) {
+        if ((int)threadIdx.x < FIN_MAXROWS && base + (int)threadIdx.x < ny) {
             int y0, y1; float fy;
             up_taps(ylo + base + threadIdx.x, sy, h, y0, y1, fy);
             wys[threadIdx.x] = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
         }
         __syncthreads();
-        const int cnt = min(64, ny - base);
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            float acc = base ? vrow[x] : 0.f;
-            const float* gp = g + (long long)(ylo + base) * W + x;
-            int k = 0;
-            for (; k + 4 <= cnt; k += 4) {
-                const float g0 = gp[(long long)k * W], g1 = gp[(long long)(k + 1) * W], g2 = gp[(long long)(k + 2) * W], g3 = gp[(long long)(k + 3) * W];
-                acc = fmaf(wys[k], g0, acc); acc = fmaf(wys[k + 1], g1, acc);
-                acc = fmaf(wys[k + 2], g2, acc); acc = fmaf(wys[k + 3], g3, acc);
+        const int cnt = min(FIN_MAXROWS, ny - base);
+        if (vec) {
+            for (int x = 4 * threadIdx.x; x < W; x += 4 * FIN_THREADS) {
+                float4 acc = base ? *reinterpret_cast<const float4*>(vrow + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* gp = g + (long long)(ylo + base) * W + x;
+#pragma unroll 8
+                for (int k = 0; k < cnt; ++k) {
+                    const float4 q = __ldcg(reinterpret_cast<const float4*>(gp + (long long)k * W));
+                    const float wk = wys[k];
+                    acc.x = fmaf(wk, q.x, acc.x); acc.y = fmaf(wk, q.y, acc.y);
+                    acc.z = fmaf(wk, q.z, acc.z); acc.w = fmaf(wk, q.w, acc.w);
+                }
+                *reinterpret_cast<float4*>(vrow + x) = acc;
             }
-            for (; k < cnt; ++k) acc = fmaf(wys[k], gp[(long long)k * W], acc);
-            vrow[x] = acc;
+        } else {
+            for (int x = threadIdx.x; x < W; x += FIN_THREADS) {
+                float acc = base ? vrow[x] : 0.f;
+                const float* gp = g + (long long)(ylo + base) * W + x;
+#pragma unroll 8
+                for (int k = 0; k < cnt; ++k) acc = fmaf(wys[k], __ldcg(gp + (long long)k * W), acc);
+                vrow[x] = acc;
+            }
         }
     }
     __syncthreads();
-    for (int xi = threadIdx.x; xi < w; xi += blockDim.x) {
+    const float rsx = sx > 0.f ? 1.0f / sx : 0.f;
+    for (int xi = threadIdx.x; xi < w; xi += FIN_THREADS) {
         int xlo = 0, xhi = W - 1;
         if (sx > 0.f) {
-            xlo = max(0, (int)floorf((float)(xi - 1) / sx) - 1);
-            xhi = min(W - 1, (int)ceilf((float)(xi + 1) / sx) + 1);
+            xlo = max(0, (int)floorf((float)(xi - 1) * rsx) - 1);
+            xhi = min(W - 1, (int)ceilf((float)(xi + 1) * rsx) + 1);
         }
         float acc = 0.f;
         for (int x = xlo; x <= xhi; ++x) {
@@ -436,6 +544,7 @@ static int march_resident() {
         const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
         int occ = 0;
         if (cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
+        cudaFuncSetAttribute(march_kernel<C, S, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_kernel<C, S, BWD>, M::THREADS, smem) != cudaSuccess) occ = 0;
         resident = occ > 0 ? occ : 8;
         if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] march_kernel<%d,%d,%d>: %d resident blocks/SM, %zu B smem/block\n", C, S, (int)BWD, resident, smem);
@@ -538,14 +647,6 @@ static void fill_pose_io(const md2_vsl_desc* d, PoseIO& io) {
     }
 }
 
-static unsigned int* get_counters(md2_ctx* ctx, int count, cudaStream_t st) {
-    Workspace& w = ctx->ws[MD2_WS_POSEIN];
-    const bool fresh = !(w.ptr && w.bytes >= sizeof(unsigned int) * count);
-    unsigned int* c = (unsigned int*)ws_get(ctx, MD2_WS_POSEIN, sizeof(unsigned int) * count);
-    if (c && fresh) cudaMemsetAsync(c, 0, ctx->ws[MD2_WS_POSEIN].bytes, st);   // kernels leave them zero
-    return c;
-}
-
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FWDBWD = 2 };
 
 static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStream_t st) {
@@ -569,15 +670,16 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
         const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
         p.depth_a = maxd - mind; p.depth_b = mind;
     }
-    int n_low = 0, max_low_h = 0;
+    int n_low = 0, low_rows = 0;
     for (int l = 0; l < L; ++l) {
         p.smooth_w[l] = d->smooth_weight[l];
         p.disp[l] = d->disparity[l]; p.dw[l] = d->disp_w[l]; p.dh[l] = d->disp_h[l];
+        p.usx[l] = up_scale(d->disp_w[l], W); p.usy[l] = up_scale(d->disp_h[l], H);
         p.gdisp[l] = bwd ? d->grad_disparity[l] : nullptr;
         if (bwd) MD2_REQUIRE(d->grad_disparity[l] != nullptr, "null grad_disparity");
         if (d->disp_w[l] != W || d->disp_h[l] != H) {
             ++n_low;
-            max_low_h = max(max_low_h, d->disp_h[l]);
+            low_rows += d->disp_h[l];
         }
     }
     {   // full-resolution views of every scale: the caller's buffers for native-size scales, L2-resident
@@ -607,31 +709,30 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     const int pose_floats = 12 * S * N;
     MD2_REQUIRE(pose_floats <= POSE_CONST_FLOATS, "S*N too large for one call (max 1024 source-image pairs)");
     p.pose_slot = pose_floats <= POSE_SLOT_FLOATS ? ctx->pose_slot * POSE_SLOT_FLOATS : 0;
-    const int LMAX = L == 1 ? 1 : (L <= 4 ? 4 : 8);
-    // prep kernel partition: 31-column strips x chunks of rows, one warp each
-    const int prep_strips = cdiv(W, PREP_COLS);
-    int prep_R = 4;   // short chains: every row of the march waits for one memory round trip
-    while (prep_R < H && (long long)prep_strips * cdiv(H, prep_R) * N > 8LL * ctx->sm_count * 4) prep_R *= 2;
-    const int prep_chunks = cdiv(H, prep_R);
-    const int prep_wpi = prep_strips * prep_chunks;
+    // prep kernel partition: 31-column x 4-row patches, one warp each, eight warps per block
+    const int prep_strips = cdiv(W, PREP_COLS), prep_chunks = cdiv(H, PREP_ROWS);
+    const int prep_nblk = cdiv((long long)prep_strips * prep_chunks, PREP_WARPS);
+    const int do_stats = mode == MODE_FWDBWD;
+    const bool zero_gs = bwd && d->zero_grad_source != 0;
+    const int zero_blocks = zero_gs ? max(1, min(64, cdiv((long long)C * W * H, 8192))) : 0;
     float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
-    float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)prep_wpi * N * 3 * LMAX);
-    unsigned int* counters = get_counters(ctx, N, st);   // prep kernel: last warp of an image
-    if (!pose_ab || !partial || !stats || !part2 || !counters) return 1;
+    float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)prep_nblk * L * N * 4);
+    if (!pose_ab || !partial || !stats || !part2) return 1;
     p.pose_ab = pose_ab; p.partial = partial; p.sums = nullptr; p.counters = nullptr;
     p.stats = stats; p.stats_out = stats; p.saved = (mode == MODE_BWD) ? nullptr : d->saved;
     if (mode == MODE_BWD && d->saved) p.stats = d->saved;   // else the ctx holds the last forward's statistics
     p.loss = (mode == MODE_BWD) ? nullptr : d->loss;
+    p.prep_part = do_stats ? part2 : nullptr;
+    p.prep_nblk = prep_nblk;
 
-    {   // prep: poses, upsampled low-res disparities (+ statistics pre-pass for the fused fwd+bwd)
-        const int do_stats = mode == MODE_FWDBWD;
-        dim3 g((do_stats || n_low) ? cdiv(prep_wpi, 4) + 1 : 1, N);
-        unsigned int* pc = counters;
-#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 128, 0, st>>>(p, prep_strips, prep_chunks, prep_R, do_stats, pose_ab, part2, stats, pc)
-        if (C == 1) { if (LMAX == 1) MD2_PREP(1, 1); else if (LMAX == 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
-        else        { if (LMAX == 1) MD2_PREP(3, 1); else if (LMAX == 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
+    {   // prep: poses, upsampled low-res disparities (+ smoothness sums for the fused fwd+bwd, + zero-fill)
+        const int nb = (do_stats || n_low) ? prep_nblk : 0;
+        dim3 g(1 + nb + S * zero_blocks, N);
+#define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 32 * PREP_WARPS, 0, st>>>(p, prep_strips, prep_chunks, nb, do_stats, pose_ab, part2, zero_blocks)
+        if (C == 1) { if (L == 1) MD2_PREP(1, 1); else if (L <= 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
+        else        { if (L == 1) MD2_PREP(3, 1); else if (L <= 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
 #undef MD2_PREP
         MD2_LAUNCH_CHECK(ctx);
     }
@@ -655,8 +756,8 @@ static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, c
     else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
     {   // loss / statistics, pose gradients, adjoint of the upsample for the low-res decoder scales
-        const int blocks = 1 + (bwd ? S * N + n_low * max_low_h * N : 0);
-        finish_kernel<<<blocks, 256, sizeof(float) * W, st>>>(p, NP, tiles, bwd ? 1 : 0, n_low, max_low_h);
+        const int blocks = 1 + (bwd ? S * N + low_rows * N : 0);
+        finish_kernel<<<blocks, FIN_THREADS, sizeof(float) * ((W + 3) & ~3), st>>>(p, NP, tiles, bwd ? 1 : 0, low_rows);
         MD2_LAUNCH_CHECK(ctx);
     }
     return 0;

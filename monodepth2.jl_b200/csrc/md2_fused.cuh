@@ -55,6 +55,11 @@ struct FusedParams {
     int m_R, pose_slot;
     const float* dfull[MAX_L];
     float* gfull[MAX_L];
+    // fused fwd+bwd call: per-block partial sums (Sx, Sy, sum d, -) of the prep kernel, (L, N, prep_nblk, 4);
+    // null when the backward takes the statistics of an earlier forward from `stats`
+    const float* prep_part;
+    int prep_nblk;
+    float usx[MAX_L], usy[MAX_L];       // up_scale(dw, W), up_scale(dh, H) of every scale (host-computed: no device divisions)
 };
 
 #if defined(__CUDA_ARCH__)

@@ -4,15 +4,18 @@
 // of one (scale, image), a chunk of rows tall; lane = image column, the warps march down the rows
 // with all rolling state in registers.  The backward runs as a two-warp producer / consumer pair:
 //
-//   warp F (forward)   per row i:
-//     L(i)    disparity -> depth -> backproject/pose/project -> 4-tap border gather of the S source
-//             frames; horizontal 3-sums for the SSIM windows come from the neighbouring lanes by
-//             warp shuffle
+//   warp F (forward)   per row i, software-pipelined over rows so that no load is consumed in the
+//   iteration that issues it:
+//     C(i)    consume the 4-tap border gathers of row i (issued one iteration earlier): bilinear value +
+//             slopes of the S warped sources; horizontal 3-sums for the SSIM windows come from the
+//             neighbouring lanes by warp shuffle
+//     A(i+1)  disparity / target of row i+1 (loaded one iteration earlier) -> depth -> backproject / pose /
+//             project -> issue the gathers of row i+1 and the disparity / target loads of row i+2
 //     W(i-1)  vertical rolling 3-sums -> SSIM + L1 photometric error, arg-min over sources,
 //             automask, loss partial sums; the per-window SSIM gradient coefficients and their
 //             horizontal adjoint 3-sums (shuffles)
-//     -> writes one slot of a shared-memory ring: the pixel packet of row i (sampler taps, slopes,
-//        projection factors, own values) and the window packet of row i-1
+//     -> fills one slot of a shared-memory ring per row: the pixel packet of row i (early part: geometry,
+//        written by A(i); late part: own values and slopes, written by C(i)) and the window packet of row i-1
 //   warp B (backward)  per pixel row r, once slot r+2 is full:
 //     P(r)    vertical adjoint sums -> d loss / d warped, sampler / projection / depth adjoints,
 //             pose accumulators, source-image scatter (lower tap pair carried to the next row,
@@ -50,8 +53,14 @@ inline int w_up(int v, int lane) { return w_shfl(v, lane > 0 ? lane - 1 : 0, lan
 inline int w_dn(int v, int lane) { return w_shfl(v, lane < 31 ? lane + 1 : 31, lane); }
 inline bool w_any(bool p) { return emu_ballot(p ? 1 : 0) != 0u; }
 typedef unsigned long long mbar_t;
-inline void mb_arrive(mbar_t* bars, int idx) { emu_mb_arrive(bars, idx); }
-inline void mb_wait(mbar_t* bars, int idx, int parity) { emu_mb_wait(bars, idx, parity); }
+typedef mbar_t* bar_ref;          // the mbarrier array
+typedef float* ring_ref;          // the ring of packets
+inline bar_ref bar_ref_of(float* q) { return reinterpret_cast<mbar_t*>(q); }
+inline ring_ref ring_ref_of(float* q, int lane) { return q + 4 * lane; }   // + this lane's Vec4 column
+inline void mb_arrive(bar_ref bars, int idx) { emu_mb_arrive(bars, idx); }
+inline void mb_wait(bar_ref bars, int idx, int parity) { emu_mb_wait(bars, idx, parity); }
+inline void s_st4(ring_ref r, int vec_index, const Vec4& v) { reinterpret_cast<Vec4*>(r)[vec_index] = v; }
+inline Vec4 s_ld4(ring_ref r, int vec_index) { return reinterpret_cast<const Vec4*>(r)[vec_index]; }
 inline float f_sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 inline float f_rcp(float x) { return 1.0f / x; }
 inline float f_ex2(float x) { return exp2f(x); }
@@ -84,23 +93,39 @@ MD2_DEV bool w_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 // Named bar.sync/bar.arrive barriers would also do, but 2 x depth of them per block cap the
 // resident blocks per SM at 4 (16 hardware barriers per block are reserved).
 typedef unsigned long long mbar_t;
+// shared-memory objects are addressed by their 32-bit shared-window offsets (no generic-address round trips)
+typedef unsigned int bar_ref;
+typedef unsigned int ring_ref;
 MD2_DEV unsigned int smem_u32(const void* q) { return (unsigned int)__cvta_generic_to_shared(q); }
-MD2_DEV void mb_init(mbar_t* bars, int idx, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + idx)), "r"(count) : "memory");
+MD2_DEV bar_ref bar_ref_of(float* q) { return smem_u32(q); }
+MD2_DEV ring_ref ring_ref_of(float* q, int lane) { return smem_u32(q) + 16u * lane; }   // + this lane's Vec4 column
+MD2_DEV void mb_init(bar_ref bars, int idx, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * idx), "r"(count) : "memory");
 }
-MD2_DEV void mb_arrive(mbar_t* bars, int idx) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bars + idx)) : "memory");
+MD2_DEV void mb_arrive(bar_ref bars, int idx) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * idx) : "memory");
 }
-MD2_DEV void mb_wait(mbar_t* bars, int idx, int parity) {   // returns once the phase of that parity has completed
+#ifndef MD2_WAIT_HINT_NS
+#define MD2_WAIT_HINT_NS 20000
+#endif
+MD2_DEV void mb_wait(bar_ref bars, int idx, int parity) {   // returns once the phase of that parity has completed
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "MB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // suspends in hardware up to the time hint
         "@p bra MB_DONE_%=;\n"
         "bra MB_WAIT_%=;\n"
         "MB_DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bars + idx)), "r"(parity) : "memory");
+        "}\n" ::"r"(bars + 8u * idx), "r"(parity), "r"(MD2_WAIT_HINT_NS) : "memory");
+}
+MD2_DEV void s_st4(ring_ref r, int vec_index, const Vec4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(r + 16u * vec_index), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+MD2_DEV Vec4 s_ld4(ring_ref r, int vec_index) {
+    Vec4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(r + 16u * vec_index) : "memory");
+    return v;
 }
 MD2_DEV float f_sat(float x) { return __saturatef(x); }
 MD2_DEV float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -111,6 +136,7 @@ MD2_DEV float i_as_float(int i) { return __int_as_float(i); }
 // re-deriving it from kernel parameters / special registers in every row
 MD2_DEV void keep(float& v) { asm volatile("" : "+f"(v)); }
 MD2_DEV void keep(int& v) { asm volatile("" : "+r"(v)); }
+MD2_DEV void keep(unsigned int& v) { asm volatile("" : "+r"(v)); }
 template <class T> MD2_DEV void keep(T*& v) { asm volatile("" : "+l"(v)); }
 // global-memory accesses with an explicit state space (pointers pinned by keep() have lost their
 // provenance, so plain dereferences would become generic LD / ATOM with address-space checks)
@@ -138,11 +164,46 @@ MD2_DEV float sgn_scaled(float d, float c) {
     return d != 0.0f ? i_as_float(f_as_int(c) ^ (f_as_int(d) & (int)0x80000000)) : 0.0f;
 }
 
-constexpr int MARCH_DEPTH = 4;       // ring slots between warp F and warp B (B holds 3, F fills the 4th)
+// smoothness / mean-disparity sums (Sx, Sy, sum d) of one (scale, image), needed by the backward
+// (src/training.jl:64-65 couples all pixels of an image): the saved statistics of an earlier forward,
+// or -- fused fwd+bwd call -- the prep kernel's per-block partials added in a fixed order
+// (lane-strided, then a butterfly: deterministic).  Called by all 32 lanes.
+MD2_DEV void prep_stats(const FusedParams& p, int scale, int n, int lane, float& ssx, float& ssy, float& dsum) {
+    if (!p.prep_part) {
+        const float* st = p.stats + ((long long)scale * p.N + n) * NSTAT;
+        ssx = st[1]; ssy = st[2]; dsum = st[3];
+        return;
+    }
+    const Vec4* pp = reinterpret_cast<const Vec4*>(p.prep_part) + ((long long)scale * p.N + n) * p.prep_nblk;
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int k = lane; k < p.prep_nblk; k += 32) {
+        const Vec4 q = pp[k];
+        a += q.x; b += q.y; c += q.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += w_shfl(a, lane ^ o, lane); b += w_shfl(b, lane ^ o, lane); c += w_shfl(c, lane ^ o, lane);
+    }
+    ssx = a; ssy = b; dsum = c;
+}
+
+constexpr int MARCH_DEPTH = 5;       // ring slots between warp F and warp B (B holds 3, F fills the 4th and pre-fills the 5th)
 constexpr int BAR_FULL = 0;          // mbarrier indices: full[s] = BAR_FULL + s, empty[s] = BAR_EMPTY + s
 constexpr int BAR_EMPTY = MARCH_DEPTH;
 constexpr int MARCH_NBAR = 2 * MARCH_DEPTH;
-constexpr int SLOT_WRAP = 4 * MARCH_DEPTH;   // the running slot counters live in [0, SLOT_WRAP)
+constexpr int SLOT_WRAP = 2 * MARCH_DEPTH;   // a running slot counter = slot index + MARCH_DEPTH * (fill parity)
+
+// position in the ring: slot index and the parity of the number of times the ring has wrapped
+struct Slot { int idx, par; };
+MD2_DEV Slot slot_of(int counter) { Slot t; t.par = counter >= MARCH_DEPTH ? 1 : 0; t.idx = counter - t.par * MARCH_DEPTH; return t; }
+MD2_DEV int counter_of(Slot t) { return t.idx + t.par * MARCH_DEPTH; }
+MD2_DEV Slot next_slot(Slot t) {
+    Slot n;
+    const bool wrap = t.idx + 1 == MARCH_DEPTH;
+    n.idx = wrap ? 0 : t.idx + 1;
+    n.par = wrap ? t.par ^ 1 : t.par;
+    return n;
+}
 
 template <int C, int S, bool BWD>
 struct March {
@@ -150,12 +211,18 @@ struct March {
     static constexpr int OW = 32 - 2 * HALO;             // output columns per strip
     static constexpr int NPART = NSTAT + 12 * S;
     // ---- ring slot layout (floats per lane) ----
-    // pixel packet of row i: own target values ym[C], disparity D, own warped values xm[S][C], depth z,
-    // then per source: A = mx q, B = my q, u, v, fx, fy, gather offset, C slopes d/dix, C slopes d/diy
-    static constexpr int O_YM = 0, O_D = C, O_XM = C + 1, O_Z = C + 1 + S * C, O_SRC = O_Z + 1;
-    static constexpr int SRCF = 7 + 2 * C;
-    static constexpr int NPPF = O_SRC + S * SRCF;
-    static constexpr int NPP4 = (NPPF + 3) / 4;
+    // pixel packet of row i, early part (known once the geometry of the row is): own target values ym[C],
+    // disparity D, depth z, then per source: A = mx q, B = my q, u, v, fx, fy, gather offset
+    static constexpr int O_YM = 0, O_D = C, O_Z = C + 1, O_SRC = C + 2;
+    static constexpr int SRCF = 7;
+    static constexpr int NEF = O_SRC + S * SRCF;
+    static constexpr int NE4 = (NEF + 3) / 4;
+    // late part (known once the gathers have returned): own warped values xm[S][C], then per source
+    // C slopes d/dix, C slopes d/diy
+    static constexpr int O_XM = NE4 * 4, O_SL = O_XM + S * C;
+    static constexpr int NLF = 3 * S * C;
+    static constexpr int NL4 = (NLF + 3) / 4;
+    static constexpr int NPP4 = NE4 + NL4;
     static constexpr int NYD4 = (C + 1 + 3) / 4;         // Vec4s holding ym[C], D
     // window packet of row i-1: t[3C], s0[3C], selected source
     static constexpr int NWPF = 6 * C + 1;
@@ -200,7 +267,7 @@ struct March {
         bool do_viz;
         const float* tg;             // target image + this lane's column
         const float* sb[S];
-        const float* dp;             // full-resolution disparity of this (scale, image)
+        const float* dp;             // full-resolution disparity of this (scale, image) + this lane's column
         const float* am;             // automask of this image or null
         float rc[C];
         float apx[S][3];
@@ -208,31 +275,46 @@ struct March {
         float Wf, Hf;
         float kq;                    // wcol ? up_photo * alpha/C * (-1/2) : 0
         float wl, wr;                // horizontal reflect-pad adjoint weights of this pixel column
-        Vec4* ring;
-        mbar_t* bars;
-        int gslot;                   // running slot counter (continues across work items)
+        ring_ref ring;               // + this lane's Vec4 column
+        bar_ref bars;
+        Slot fill;                   // slot of the row being consumed (C / W stages); A pre-fills the next one
     };
     struct AccF { float warp_sum, ssx, ssy, dsum; };
+    // rows in flight between the stages of warp F
+    struct PipeF {
+        float G[S][C][4];            // the four taps of row i per source and channel (loads issued by A(i))
+        float fx[S], fy[S];          // their bilinear fractions
+        float Tc[C], d;              // centred target values / disparity of row i
+        float Tn[C], dn;             // raw target values / disparity of row i+1 (loads issued by A(i))
+    };
 
-    // ---- L(i) ----
-    static MD2_DEV void stage_load(const FusedParams& p, const CtxF& c, Row& cur, int i, float (&pk)[NPP4 * 4]) {
+    // image row read for march row i (reflect-pad(1) above and below the image, clamped beyond)
+    static MD2_DEV int image_row(int i, int H) {
+        int gym = i == -1 ? 1 : (i == H ? H - 2 : i);
+        gym = gym < 0 ? 0 : (gym > H - 1 ? H - 1 : gym);
+        return gym;
+    }
+
+    static MD2_DEV int slot_vec(Slot t) { return t.idx * (SLOT4 * 32); }   // Vec4 index of a slot's first packet
+
+    // ---- A(i): geometry of row i from the disparity / target loaded one row ago; issues the gathers of
+    // row i and the disparity / target loads of row i+1; BWD: pre-fills the early part of slot `t` ----
+    static MD2_DEV void stage_issue(const FusedParams& p, const CtxF& c, PipeF& f, int i, Slot t) {
         const Geo& g = c.g;
-        const int lane = g.lane;
-        int gym = i == -1 ? 1 : (i == g.H ? g.H - 2 : i);
-        gym = gym < 0 ? 0 : (gym > g.H - 1 ? g.H - 1 : gym);
+        const int gym = image_row(i, g.H);
         const float py = (float)(gym + 1);
-        const int toff = gym * g.W;
-        const float d = g_ld(c.dp + (toff + g.gxm));
-        if (gym + 1 < g.H) {   // next row's disparity / target lines
-            g_pf(c.dp + (toff + g.W + g.gxm));
+        const float d = f.dn;
+        f.d = d;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) g_pf(c.tg + (ch * g.HW + toff + g.W));
+        for (int ch = 0; ch < C; ++ch) f.Tc[ch] = f.Tn[ch] - c.rc[ch];
+        {   // next row
+            const int toff = image_row(i + 1, g.H) * g.W;
+            f.dn = g_ld(c.dp + toff);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) f.Tn[ch] = g_ld(c.tg + (ch * g.HW + toff));
         }
-        cur.D = d;
         const float zv = rcp_acc(fmaf(d, p.depth_a, p.depth_b));
-        float Tc[C], Xc[S][C];
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) Tc[ch] = g_ld(c.tg + (ch * g.HW + toff)) - c.rc[ch];
+        float ek[NE4 * 4];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const float ap0 = fmaf(MD2_POSE(p, c.pb[s] + 1), py, c.apx[s][0]);
@@ -259,48 +341,84 @@ struct March {
             }
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-                const float v00 = g_ld(r0 + ch * g.HW), v01 = g_ld1(r0 + ch * g.HW), v10 = g_ld(r1 + ch * g.HW), v11 = g_ld1(r1 + ch * g.HW);
+                f.G[s][ch][0] = g_ld(r0 + ch * g.HW); f.G[s][ch][1] = g_ld1(r0 + ch * g.HW);
+                f.G[s][ch][2] = g_ld(r1 + ch * g.HW); f.G[s][ch][3] = g_ld1(r1 + ch * g.HW);
+            }
+            f.fx[s] = fx; f.fy[s] = fy;
+            if (BWD) {
+                // clip-gradient masks (0 where the un-clipped coordinate is <= 1 or >= size), folded into q
+                ek[O_SRC + s * SRCF + 0] = (u > 1.0f && u < c.Wf) ? q : 0.0f;
+                ek[O_SRC + s * SRCF + 1] = (vv > 1.0f && vv < c.Hf) ? q : 0.0f;
+                ek[O_SRC + s * SRCF + 2] = u; ek[O_SRC + s * SRCF + 3] = vv;
+                ek[O_SRC + s * SRCF + 4] = fx; ek[O_SRC + s * SRCF + 5] = fy;
+                ek[O_SRC + s * SRCF + 6] = i_as_float(off);
+            }
+        }
+        if (BWD) {
+            ek[O_Z] = zv; ek[O_D] = d;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) ek[O_YM + ch] = f.Tc[ch];
+#pragma unroll
+            for (int k = NEF; k < NE4 * 4; ++k) ek[k] = 0.f;
+            mb_wait(c.bars, BAR_EMPTY + t.idx, t.par ^ 1);   // the previous fill of this slot has been consumed
+            const int base = slot_vec(t);
+#pragma unroll
+            for (int k = 0; k < NE4; ++k) {
+                Vec4 s4; s4.x = ek[4 * k]; s4.y = ek[4 * k + 1]; s4.z = ek[4 * k + 2]; s4.w = ek[4 * k + 3];
+                s_st4(c.ring, base + k * 32, s4);
+            }
+        }
+    }
+
+    // ---- C(i): the gathers of row i have returned: bilinear value + slopes (BWD: late part of the slot),
+    // horizontal 3-sums (window column centred on this lane) ----
+    static MD2_DEV void stage_consume(const CtxF& c, const PipeF& f, Row& cur) {
+        const Geo& g = c.g;
+        const int lane = g.lane;
+        float Xc[S][C], lk[NL4 * 4];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float fx = f.fx[s], fy = f.fy[s];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                const float v00 = f.G[s][ch][0], v01 = f.G[s][ch][1], v10 = f.G[s][ch][2], v11 = f.G[s][ch][3];
                 const float dtop = v01 - v00, dbot = v11 - v10, dl = v10 - v00;
                 const float dd = dbot - dtop;
                 const float dix = fmaf(fy, dd, dtop);          // d value / d ix
                 const float diy = fmaf(fx, dd, dl);            // d value / d iy
                 Xc[s][ch] = fmaf(fy, diy, fmaf(fx, dtop, v00)) - c.rc[ch];
-                if (BWD) { pk[O_SRC + s * SRCF + 7 + ch] = dix; pk[O_SRC + s * SRCF + 7 + C + ch] = diy; }
-            }
-            if (BWD) {
-                // clip-gradient masks (0 where the un-clipped coordinate is <= 1 or >= size), folded into q
-                pk[O_SRC + s * SRCF + 0] = (u > 1.0f && u < c.Wf) ? q : 0.0f;
-                pk[O_SRC + s * SRCF + 1] = (vv > 1.0f && vv < c.Hf) ? q : 0.0f;
-                pk[O_SRC + s * SRCF + 2] = u; pk[O_SRC + s * SRCF + 3] = vv;
-                pk[O_SRC + s * SRCF + 4] = fx; pk[O_SRC + s * SRCF + 5] = fy;
-                pk[O_SRC + s * SRCF + 6] = i_as_float(off);
+                if (BWD) {
+                    lk[(O_XM - O_XM) + s * C + ch] = Xc[s][ch];
+                    lk[(O_SL - O_XM) + s * 2 * C + ch] = dix; lk[(O_SL - O_XM) + s * 2 * C + C + ch] = diy;
+                }
             }
         }
         if (BWD) {
-            pk[O_Z] = zv; pk[O_D] = d;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                pk[O_YM + ch] = Tc[ch];
+            for (int k = NLF; k < NL4 * 4; ++k) lk[k] = 0.f;
+            const int base = slot_vec(c.fill) + NE4 * 32;
 #pragma unroll
-                for (int s = 0; s < S; ++s) pk[O_XM + s * C + ch] = Xc[s][ch];
+            for (int k = 0; k < NL4; ++k) {
+                Vec4 s4; s4.x = lk[4 * k]; s4.y = lk[4 * k + 1]; s4.z = lk[4 * k + 2]; s4.w = lk[4 * k + 3];
+                s_st4(c.ring, base + k * 32, s4);
             }
-#pragma unroll
-            for (int k = NPPF; k < NPP4 * 4; ++k) pk[k] = 0.f;
         }
+        cur.D = f.d;
         // horizontal 3-sums (window column centred on this lane)
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            const float yl = w_up(Tc[ch], lane), yr = w_dn(Tc[ch], lane);
-            cur.ym[ch] = Tc[ch];
-            cur.hy[ch] = yl + Tc[ch] + yr;
-            cur.hyy[ch] = fmaf(yr, yr, fmaf(Tc[ch], Tc[ch], yl * yl));
+            const float Tc = f.Tc[ch];
+            const float yl = w_up(Tc, lane), yr = w_dn(Tc, lane);
+            cur.ym[ch] = Tc;
+            cur.hy[ch] = yl + Tc + yr;
+            cur.hyy[ch] = fmaf(yr, yr, fmaf(Tc, Tc, yl * yl));
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 const float xl = w_up(Xc[s][ch], lane), xr = w_dn(Xc[s][ch], lane);
                 cur.xm[s][ch] = Xc[s][ch];
                 cur.hx[s][ch] = xl + Xc[s][ch] + xr;
                 cur.hxx[s][ch] = fmaf(xr, xr, fmaf(Xc[s][ch], Xc[s][ch], xl * xl));
-                cur.hxy[s][ch] = fmaf(xr, yr, fmaf(Xc[s][ch], Tc[ch], xl * yl));
+                cur.hxy[s][ch] = fmaf(xr, yr, fmaf(Xc[s][ch], Tc, xl * yl));
             }
         }
     }
@@ -424,30 +542,30 @@ struct March {
         }
     }
 
-    // hand one ring slot to warp B: wait until it is empty, store the packets, signal full
-    static MD2_DEV void publish(CtxF& c, const float (&pk)[NPP4 * 4], const float (&wp)[NWP4 * 4]) {
-        const int slot = c.gslot % MARCH_DEPTH, fill = c.gslot / MARCH_DEPTH;
-        mb_wait(c.bars, BAR_EMPTY + slot, (fill & 1) ^ 1);   // the previous fill of this slot has been consumed
-        Vec4* dst = c.ring + slot * (SLOT4 * 32) + c.g.lane;
-#pragma unroll
-        for (int k = 0; k < NPP4; ++k) {
-            Vec4 s4; s4.x = pk[4 * k]; s4.y = pk[4 * k + 1]; s4.z = pk[4 * k + 2]; s4.w = pk[4 * k + 3];
-            dst[k * 32] = s4;
-        }
+    // the window packet completes the slot of the consumed row: store it and hand the slot to warp B
+    static MD2_DEV void finish_slot(CtxF& c, const float (&wp)[NWP4 * 4]) {
+        const int base = slot_vec(c.fill) + NPP4 * 32;
 #pragma unroll
         for (int k = 0; k < NWP4; ++k) {
             Vec4 s4; s4.x = wp[4 * k]; s4.y = wp[4 * k + 1]; s4.z = wp[4 * k + 2]; s4.w = wp[4 * k + 3];
-            dst[(NPP4 + k) * 32] = s4;
+            s_st4(c.ring, base + k * 32, s4);
         }
-        mb_arrive(c.bars, BAR_FULL + slot);
-        c.gslot = c.gslot + 1 == SLOT_WRAP ? 0 : c.gslot + 1;
+        mb_arrive(c.bars, BAR_FULL + c.fill.idx);
+        c.fill = next_slot(c.fill);
     }
 
-    static MD2_DEV void stepF(const FusedParams& p, CtxF& c, AccF& acc, Row& a, Row& b, Row& cur, int i) {
-        float pk[NPP4 * 4], wp[NWP4 * 4];
-        stage_load(p, c, cur, i, pk);
-        stage_windows(p, c, acc, a, b, cur, i, wp);
-        if (BWD) publish(c, pk, wp);
+    // one row of the pipeline: C(i), A(i+1), W(i-1)
+    static MD2_DEV void stepF(const FusedParams& p, CtxF& c, PipeF& f, AccF& acc, Row& a, Row& b, Row& cur, int i, int iend,
+                              bool windows) {
+        float wp[NWP4 * 4];
+        stage_consume(c, f, cur);
+        if (i + 1 < iend) stage_issue(p, c, f, i + 1, next_slot(c.fill));
+        if (windows) stage_windows(p, c, acc, a, b, cur, i, wp);
+        else {
+#pragma unroll
+            for (int k = 0; k < NWP4 * 4; ++k) wp[k] = 0.f;
+        }
+        if (BWD) finish_slot(c, wp);
     }
 
     // warp F of one work item; gslot: running ring-slot counter of this warp
@@ -462,7 +580,7 @@ struct March {
         c.tg = tgn + g.gxm;
 #pragma unroll
         for (int s = 0; s < S; ++s) c.sb[s] = p.src[s] + (long long)g.n * p.src_ns[s];
-        c.dp = p.dfull[g.scale] + (long long)g.n * g.HW;
+        c.dp = p.dfull[g.scale] + (long long)g.n * g.HW + g.gxm;
         c.am = p.automask ? p.automask + (long long)g.n * g.HW : nullptr;
         // centring constant of the window sums (any constant is exact; a local value keeps the
         // centred squares small): the target at the middle of the strip chunk
@@ -484,11 +602,11 @@ struct March {
         c.kq = wcol ? up_photo * (PHOTO_ALPHA / C) * (-0.5f) : 0.f;
         c.wl = (g.gxr == 1) ? 2.f : 1.f;
         c.wr = (g.gxr == g.W - 2) ? 2.f : 1.f;
-        c.ring = reinterpret_cast<Vec4*>(wsm);
-        c.bars = reinterpret_cast<mbar_t*>(wsm + RING_FLOATS);
-        c.gslot = gslot;
+        c.ring = ring_ref_of(wsm, lane);
+        c.bars = bar_ref_of(wsm + RING_FLOATS);
+        c.fill = slot_of(gslot);
         // pin the per-lane invariants in registers (otherwise they are re-derived in every row)
-        keep(c.g.gxm); keep(c.tg); keep(c.dp);
+        keep(c.g.gxm); keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.sb[s]);
@@ -502,30 +620,30 @@ struct March {
         AccF acc;
         acc.warp_sum = acc.ssx = acc.ssy = acc.dsum = 0.f;
         Row r0, r1, r2;
-        // rows i0, i0+1: load only (their ring slots carry pixel packets, no window packet yet); then
-        // every row runs L(i), W(i-1); the loop is unrolled by 3 so that the three row registers
-        // rotate roles without moves
+        PipeF f;
+        // rows i0, i0+1 carry pixel packets only (no window yet); then every row runs C(i), A(i+1), W(i-1);
+        // the loop is unrolled by 3 so that the three row registers rotate roles without moves
         const int i0 = g.Y0 - HALO, iend = g.Y1 + HALO;
-        {
-            float pk[NPP4 * 4], wp[NWP4 * 4];
+        {   // prime the pipeline: loads of row i0, then A(i0)
+            const int toff = image_row(i0, g.H) * g.W;
+            f.dn = g_ld(c.dp + toff);
 #pragma unroll
-            for (int k = 0; k < NWP4 * 4; ++k) wp[k] = 0.f;
-            stage_load(p, c, r0, i0, pk);
-            if (BWD) publish(c, pk, wp);
-            stage_load(p, c, r1, i0 + 1, pk);
-            if (BWD) publish(c, pk, wp);
+            for (int ch = 0; ch < C; ++ch) f.Tn[ch] = g_ld(c.tg + (ch * g.HW + toff));
+            stage_issue(p, c, f, i0, c.fill);
         }
+        stepF(p, c, f, acc, r0, r0, r0, i0, iend, false);
+        stepF(p, c, f, acc, r0, r0, r1, i0 + 1, iend, false);
         int i = i0 + 2;
         for (; i + 2 < iend; i += 3) {
-            stepF(p, c, acc, r0, r1, r2, i);
-            stepF(p, c, acc, r1, r2, r0, i + 1);
-            stepF(p, c, acc, r2, r0, r1, i + 2);
+            stepF(p, c, f, acc, r0, r1, r2, i, iend, true);
+            stepF(p, c, f, acc, r1, r2, r0, i + 1, iend, true);
+            stepF(p, c, f, acc, r2, r0, r1, i + 2, iend, true);
         }
         if (i < iend) {
-            stepF(p, c, acc, r0, r1, r2, i);
-            if (i + 1 < iend) stepF(p, c, acc, r1, r2, r0, i + 1);
+            stepF(p, c, f, acc, r0, r1, r2, i, iend, true);
+            if (i + 1 < iend) stepF(p, c, f, acc, r1, r2, r0, i + 1, iend, true);
         }
-        gslot = c.gslot;
+        gslot = counter_of(c.fill);
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = 0.f;
         v[0] = acc.warp_sum; v[1] = acc.ssx; v[2] = acc.ssy; v[3] = acc.dsum;
@@ -543,8 +661,8 @@ struct March {
         float cl1;                   // up_photo * (1-alpha)/C
         float mp;                    // pcol ? 1 : 0
         float cxn, cyn, sA, sB, nega;
-        const Vec4* ring;
-        mbar_t* bars;
+        ring_ref ring;               // + this lane's Vec4 column
+        bar_ref bars;
     };
     struct AccB {
         float P0[S][3], P1[S][3], Ph[S][3];
@@ -553,10 +671,9 @@ struct March {
         float ey_prev;
     };
 
-    static MD2_DEV const Vec4* slot_ptr(const CtxB& c, int gs) { return c.ring + (gs % MARCH_DEPTH) * (SLOT4 * 32) + c.g.lane; }
     // acquire = wait until warp F has filled the slot, release = hand it back
-    static MD2_DEV void acquire(const CtxB& c, int gs) { mb_wait(c.bars, BAR_FULL + gs % MARCH_DEPTH, (gs / MARCH_DEPTH) & 1); }
-    static MD2_DEV void release(const CtxB& c, int gs) { mb_arrive(c.bars, BAR_EMPTY + gs % MARCH_DEPTH); }
+    static MD2_DEV void acquire(const CtxB& c, Slot t) { mb_wait(c.bars, BAR_FULL + t.idx, t.par); }
+    static MD2_DEV void release(const CtxB& c, Slot t) { mb_arrive(c.bars, BAR_EMPTY + t.idx); }
 
     // vertical smoothness edge between rows y and y+1 (own target values / disparities of both rows)
     static MD2_DEV float edge_y(const CtxB& c, int y, const float* ymA, float DA, const float* ymB, float DB) {
@@ -568,26 +685,26 @@ struct March {
     }
 
     // ---- P(r): slot s0 = row r (pixel packet, window packet r-1), s1 = row r+1 (window r), s2 = row r+2 (window r+1) ----
-    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, const Vec4* s0, const Vec4* s1,
-                                     const Vec4* s2) {
+    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, Slot t1, Slot t2) {
         const Geo& g = c.g;
         const int lane = g.lane;
+        const int s0 = slot_vec(t0), s1 = slot_vec(t1), s2 = slot_vec(t2);
         float pk[NPP4 * 4], wa[NWP4 * 4], wb[NWP4 * 4], wc[NWP4 * 4], nx[NYD4 * 4];
 #pragma unroll
         for (int k = 0; k < NPP4; ++k) {
-            const Vec4 t = s0[k * 32];
+            const Vec4 t = s_ld4(c.ring, s0 + k * 32);
             pk[4 * k] = t.x; pk[4 * k + 1] = t.y; pk[4 * k + 2] = t.z; pk[4 * k + 3] = t.w;
         }
 #pragma unroll
         for (int k = 0; k < NWP4; ++k) {
-            const Vec4 ta = s0[(NPP4 + k) * 32], tb = s1[(NPP4 + k) * 32], tc = s2[(NPP4 + k) * 32];
+            const Vec4 ta = s_ld4(c.ring, s0 + (NPP4 + k) * 32), tb = s_ld4(c.ring, s1 + (NPP4 + k) * 32), tc = s_ld4(c.ring, s2 + (NPP4 + k) * 32);
             wa[4 * k] = ta.x; wa[4 * k + 1] = ta.y; wa[4 * k + 2] = ta.z; wa[4 * k + 3] = ta.w;
             wb[4 * k] = tb.x; wb[4 * k + 1] = tb.y; wb[4 * k + 2] = tb.z; wb[4 * k + 3] = tb.w;
             wc[4 * k] = tc.x; wc[4 * k + 1] = tc.y; wc[4 * k + 2] = tc.z; wc[4 * k + 3] = tc.w;
         }
 #pragma unroll
         for (int k = 0; k < NYD4; ++k) {   // ym[C], D of row r+1
-            const Vec4 t = s1[k * 32];
+            const Vec4 t = s_ld4(c.ring, s1 + k * 32);
             nx[4 * k] = t.x; nx[4 * k + 1] = t.y; nx[4 * k + 2] = t.z; nx[4 * k + 3] = t.w;
         }
         const float Da = pk[O_D];
@@ -631,8 +748,8 @@ struct March {
                 float du = 0.f, dv = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
-                    du = fmaf(ibar[ch], st[7 + ch], du);
-                    dv = fmaf(ibar[ch], st[7 + C + ch], dv);
+                    du = fmaf(ibar[ch], pk[O_SL + s * 2 * C + ch], du);
+                    dv = fmaf(ibar[ch], pk[O_SL + s * 2 * C + C + ch], dv);
                 }
                 const float cb0 = du * qa, cb1 = dv * qb;
                 const float cb2 = -fmaf(cb0, u, cb1 * vv);
@@ -743,18 +860,19 @@ struct March {
         c.cyn = 1.0f / ((float)g.W * (float)(g.H - 1) * (float)p.N);
         c.nega = -p.depth_a;
         {
-            const float* st = p.stats + ((long long)g.scale * p.N + g.n) * NSTAT;
             const float up_s = p.gloss * p.loss_scale * p.smooth_w[g.scale];
             c.sA = up_s; c.sB = 0.f;
             if (p.normalize_disp) {
-                const float m = st[3] / (float)g.HW + 1e-7f;
+                float ssx, ssy, dsum;
+                prep_stats(p, g.scale, g.n, lane, ssx, ssy, dsum);
+                const float m = dsum / (float)g.HW + 1e-7f;
                 c.sA = up_s / m;
-                c.sB = up_s * (c.cxn * st[1] + c.cyn * st[2]) / (m * m * (float)g.HW);
+                c.sB = up_s * (c.cxn * ssx + c.cyn * ssy) / (m * m * (float)g.HW);
             }
         }
-        c.ring = reinterpret_cast<const Vec4*>(wsm);
-        c.bars = reinterpret_cast<mbar_t*>(wsm + RING_FLOATS);
-        keep(c.g.gxm); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB);
+        c.ring = ring_ref_of(wsm, lane);
+        c.bars = bar_ref_of(wsm + RING_FLOATS);
+        keep(c.g.gxm); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.gb[s]);
@@ -771,37 +889,39 @@ struct March {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) acc.car0[s][ch] = acc.car1[s][ch] = 0.f;
         }
-        // ring slot gslot + j holds row Y0 - 2 + j of this item
-        int gs = gslot;
-        acquire(c, gs);                                            // row Y0-2: nothing to read
-        release(c, gs);
-        acquire(c, gs + 1);                                        // row Y0-1
-        acquire(c, gs + 2);                                        // row Y0
+        // the ring slots after `gslot` hold rows Y0-2, Y0-1, Y0, ... of this item
+        Slot ta = slot_of(gslot);
+        acquire(c, ta);                                            // row Y0-2: nothing to read
+        release(c, ta);
+        ta = next_slot(ta);
+        acquire(c, ta);                                            // row Y0-1
+        Slot tb = next_slot(ta);
+        acquire(c, tb);                                            // row Y0
         {   // the "up" edge of the first row
             float ya[NYD4 * 4], yb[NYD4 * 4];
-            const Vec4* sa = slot_ptr(c, gs + 1);
-            const Vec4* sb = slot_ptr(c, gs + 2);
+            const int sa = slot_vec(ta), sb = slot_vec(tb);
 #pragma unroll
             for (int k = 0; k < NYD4; ++k) {
-                const Vec4 ta = sa[k * 32], tb = sb[k * 32];
-                ya[4 * k] = ta.x; ya[4 * k + 1] = ta.y; ya[4 * k + 2] = ta.z; ya[4 * k + 3] = ta.w;
-                yb[4 * k] = tb.x; yb[4 * k + 1] = tb.y; yb[4 * k + 2] = tb.z; yb[4 * k + 3] = tb.w;
+                const Vec4 va = s_ld4(c.ring, sa + k * 32), vb = s_ld4(c.ring, sb + k * 32);
+                ya[4 * k] = va.x; ya[4 * k + 1] = va.y; ya[4 * k + 2] = va.z; ya[4 * k + 3] = va.w;
+                yb[4 * k] = vb.x; yb[4 * k + 1] = vb.y; yb[4 * k + 2] = vb.z; yb[4 * k + 3] = vb.w;
             }
             acc.ey_prev = edge_y(c, g.Y0 - 1, ya + O_YM, ya[O_D], yb + O_YM, yb[O_D]);
         }
-        release(c, gs + 1);
-        acquire(c, gs + 3);                                        // row Y0+1
-        gs += 2;                                                   // gs = slot of row r
+        release(c, ta);
+        ta = tb;                                                   // ta = slot of row r, tb = slot of row r+1
+        tb = next_slot(tb);
+        acquire(c, tb);                                            // row Y0+1
         for (int r = g.Y0; r < g.Y1; ++r) {
-            acquire(c, gs + 2);                                    // row r+2 (carries window row r+1)
-            stage_pixels(p, c, acc, r, slot_ptr(c, gs), slot_ptr(c, gs + 1), slot_ptr(c, gs + 2));
-            release(c, gs);
-            ++gs;
-            if (gs >= 2 * SLOT_WRAP) gs -= SLOT_WRAP;              // keep the counter small (slot and parity are periodic)
+            const Slot tc = next_slot(tb);
+            acquire(c, tc);                                        // row r+2 (carries window row r+1)
+            stage_pixels(p, c, acc, r, ta, tb, tc);
+            release(c, ta);
+            ta = tb; tb = tc;
         }
-        release(c, gs);                                            // rows Y1, Y1+1
-        release(c, gs + 1);
-        gslot = (gs + 2) % SLOT_WRAP;
+        release(c, ta);                                            // rows Y1, Y1+1
+        release(c, tb);
+        gslot = counter_of(next_slot(tb));
         // flush the carried lower tap pairs of the last row
 #pragma unroll
         for (int s = 0; s < S; ++s)

@@ -266,6 +266,7 @@ struct VslDesc
     grad_rot::NTuple{MAX_S, P32}; grad_trans::NTuple{MAX_S, P32}; grad_source::NTuple{MAX_S, P32}
     viz_warped::NTuple{MAX_S, P32}; viz_loss::P32
     saved::P32
+    zero_grad_source::Int32
 end
 pad(v, n, z) = ntuple(i -> i <= length(v) ? v[i] : z, n)
 frameptr(x::CuF, id) = pointer(x, (id - 1) * size(x, 1) * size(x, 2) * size(x, 3) + 1)   # x (W,H,C,L,N), 1-based frame id
@@ -297,7 +298,7 @@ function vsl_fwdbwd(x::CuF, disparities, rvecs, tvecs, K::CuF, invK::CuF; target
         Float32(loss_scale === nothing ? 1 / L : loss_scale), Int32(normalize), ptr(loss),
         pad([ptr(g) for g in gd], MAX_L, P32(0)), pad([ptr(g) for g in gr], MAX_S, P32(0)),
         pad([ptr(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
-        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0)))
+        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0), Int32(0)))
     GC.@preserve x disparities rvecs tvecs K invK auto_loss loss gd gr gt vw vl begin
         check(ccall((:md2_view_synthesis_loss_fwdbwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Ptr{Cvoid}),
                     ctx(), desc, 1f0, stream()))
@@ -362,7 +363,7 @@ function _warp_desc(disp, x, Ps, invKs, Ks, min_depth, max_depth, source_ids, gr
             pad([ptr(disp)], MAX_L, z), pad(Int32[W], MAX_L, Int32(0)), pad(Int32[H], MAX_L, Int32(0)), ptr(Ks), ptr(invKs),
             Int32(0), pad([ptr(P[1]) for P in Ps], MAX_S, z), pad([ptr(P[2]) for P in Ps], MAX_S, z), pad(Int32[], MAX_S, Int32(0)),
             z, Float32(min_depth), Float32(max_depth), pad(Float32[], MAX_L, 0f0), 1f0, Int32(0), z,
-            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z)
+            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z, Int32(0))
 end
 function rrule(::typeof(warp), disp::CuF, x::CuF, Ps, backprojections, projections, invKs::CuF, Ks::CuF; min_depth, max_depth, source_ids)
     outs = warp(disp, x, Ps, backprojections, projections, invKs, Ks; min_depth, max_depth, source_ids)

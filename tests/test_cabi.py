@@ -49,9 +49,9 @@ def test_desc_layout_matches_c():
 #include <stddef.h>
 #include "md2.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(md2_vsl_desc), offsetof(md2_vsl_desc, disparity),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(md2_vsl_desc), offsetof(md2_vsl_desc, disparity),
          offsetof(md2_vsl_desc, K), offsetof(md2_vsl_desc, automask), offsetof(md2_vsl_desc, loss),
-         offsetof(md2_vsl_desc, grad_source), offsetof(md2_vsl_desc, saved));
+         offsetof(md2_vsl_desc, grad_source), offsetof(md2_vsl_desc, saved), offsetof(md2_vsl_desc, zero_grad_source));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(code)
@@ -59,7 +59,7 @@ int main(void) {
         vals = [int(v) for v in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
     D = L.VslDesc
     assert vals == [C.sizeof(D), D.disparity.offset, D.K.offset, D.automask.offset, D.loss.offset,
-                    D.grad_source.offset, D.saved.offset]
+                    D.grad_source.offset, D.saved.offset, D.zero_grad_source.offset]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
