@@ -147,7 +147,7 @@ MD2_DEV void g_red(float* q, float v) { asm volatile("red.global.add.f32 [%0], %
 MD2_DEV void g_red1(float* q, float v) { asm volatile("red.global.add.f32 [%0+4], %1;" ::"l"(q), "f"(v)); }
 // pull a line into L1 one row ahead of its use (every row of the march touches new lines)
 #ifndef MD2_PREFETCH
-#define MD2_PREFETCH 1
+#define MD2_PREFETCH 0   // measured: with the register pipeline of warp F the L1 prefetch of source rows costs more than it saves
 #endif
 MD2_DEV void g_pf(const float* q) {
 #if MD2_PREFETCH == 1
@@ -212,9 +212,9 @@ struct March {
     static constexpr int NPART = NSTAT + 12 * S;
     // ---- ring slot layout (floats per lane) ----
     // pixel packet of row i, early part (known once the geometry of the row is): own target values ym[C],
-    // disparity D, depth z, then per source: A = mx q, B = my q, u, v, fx, fy, gather offset
+    // disparity D, depth z, then per source: q = 1/(c3 + eps), u, v, fx, fy, gather offset
     static constexpr int O_YM = 0, O_D = C, O_Z = C + 1, O_SRC = C + 2;
-    static constexpr int SRCF = 7;
+    static constexpr int SRCF = 6;
     static constexpr int NEF = O_SRC + S * SRCF;
     static constexpr int NE4 = (NEF + 3) / 4;
     // late part (known once the gathers have returned): own warped values xm[S][C], then per source
@@ -224,8 +224,9 @@ struct March {
     static constexpr int NL4 = (NLF + 3) / 4;
     static constexpr int NPP4 = NE4 + NL4;
     static constexpr int NYD4 = (C + 1 + 3) / 4;         // Vec4s holding ym[C], D
-    // window packet of row i-1: t[3C], s0[3C], selected source
-    static constexpr int NWPF = 6 * C + 1;
+    // window packet of row i-1: the SSIM gradient coefficients (alpha, beta, gamma)[C] of the selected source,
+    // scaled by the window's upstream cotangent, and the selected source
+    static constexpr int NWPF = 3 * C + 1;
     static constexpr int NWP4 = (NWPF + 3) / 4;
     static constexpr int SLOT4 = NPP4 + NWP4;            // Vec4 per lane and slot
     static constexpr int RING_FLOATS = BWD ? (MARCH_DEPTH * SLOT4 * 32 * 4) : 0;
@@ -274,7 +275,6 @@ struct March {
         int pb[S];
         float Wf, Hf;
         float kq;                    // wcol ? up_photo * alpha/C * (-1/2) : 0
-        float wl, wr;                // horizontal reflect-pad adjoint weights of this pixel column
         ring_ref ring;               // + this lane's Vec4 column
         bar_ref bars;
         Slot fill;                   // slot of the row being consumed (C / W stages); A pre-fills the next one
@@ -346,12 +346,10 @@ struct March {
             }
             f.fx[s] = fx; f.fy[s] = fy;
             if (BWD) {
-                // clip-gradient masks (0 where the un-clipped coordinate is <= 1 or >= size), folded into q
-                ek[O_SRC + s * SRCF + 0] = (u > 1.0f && u < c.Wf) ? q : 0.0f;
-                ek[O_SRC + s * SRCF + 1] = (vv > 1.0f && vv < c.Hf) ? q : 0.0f;
-                ek[O_SRC + s * SRCF + 2] = u; ek[O_SRC + s * SRCF + 3] = vv;
-                ek[O_SRC + s * SRCF + 4] = fx; ek[O_SRC + s * SRCF + 5] = fy;
-                ek[O_SRC + s * SRCF + 6] = i_as_float(off);
+                ek[O_SRC + s * SRCF + 0] = q;
+                ek[O_SRC + s * SRCF + 1] = u; ek[O_SRC + s * SRCF + 2] = vv;
+                ek[O_SRC + s * SRCF + 3] = fx; ek[O_SRC + s * SRCF + 4] = fy;
+                ek[O_SRC + s * SRCF + 5] = i_as_float(off);
             }
         }
         if (BWD) {
@@ -525,18 +523,12 @@ struct March {
             }
         }
         if (BWD) {
-            // scale by the upstream cotangent of this window (0 outside the image / where the automask won)
+            // scale by the upstream cotangent of this window (0 outside the image / where the automask won);
+            // warp B forms the horizontal adjoint sums
             const float k = (row_in && sel >= 0) ? c.kq : 0.f;
-            const int e0 = w_up(sel, lane), e2 = w_dn(sel, lane);
-            const float m0 = (e0 == 0) ? c.wl : 0.f, m1 = (sel == 0) ? 1.f : 0.f, m2 = (e2 == 0) ? c.wr : 0.f;
 #pragma unroll
-            for (int j = 0; j < 3 * C; ++j) {
-                const float c1 = cf[j] * k;
-                const float c0 = w_up(c1, lane), c2 = w_dn(c1, lane);
-                wp[j] = fmaf(c.wl, c0, fmaf(c.wr, c2, c1));
-                wp[3 * C + j] = (S > 1) ? fmaf(m0, c0, fmaf(m2, c2, m1 * c1)) : 0.f;
-            }
-            wp[6 * C] = i_as_float(sel);
+            for (int j = 0; j < 3 * C; ++j) wp[j] = cf[j] * k;
+            wp[3 * C] = i_as_float(sel);
 #pragma unroll
             for (int k2 = NWPF; k2 < NWP4 * 4; ++k2) wp[k2] = 0.f;
         }
@@ -600,8 +592,6 @@ struct March {
         }
         const float up_photo = p.gloss * p.loss_scale / ((float)g.W * (float)g.H * (float)p.N);
         c.kq = wcol ? up_photo * (PHOTO_ALPHA / C) * (-0.5f) : 0.f;
-        c.wl = (g.gxr == 1) ? 2.f : 1.f;
-        c.wr = (g.gxr == g.W - 2) ? 2.f : 1.f;
         c.ring = ring_ref_of(wsm, lane);
         c.bars = bar_ref_of(wsm + RING_FLOATS);
         c.fill = slot_of(gslot);
@@ -661,9 +651,14 @@ struct March {
         float cl1;                   // up_photo * (1-alpha)/C
         float mp;                    // pcol ? 1 : 0
         float cxn, cyn, sA, sB, nega;
+        float wl, wr;                // horizontal reflect-pad adjoint weights of this pixel column
+        float Wf, Hf;
         ring_ref ring;               // + this lane's Vec4 column
         bar_ref bars;
     };
+    // one window row after the horizontal adjoint 3-sums: t = sums of the (scaled) coefficients of the
+    // three windows around this column, z = the part of t selected for source 0, sel = this column's selection
+    struct WinRow { float t[3 * C], z[3 * C]; int sel; };
     struct AccB {
         float P0[S][3], P1[S][3], Ph[S][3];
         float car0[S][C], car1[S][C];
@@ -684,23 +679,41 @@ struct March {
         return (y >= 0 && y + 1 < c.g.H) ? sgn_scaled(DA - DB, w) : 0.f;
     }
 
-    // ---- P(r): slot s0 = row r (pixel packet, window packet r-1), s1 = row r+1 (window r), s2 = row r+2 (window r+1) ----
-    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, Slot t1, Slot t2) {
+    // window row carried by slot `t` (window packet of the row above the slot's pixel row): horizontal adjoint 3-sums
+    static MD2_DEV void load_window_row(const CtxB& c, Slot t, WinRow& w) {
+        const int lane = c.g.lane;
+        const int sv = slot_vec(t) + NPP4 * 32;
+        float wq[NWP4 * 4];
+#pragma unroll
+        for (int k = 0; k < NWP4; ++k) {
+            const Vec4 q = s_ld4(c.ring, sv + k * 32);
+            wq[4 * k] = q.x; wq[4 * k + 1] = q.y; wq[4 * k + 2] = q.z; wq[4 * k + 3] = q.w;
+        }
+        const int sel = f_as_int(wq[3 * C]);
+        w.sel = sel;
+        const int e0 = w_up(sel, lane), e2 = w_dn(sel, lane);
+        const float m0 = (e0 == 0) ? c.wl : 0.f, m1 = (sel == 0) ? 1.f : 0.f, m2 = (e2 == 0) ? c.wr : 0.f;
+#pragma unroll
+        for (int j = 0; j < 3 * C; ++j) {
+            const float c1 = wq[j];
+            const float c0 = w_up(c1, lane), c2 = w_dn(c1, lane);
+            w.t[j] = fmaf(c.wl, c0, fmaf(c.wr, c2, c1));
+            w.z[j] = (S > 1) ? fmaf(m0, c0, fmaf(m2, c2, m1 * c1)) : 0.f;
+        }
+    }
+
+    // ---- P(r): slot t0 = row r (pixel packet), t1 = row r+1 (target values / disparity for the vertical edge);
+    // wa, wb, wc = window rows r-1, r, r+1 ----
+    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, Slot t1, const WinRow& wa,
+                                     const WinRow& wb, const WinRow& wc) {
         const Geo& g = c.g;
         const int lane = g.lane;
-        const int s0 = slot_vec(t0), s1 = slot_vec(t1), s2 = slot_vec(t2);
-        float pk[NPP4 * 4], wa[NWP4 * 4], wb[NWP4 * 4], wc[NWP4 * 4], nx[NYD4 * 4];
+        const int s0 = slot_vec(t0), s1 = slot_vec(t1);
+        float pk[NPP4 * 4], nx[NYD4 * 4];
 #pragma unroll
         for (int k = 0; k < NPP4; ++k) {
             const Vec4 t = s_ld4(c.ring, s0 + k * 32);
             pk[4 * k] = t.x; pk[4 * k + 1] = t.y; pk[4 * k + 2] = t.z; pk[4 * k + 3] = t.w;
-        }
-#pragma unroll
-        for (int k = 0; k < NWP4; ++k) {
-            const Vec4 ta = s_ld4(c.ring, s0 + (NPP4 + k) * 32), tb = s_ld4(c.ring, s1 + (NPP4 + k) * 32), tc = s_ld4(c.ring, s2 + (NPP4 + k) * 32);
-            wa[4 * k] = ta.x; wa[4 * k + 1] = ta.y; wa[4 * k + 2] = ta.z; wa[4 * k + 3] = ta.w;
-            wb[4 * k] = tb.x; wb[4 * k + 1] = tb.y; wb[4 * k + 2] = tb.z; wb[4 * k + 3] = tb.w;
-            wc[4 * k] = tc.x; wc[4 * k + 1] = tc.y; wc[4 * k + 2] = tc.z; wc[4 * k + 3] = tc.w;
         }
 #pragma unroll
         for (int k = 0; k < NYD4; ++k) {   // ym[C], D of row r+1
@@ -711,7 +724,7 @@ struct March {
         const float ey = edge_y(c, r, pk + O_YM, Da, nx + O_YM, nx[O_D]);
         const float wu = (r == 1) ? 2.f : 1.f, wd = (r == g.H - 2) ? 2.f : 1.f;
         const float pyr = (float)(r + 1);
-        const int selr = f_as_int(wb[6 * C]);
+        const int selr = wb.sel;
         const float zr = pk[O_Z];
         float dbar_z = 0.f;
 #pragma unroll
@@ -723,14 +736,14 @@ struct March {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
                 float sa, sb_, sg;
-                const float ta = fmaf(wu, wa[3 * ch], fmaf(wd, wc[3 * ch], wb[3 * ch]));
-                const float tb = fmaf(wu, wa[3 * ch + 1], fmaf(wd, wc[3 * ch + 1], wb[3 * ch + 1]));
-                const float tgm = fmaf(wu, wa[3 * ch + 2], fmaf(wd, wc[3 * ch + 2], wb[3 * ch + 2]));
+                const float ta = fmaf(wu, wa.t[3 * ch], fmaf(wd, wc.t[3 * ch], wb.t[3 * ch]));
+                const float tb = fmaf(wu, wa.t[3 * ch + 1], fmaf(wd, wc.t[3 * ch + 1], wb.t[3 * ch + 1]));
+                const float tgm = fmaf(wu, wa.t[3 * ch + 2], fmaf(wd, wc.t[3 * ch + 2], wb.t[3 * ch + 2]));
                 if (S == 1) { sa = ta; sb_ = tb; sg = tgm; }
                 else {
-                    const float za = fmaf(wu, wa[3 * C + 3 * ch], fmaf(wd, wc[3 * C + 3 * ch], wb[3 * C + 3 * ch]));
-                    const float zb = fmaf(wu, wa[3 * C + 3 * ch + 1], fmaf(wd, wc[3 * C + 3 * ch + 1], wb[3 * C + 3 * ch + 1]));
-                    const float zg = fmaf(wu, wa[3 * C + 3 * ch + 2], fmaf(wd, wc[3 * C + 3 * ch + 2], wb[3 * C + 3 * ch + 2]));
+                    const float za = fmaf(wu, wa.z[3 * ch], fmaf(wd, wc.z[3 * ch], wb.z[3 * ch]));
+                    const float zb = fmaf(wu, wa.z[3 * ch + 1], fmaf(wd, wc.z[3 * ch + 1], wb.z[3 * ch + 1]));
+                    const float zg = fmaf(wu, wa.z[3 * ch + 2], fmaf(wd, wc.z[3 * ch + 2], wb.z[3 * ch + 2]));
                     if (s == 0) { sa = za; sb_ = zb; sg = zg; }
                     else { sa = ta - za; sb_ = tb - zb; sg = tgm - zg; }
                 }
@@ -742,9 +755,12 @@ struct March {
             }
             // sources not selected anywhere in the 3x3 neighbourhood of any lane skip all of this
             if (w_any(act)) {
-                const float qa = st[0], qb = st[1], u = st[2], vv = st[3];
-                const float fx = st[4], fy = st[5];
-                const int off = f_as_int(st[6]);
+                const float q = st[0], u = st[1], vv = st[2];
+                const float fx = st[3], fy = st[4];
+                const int off = f_as_int(st[5]);
+                // clip-gradient masks (0 where the un-clipped coordinate is <= 1 or >= size), folded into q
+                const float qa = (u > 1.0f && u < c.Wf) ? q : 0.0f;
+                const float qb = (vv > 1.0f && vv < c.Hf) ? q : 0.0f;
                 float du = 0.f, dv = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
@@ -859,6 +875,9 @@ struct March {
         c.cxn = 1.0f / ((float)(g.W - 1) * (float)g.H * (float)p.N);
         c.cyn = 1.0f / ((float)g.W * (float)(g.H - 1) * (float)p.N);
         c.nega = -p.depth_a;
+        c.wl = (g.gxr == 1) ? 2.f : 1.f;
+        c.wr = (g.gxr == g.W - 2) ? 2.f : 1.f;
+        c.Wf = (float)g.W; c.Hf = (float)g.H;
         {
             const float up_s = p.gloss * p.loss_scale * p.smooth_w[g.scale];
             c.sA = up_s; c.sB = 0.f;
@@ -912,13 +931,32 @@ struct March {
         ta = tb;                                                   // ta = slot of row r, tb = slot of row r+1
         tb = next_slot(tb);
         acquire(c, tb);                                            // row Y0+1
-        for (int r = g.Y0; r < g.Y1; ++r) {
-            const Slot tc = next_slot(tb);
-            acquire(c, tc);                                        // row r+2 (carries window row r+1)
-            stage_pixels(p, c, acc, r, ta, tb, tc);
-            release(c, ta);
-            ta = tb; tb = tc;
+        // slot(i) carries window row i-1; the three window rows around pixel row r rotate through w0, w1, w2
+        // (loop unrolled by 3: no register moves)
+        WinRow w0, w1, w2;
+        load_window_row(c, ta, w0);                                // window row Y0-1
+        load_window_row(c, tb, w1);                                // window row Y0
+        int r = g.Y0;
+#define MD2_STEP_B(WA, WB, WC)                                                                        \
+        {                                                                                             \
+            const Slot tc = next_slot(tb);                                                            \
+            acquire(c, tc);                                        /* row r+2: carries window row r+1 */ \
+            load_window_row(c, tc, WC);                                                               \
+            stage_pixels(p, c, acc, r, ta, tb, WA, WB, WC);                                           \
+            release(c, ta);                                                                           \
+            ta = tb; tb = tc;                                                                         \
+            ++r;                                                                                      \
         }
+        for (; r + 2 < g.Y1;) {
+            MD2_STEP_B(w0, w1, w2)
+            MD2_STEP_B(w1, w2, w0)
+            MD2_STEP_B(w2, w0, w1)
+        }
+        if (r < g.Y1) {
+            MD2_STEP_B(w0, w1, w2)
+            if (r < g.Y1) MD2_STEP_B(w1, w2, w0)
+        }
+#undef MD2_STEP_B
         release(c, ta);                                            // rows Y1, Y1+1
         release(c, tb);
         gslot = counter_of(next_slot(tb));
