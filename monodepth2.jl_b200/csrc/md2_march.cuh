@@ -225,8 +225,9 @@ struct March {
     static constexpr int NPP4 = NE4 + NL4;
     static constexpr int NYD4 = (C + 1 + 3) / 4;         // Vec4s holding ym[C], D
     // window packet of row i-1: the SSIM gradient coefficients (alpha, beta, gamma)[C] of the selected source,
-    // scaled by the window's upstream cotangent, and the selected source
-    static constexpr int NWPF = 3 * C + 1;
+    // scaled by the window's upstream cotangent, the selected source, and the un-normalised smoothness
+    // gradient ghat of the pixel (divergence of the edge-weighted sign field, src/utils.jl:159-173)
+    static constexpr int NWPF = 3 * C + 2;
     static constexpr int NWP4 = (NWPF + 3) / 4;
     static constexpr int SLOT4 = NPP4 + NWP4;            // Vec4 per lane and slot
     static constexpr int RING_FLOATS = BWD ? (MARCH_DEPTH * SLOT4 * 32 * 4) : 0;
@@ -275,11 +276,12 @@ struct March {
         int pb[S];
         float Wf, Hf;
         float kq;                    // wcol ? up_photo * alpha/C * (-1/2) : 0
+        float cxn, cyn;              // 1 / ((W-1) H N), 1 / (W (H-1) N): the means of src/utils.jl:172
         ring_ref ring;               // + this lane's Vec4 column
         bar_ref bars;
         Slot fill;                   // slot of the row being consumed (C / W stages); A pre-fills the next one
     };
-    struct AccF { float warp_sum, ssx, ssy, dsum; };
+    struct AccF { float warp_sum, ssx, ssy, dsum, ey_prev; };
     // rows in flight between the stages of warp F
     struct PipeF {
         float G[S][C][4];            // the four taps of row i per source and channel (loads issued by A(i))
@@ -529,6 +531,24 @@ struct March {
 #pragma unroll
             for (int j = 0; j < 3 * C; ++j) wp[j] = cf[j] * k;
             wp[3 * C] = i_as_float(sel);
+            // smoothness gradient of pixel row q before the mean-normalisation (warp B applies A ghat - B):
+            // ghat = (ex(q) - ex(q)[left lane]) + (ey(q) - ey(q-1)), e = sign(d - d') exp(-mean_c |T - T'|) / count
+            {
+                const float Dr = w_dn(b.D, lane);
+                float gxs = 0.f, gys = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    gxs += fabsf(b.ym[ch] - w_dn(b.ym[ch], lane));
+                    gys += fabsf(b.ym[ch] - cur.ym[ch]);
+                }
+                const float wx = f_ex2(gxs * (-1.4426950408889634f / C)) * c.cxn;
+                const float wy = f_ex2(gys * (-1.4426950408889634f / C)) * c.cyn;
+                const float ex = g.has_right ? sgn_scaled(b.D - Dr, wx) : 0.f;
+                const float ey = (q >= 0 && q + 1 < g.H) ? sgn_scaled(b.D - cur.D, wy) : 0.f;
+                const float exl = w_up(ex, lane);
+                wp[3 * C + 1] = (ex - exl) + (ey - acc.ey_prev);
+                acc.ey_prev = ey;
+            }
 #pragma unroll
             for (int k2 = NWPF; k2 < NWP4 * 4; ++k2) wp[k2] = 0.f;
         }
@@ -592,6 +612,8 @@ struct March {
         }
         const float up_photo = p.gloss * p.loss_scale / ((float)g.W * (float)g.H * (float)p.N);
         c.kq = wcol ? up_photo * (PHOTO_ALPHA / C) * (-0.5f) : 0.f;
+        c.cxn = 1.0f / ((float)(g.W - 1) * (float)g.H * (float)p.N);
+        c.cyn = 1.0f / ((float)g.W * (float)(g.H - 1) * (float)p.N);
         c.ring = ring_ref_of(wsm, lane);
         c.bars = bar_ref_of(wsm + RING_FLOATS);
         c.fill = slot_of(gslot);
@@ -608,7 +630,7 @@ struct March {
         for (int ch = 0; ch < C; ++ch) keep(c.rc[ch]);
 
         AccF acc;
-        acc.warp_sum = acc.ssx = acc.ssy = acc.dsum = 0.f;
+        acc.warp_sum = acc.ssx = acc.ssy = acc.dsum = acc.ey_prev = 0.f;
         Row r0, r1, r2;
         PipeF f;
         // rows i0, i0+1 carry pixel packets only (no window yet); then every row runs C(i), A(i+1), W(i-1);
@@ -658,26 +680,16 @@ struct March {
     };
     // one window row after the horizontal adjoint 3-sums: t = sums of the (scaled) coefficients of the
     // three windows around this column, z = the part of t selected for source 0, sel = this column's selection
-    struct WinRow { float t[3 * C], z[3 * C]; int sel; };
+    struct WinRow { float t[3 * C], z[3 * C]; int sel; float gh; };
     struct AccB {
         float P0[S][3], P1[S][3], Ph[S][3];
         float car0[S][C], car1[S][C];
         int coff[S];
-        float ey_prev;
     };
 
     // acquire = wait until warp F has filled the slot, release = hand it back
     static MD2_DEV void acquire(const CtxB& c, Slot t) { mb_wait(c.bars, BAR_FULL + t.idx, t.par); }
     static MD2_DEV void release(const CtxB& c, Slot t) { mb_arrive(c.bars, BAR_EMPTY + t.idx); }
-
-    // vertical smoothness edge between rows y and y+1 (own target values / disparities of both rows)
-    static MD2_DEV float edge_y(const CtxB& c, int y, const float* ymA, float DA, const float* ymB, float DB) {
-        float gsum = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) gsum += fabsf(ymA[ch] - ymB[ch]);
-        const float w = f_ex2(gsum * (-1.4426950408889634f / C)) * c.cyn;
-        return (y >= 0 && y + 1 < c.g.H) ? sgn_scaled(DA - DB, w) : 0.f;
-    }
 
     // window row carried by slot `t` (window packet of the row above the slot's pixel row): horizontal adjoint 3-sums
     static MD2_DEV void load_window_row(const CtxB& c, Slot t, WinRow& w) {
@@ -691,6 +703,7 @@ struct March {
         }
         const int sel = f_as_int(wq[3 * C]);
         w.sel = sel;
+        w.gh = wq[3 * C + 1];
         const int e0 = w_up(sel, lane), e2 = w_dn(sel, lane);
         const float m0 = (e0 == 0) ? c.wl : 0.f, m1 = (sel == 0) ? 1.f : 0.f, m2 = (e2 == 0) ? c.wr : 0.f;
 #pragma unroll
@@ -702,26 +715,18 @@ struct March {
         }
     }
 
-    // ---- P(r): slot t0 = row r (pixel packet), t1 = row r+1 (target values / disparity for the vertical edge);
-    // wa, wb, wc = window rows r-1, r, r+1 ----
-    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, Slot t1, const WinRow& wa,
+    // ---- P(r): slot t0 = row r (pixel packet); wa, wb, wc = window rows r-1, r, r+1 ----
+    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, const WinRow& wa,
                                      const WinRow& wb, const WinRow& wc) {
         const Geo& g = c.g;
         const int lane = g.lane;
-        const int s0 = slot_vec(t0), s1 = slot_vec(t1);
-        float pk[NPP4 * 4], nx[NYD4 * 4];
+        const int s0 = slot_vec(t0);
+        float pk[NPP4 * 4];
 #pragma unroll
         for (int k = 0; k < NPP4; ++k) {
             const Vec4 t = s_ld4(c.ring, s0 + k * 32);
             pk[4 * k] = t.x; pk[4 * k + 1] = t.y; pk[4 * k + 2] = t.z; pk[4 * k + 3] = t.w;
         }
-#pragma unroll
-        for (int k = 0; k < NYD4; ++k) {   // ym[C], D of row r+1
-            const Vec4 t = s_ld4(c.ring, s1 + k * 32);
-            nx[4 * k] = t.x; nx[4 * k + 1] = t.y; nx[4 * k + 2] = t.z; nx[4 * k + 3] = t.w;
-        }
-        const float Da = pk[O_D];
-        const float ey = edge_y(c, r, pk + O_YM, Da, nx + O_YM, nx[O_D]);
         const float wu = (r == 1) ? 2.f : 1.f, wd = (r == g.H - 2) ? 2.f : 1.f;
         const float pyr = (float)(r + 1);
         const int selr = wb.sel;
@@ -836,20 +841,9 @@ struct March {
         // depth -> disparity:  dz/dd = -a z^2
         float gd = c.nega * zr * zr * dbar_z;
         // smoothness gradient (src/utils.jl:159-173 with the mean-normalisation of
-        // src/training.jl:64-65 folded in):  A ghat_j - B
-        {
-            const float Dr = w_dn(Da, lane);
-            float gsum = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) gsum += fabsf(pk[O_YM + ch] - w_dn(pk[O_YM + ch], lane));
-            const float w = f_ex2(gsum * (-1.4426950408889634f / C)) * c.cxn;
-            const float ex = g.has_right ? sgn_scaled(Da - Dr, w) : 0.f;
-            const float exl = w_up(ex, lane);
-            const float gh = (ex - exl) + (ey - acc.ey_prev);
-            gd += fmaf(c.sA, gh, -c.sB);
-        }
+        // src/training.jl:64-65 folded in):  A ghat_j - B   (ghat comes from warp F with the window row)
+        gd += fmaf(c.sA, wb.gh, -c.sB);
         if (g.pcol) g_st(c.gd + (r * g.W + g.gxm), gd);   // (gxm == gxr on the output columns)
-        acc.ey_prev = ey;
     }
 
     // warp B of one work item; gslot: running ring-slot counter of this warp
@@ -899,7 +893,6 @@ struct March {
             for (int k = 0; k < 3; ++k) keep(c.apx[s][k]);
         }
         AccB acc;
-        acc.ey_prev = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             acc.coff[s] = -1;
@@ -916,17 +909,6 @@ struct March {
         acquire(c, ta);                                            // row Y0-1
         Slot tb = next_slot(ta);
         acquire(c, tb);                                            // row Y0
-        {   // the "up" edge of the first row
-            float ya[NYD4 * 4], yb[NYD4 * 4];
-            const int sa = slot_vec(ta), sb = slot_vec(tb);
-#pragma unroll
-            for (int k = 0; k < NYD4; ++k) {
-                const Vec4 va = s_ld4(c.ring, sa + k * 32), vb = s_ld4(c.ring, sb + k * 32);
-                ya[4 * k] = va.x; ya[4 * k + 1] = va.y; ya[4 * k + 2] = va.z; ya[4 * k + 3] = va.w;
-                yb[4 * k] = vb.x; yb[4 * k + 1] = vb.y; yb[4 * k + 2] = vb.z; yb[4 * k + 3] = vb.w;
-            }
-            acc.ey_prev = edge_y(c, g.Y0 - 1, ya + O_YM, ya[O_D], yb + O_YM, yb[O_D]);
-        }
         release(c, ta);
         ta = tb;                                                   // ta = slot of row r, tb = slot of row r+1
         tb = next_slot(tb);
@@ -942,7 +924,7 @@ struct March {
             const Slot tc = next_slot(tb);                                                            \
             acquire(c, tc);                                        /* row r+2: carries window row r+1 */ \
             load_window_row(c, tc, WC);                                                               \
-            stage_pixels(p, c, acc, r, ta, tb, WA, WB, WC);                                           \
+            stage_pixels(p, c, acc, r, ta, WA, WB, WC);                                           \
             release(c, ta);                                                                           \
             ta = tb; tb = tc;                                                                         \
             ++r;                                                                                      \
