@@ -167,6 +167,15 @@ int md2_view_synthesis_loss_bwd(md2_ctx*, const md2_vsl_desc*, float upstream, m
 /* value and gradient in one pass (gradient seeded with `seed`, normally 1) */
 int md2_view_synthesis_loss_fwdbwd(md2_ctx*, const md2_vsl_desc*, float seed, md2_stream);
 
+/* The same, for a caller whose buffers live in HOST memory (pinned for full speed): EVERY pointer of
+ * the descriptor is a host pointer (inputs, K / invK, loss and all gradients; target / source /
+ * grad_source keep their per-image strides).  This is the reference's per-step `x = device(x)` ...
+ * `cpu(loss)` traffic (src/Monodepth.jl:156-176) folded into the call: the batch is cut into `groups`
+ * groups of images whose host-to-device copies, kernels and device-to-host copies are pipelined over
+ * three streams, and the pipeline is replayed as one CUDA graph while the descriptor stays the same.
+ * Synchronous: returns when every output is in host memory.  saved / viz_* must be NULL. */
+int md2_view_synthesis_loss_fwdbwd_host(md2_ctx*, const md2_vsl_desc* host_desc, float seed, int32_t groups);
+
 /* warp: disparity (W,H,1,N) -> S warped images (W,H,C,N); uses the desc fields
  * W,H,N,C,S, source*, disparity[0], K, invK, pose_*, rot, trans, invert, min/max_depth;
  * out[s] contiguous (W,H,C,N). */

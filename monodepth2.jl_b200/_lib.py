@@ -147,6 +147,7 @@ _SIGS = {
     "md2_view_synthesis_loss_fwd": [c_void, C.POINTER(VslDesc), _P],
     "md2_view_synthesis_loss_bwd": [c_void, C.POINTER(VslDesc), _F, _P],
     "md2_view_synthesis_loss_fwdbwd": [c_void, C.POINTER(VslDesc), _F, _P],
+    "md2_view_synthesis_loss_fwdbwd_host": [c_void, C.POINTER(VslDesc), _F, _I32],
     "md2_warp_fwd": [c_void, C.POINTER(VslDesc), C.POINTER(_P), _P],
     "md2_warp_bwd": [c_void, C.POINTER(VslDesc), C.POINTER(_P), _P],
 }

@@ -35,6 +35,7 @@ struct md2_ctx {
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
     size_t prof_used = 0;
+    void* host = nullptr;   // state of the host-buffer entry point (md2_host.cu), created on first use
 };
 
 namespace md2 {

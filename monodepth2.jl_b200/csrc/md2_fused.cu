@@ -11,6 +11,8 @@
 
 namespace md2 {
 
+void host_path_destroy(md2_ctx* ctx);   // md2_host.cu
+
 // ------------------------------------------------------------------------------------------
 // error / ctx plumbing
 // ------------------------------------------------------------------------------------------
@@ -649,7 +651,7 @@ static void fill_pose_io(const md2_vsl_desc* d, PoseIO& io) {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FWDBWD = 2 };
 
-static int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStream_t st) {
+int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStream_t st) {
     if (check_desc(d, true)) return 1;
     MD2_CHECK(cudaSetDevice(ctx->device));
     const int W = d->W, H = d->H, N = d->N, L = d->L, S = d->S, C = d->C;
@@ -962,6 +964,7 @@ int md2_destroy(md2_ctx* ctx) {
     for (int i = 0; i < MD2_WS_COUNT; ++i)
         if (ctx->ws[i].ptr) cudaFree(ctx->ws[i].ptr);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    md2::host_path_destroy(ctx);
     delete ctx;
     return 0;
 }

@@ -1,0 +1,268 @@
+// Host-buffer entry point of the fused view-synthesis loss: md2_view_synthesis_loss_fwdbwd_host.
+//
+// The reference moves every batch to the device with `x = device(x)` and reads the loss back with
+// `cpu(loss)` once per step (src/Monodepth.jl:156-176).  This entry point does the same for a caller
+// whose buffers are in (pinned) host memory, without a per-step serial copy -> compute -> copy chain:
+// the batch is cut into groups of images (the path is independent per image) that
+// are pipelined over three streams -- the host-to-device copies of group k+1 overlap the kernels of
+// group k and the device-to-host copies of group k-1 -- and the whole pipeline (2-D strided copies,
+// three kernels per group, events) is captured once per distinct descriptor into a CUDA graph, so a
+// step is one cudaGraphLaunch + one synchronisation.
+#include <string.h>
+
+#include "md2_common.cuh"
+#include "md2_fused.cuh"
+
+namespace md2 {
+
+int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStream_t st);   // md2_fused.cu
+
+constexpr int HOST_MAX_GROUPS = 16;
+
+struct HostPath {
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_in0 = nullptr, ev_in[HOST_MAX_GROUPS] = {}, ev_done[HOST_MAX_GROUPS] = {},
+                ev_join_in = nullptr, ev_join_run = nullptr;
+    char* dbuf = nullptr;          // device staging of every input and output of one call
+    size_t dbytes = 0;
+    float* hloss = nullptr;        // pinned: one partial loss per group
+    cudaGraphExec_t exec = nullptr;
+    md2_vsl_desc key;              // descriptor the graph was captured for
+    int key_groups = 0;
+    float key_seed = 0.f;
+    bool have_key = false;
+};
+
+static HostPath* host_path(md2_ctx* ctx) {
+    if (!ctx->host) {
+        HostPath* h = new HostPath();
+        bool ok = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaMallocHost(&h->hloss, sizeof(float) * HOST_MAX_GROUPS) == cudaSuccess;
+        cudaEvent_t* evs[] = {&h->ev_fork, &h->ev_in0, &h->ev_join_in, &h->ev_join_run};
+        for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < HOST_MAX_GROUPS; ++k)
+            ok = ok && cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            set_error("host path: stream / event / pinned-memory creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            delete h;
+            return nullptr;
+        }
+        ctx->host = h;
+    }
+    return static_cast<HostPath*>(ctx->host);
+}
+
+void host_path_destroy(md2_ctx* ctx) {
+    HostPath* h = static_cast<HostPath*>(ctx->host);
+    if (!h) return;
+    if (h->exec) cudaGraphExecDestroy(h->exec);
+    if (h->dbuf) cudaFree(h->dbuf);
+    if (h->hloss) cudaFreeHost(h->hloss);
+    cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_run); cudaStreamDestroy(h->s_out);
+    cudaEvent_t evs[] = {h->ev_fork, h->ev_in0, h->ev_join_in, h->ev_join_run};
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    for (int k = 0; k < HOST_MAX_GROUPS; ++k) { cudaEventDestroy(h->ev_in[k]); cudaEventDestroy(h->ev_done[k]); }
+    delete h;
+    ctx->host = nullptr;
+}
+
+// bump allocator over the staging buffer (256-byte aligned pieces)
+struct Carver {
+    char* base; size_t off = 0;
+    float* take(size_t floats) {
+        float* q = base ? reinterpret_cast<float*>(base + off) : nullptr;
+        off += (floats * sizeof(float) + 255) & ~(size_t)255;
+        return q;
+    }
+};
+
+// device mirror of the host descriptor: dense (N,C,H,W) frames, every scale, poses, outputs
+struct Mirror {
+    float *tgt, *src[MAX_S], *disp[MAX_L], *K, *invK, *rot[MAX_S], *trans[MAX_S], *automask;
+    float *loss, *gdisp[MAX_L], *grot[MAX_S], *gtrans[MAX_S], *gsrc[MAX_S];
+};
+
+static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
+    Carver c{base};
+    const size_t img = (size_t)d->C * d->W * d->H, N = d->N;
+    const int pr = d->pose_mode == 0 ? 9 : 3;
+    m.tgt = c.take(N * img);
+    for (int s = 0; s < MAX_S; ++s) {
+        const bool on = s < d->S;
+        m.src[s] = on ? c.take(N * img) : nullptr;
+        m.rot[s] = on ? c.take(N * pr) : nullptr;
+        m.trans[s] = on ? c.take(N * 3) : nullptr;
+        m.grot[s] = on ? c.take(N * pr) : nullptr;
+        m.gtrans[s] = on ? c.take(N * 3) : nullptr;
+        m.gsrc[s] = (on && d->grad_source[s]) ? c.take(N * img) : nullptr;
+    }
+    for (int l = 0; l < MAX_L; ++l) {
+        const bool on = l < d->L;
+        const size_t px = on ? (size_t)d->disp_w[l] * d->disp_h[l] : 0;
+        m.disp[l] = on ? c.take(N * px) : nullptr;
+        m.gdisp[l] = on ? c.take(N * px) : nullptr;
+    }
+    m.K = c.take(9); m.invK = c.take(9);
+    m.automask = d->automask ? c.take(N * (size_t)d->W * d->H) : nullptr;
+    m.loss = c.take(HOST_MAX_GROUPS);
+    return c.off;
+}
+
+#define MD2_H2D(dst, src, bytes) MD2_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, h->s_in))
+#define MD2_D2H(dst, src, bytes) MD2_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, h->s_out))
+
+// enqueue the whole pipeline on the three streams (eagerly, or under stream capture)
+static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirror& m, float seed, int groups) {
+    const int N = d->N, W = d->W, H = d->H, C = d->C, S = d->S, L = d->L;
+    const size_t img = (size_t)C * W * H, imgb = img * sizeof(float);
+    const int pr = d->pose_mode == 0 ? 9 : 3;
+    // fork: the copy streams join the origin stream (s_run)
+    MD2_CHECK(cudaEventRecord(h->ev_fork, h->s_run));
+    MD2_CHECK(cudaStreamWaitEvent(h->s_in, h->ev_fork, 0));
+    MD2_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
+    // once per call: intrinsics, poses, the low-resolution disparities (small)
+    MD2_H2D(m.K, d->K, 9 * sizeof(float));
+    MD2_H2D(m.invK, d->invK, 9 * sizeof(float));
+    for (int s = 0; s < S; ++s) {
+        MD2_H2D(m.rot[s], d->rot[s], sizeof(float) * pr * N);
+        MD2_H2D(m.trans[s], d->trans[s], sizeof(float) * 3 * N);
+    }
+    for (int l = 0; l < L; ++l)
+        if (d->disp_w[l] != W || d->disp_h[l] != H)
+            MD2_H2D(m.disp[l], d->disparity[l], sizeof(float) * (size_t)N * d->disp_w[l] * d->disp_h[l]);
+    MD2_CHECK(cudaEventRecord(h->ev_in0, h->s_in));
+    MD2_CHECK(cudaStreamWaitEvent(h->s_run, h->ev_in0, 0));
+    for (int k = 0; k < groups; ++k) {
+        const int n0 = (int)((long long)N * k / groups), n1 = (int)((long long)N * (k + 1) / groups), nk = n1 - n0;
+        if (nk == 0) { h->hloss[k] = 0.f; continue; }
+        // ---- inputs of group k: frames (strided host views -> dense), full-resolution disparities, automask
+        MD2_CHECK(cudaMemcpy2DAsync(m.tgt + n0 * img, imgb, d->target + (size_t)n0 * d->target_image_stride,
+                                    sizeof(float) * d->target_image_stride, imgb, nk, cudaMemcpyHostToDevice, h->s_in));
+        for (int s = 0; s < S; ++s)
+            MD2_CHECK(cudaMemcpy2DAsync(m.src[s] + n0 * img, imgb, d->source[s] + (size_t)n0 * d->source_image_stride[s],
+                                        sizeof(float) * d->source_image_stride[s], imgb, nk, cudaMemcpyHostToDevice, h->s_in));
+        for (int l = 0; l < L; ++l)
+            if (d->disp_w[l] == W && d->disp_h[l] == H)
+                MD2_H2D(m.disp[l] + (size_t)n0 * W * H, d->disparity[l] + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
+        if (d->automask) MD2_H2D(m.automask + (size_t)n0 * W * H, d->automask + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
+        MD2_CHECK(cudaEventRecord(h->ev_in[k], h->s_in));
+        // ---- kernels of group k: the device descriptor of its images; loss_scale carries the group's share
+        md2_vsl_desc g = *d;
+        g.N = nk;
+        g.target = m.tgt + n0 * img; g.target_image_stride = (int64_t)img;
+        for (int s = 0; s < S; ++s) {
+            g.source[s] = m.src[s] + n0 * img; g.source_image_stride[s] = (int64_t)img;
+            g.rot[s] = m.rot[s] + (size_t)n0 * pr; g.trans[s] = m.trans[s] + (size_t)n0 * 3;
+            g.grad_rot[s] = m.grot[s] + (size_t)n0 * pr; g.grad_trans[s] = m.gtrans[s] + (size_t)n0 * 3;
+            g.grad_source[s] = m.gsrc[s] ? m.gsrc[s] + n0 * img : nullptr;
+            g.viz_warped[s] = nullptr;
+        }
+        for (int l = 0; l < L; ++l) {
+            const size_t px = (size_t)d->disp_w[l] * d->disp_h[l];
+            g.disparity[l] = m.disp[l] + n0 * px; g.grad_disparity[l] = m.gdisp[l] + n0 * px;
+        }
+        g.K = m.K; g.invK = m.invK;
+        g.automask = m.automask ? m.automask + (size_t)n0 * W * H : nullptr;
+        g.loss = m.loss + k; g.viz_loss = nullptr; g.saved = nullptr;
+        g.loss_scale = d->loss_scale * (float)nk / (float)N;   // mean over the whole batch = sum of the group shares
+        g.zero_grad_source = 1;
+        MD2_CHECK(cudaStreamWaitEvent(h->s_run, h->ev_in[k], 0));
+        if (run_vsl(ctx, &g, /*MODE_FWDBWD*/ 2, seed, h->s_run)) return 1;
+        MD2_CHECK(cudaEventRecord(h->ev_done[k], h->s_run));
+        // ---- outputs of group k
+        MD2_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[k], 0));
+        for (int l = 0; l < L; ++l)
+            if (d->disp_w[l] == W && d->disp_h[l] == H)
+                MD2_D2H(d->grad_disparity[l] + (size_t)n0 * W * H, m.gdisp[l] + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
+        for (int s = 0; s < S; ++s)
+            if (m.gsrc[s])
+                MD2_CHECK(cudaMemcpy2DAsync(d->grad_source[s] + (size_t)n0 * d->source_image_stride[s],
+                                            sizeof(float) * d->source_image_stride[s], m.gsrc[s] + n0 * img, imgb, imgb, nk,
+                                            cudaMemcpyDeviceToHost, h->s_out));
+    }
+    // once per call: the small outputs of all groups
+    for (int l = 0; l < L; ++l)
+        if (d->disp_w[l] != W || d->disp_h[l] != H)
+            MD2_D2H(d->grad_disparity[l], m.gdisp[l], sizeof(float) * (size_t)N * d->disp_w[l] * d->disp_h[l]);
+    for (int s = 0; s < S; ++s) {
+        if (d->grad_rot[s]) MD2_D2H(d->grad_rot[s], m.grot[s], sizeof(float) * pr * N);
+        if (d->grad_trans[s]) MD2_D2H(d->grad_trans[s], m.gtrans[s], sizeof(float) * 3 * N);
+    }
+    MD2_D2H(h->hloss, m.loss, sizeof(float) * groups);
+    // join: everything ends on the origin stream
+    MD2_CHECK(cudaEventRecord(h->ev_join_in, h->s_in));
+    MD2_CHECK(cudaEventRecord(h->ev_join_run, h->s_out));
+    MD2_CHECK(cudaStreamWaitEvent(h->s_run, h->ev_join_in, 0));
+    MD2_CHECK(cudaStreamWaitEvent(h->s_run, h->ev_join_run, 0));
+    return 0;
+}
+
+static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups) {
+    MD2_REQUIRE(d != nullptr, "null descriptor");
+    MD2_REQUIRE(d->N >= 1 && d->S >= 1 && d->S <= MAX_S && d->L >= 1 && d->L <= MAX_L, "bad N / S / L");
+    MD2_REQUIRE(d->target && d->K && d->invK && d->loss, "null target / K / invK / loss");
+    MD2_REQUIRE(!d->saved && !d->viz_loss && !d->viz_warped[0] && !d->viz_warped[1], "saved / viz outputs are not supported by the host entry point");
+    for (int s = 0; s < d->S; ++s) MD2_REQUIRE(d->source[s] && d->rot[s] && d->trans[s], "null source / pose");
+    for (int l = 0; l < d->L; ++l) MD2_REQUIRE(d->disparity[l] && d->grad_disparity[l], "null disparity / grad_disparity");
+    if (groups < 1) groups = 1;
+    if (groups > HOST_MAX_GROUPS) groups = HOST_MAX_GROUPS;
+    if (groups > d->N) groups = d->N;
+    MD2_CHECK(cudaSetDevice(ctx->device));
+    MD2_REQUIRE(!ctx->prof_on, "kernel profiling (md2_profile_enable) is not available on the host entry point");
+    HostPath* h = host_path(ctx);
+    if (!h) return 1;
+    Mirror m;
+    const size_t need = carve(d, nullptr, m);
+    if (need > h->dbytes) {
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; h->have_key = false; }
+        if (h->dbuf) { MD2_CHECK(cudaDeviceSynchronize()); cudaFree(h->dbuf); h->dbuf = nullptr; h->dbytes = 0; }
+        MD2_CHECK(cudaMalloc(&h->dbuf, need + need / 4));
+        h->dbytes = need + need / 4;
+    }
+    carve(d, h->dbuf, m);
+    const bool same = h->have_key && h->exec && h->key_groups == groups && h->key_seed == seed && memcmp(&h->key, d, sizeof(*d)) == 0;
+    if (!same) {
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
+        h->have_key = false;
+        // first call for this descriptor: run eagerly (sizes every workspace, validates the arguments) ...
+        if (enqueue(ctx, h, d, m, seed, groups)) return 1;
+        MD2_CHECK(cudaStreamSynchronize(h->s_run));
+        // ... then capture the same pipeline for the calls that follow
+        if (!getenv("MD2_HOST_NO_GRAPH")) {
+            cudaGraph_t graph = nullptr;
+            const int64_t launches = ctx->launches;
+            MD2_CHECK(cudaStreamBeginCapture(h->s_run, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue(ctx, h, d, m, seed, groups);
+            const cudaError_t ce = cudaStreamEndCapture(h->s_run, &graph);
+            ctx->launches = launches;   // nothing ran while capturing
+            if (rc || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (rc) return 1;
+                return set_error("host path: stream capture failed: %s", cudaGetErrorString(ce));
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&h->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { h->exec = nullptr; return set_error("host path: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            h->key = *d; h->key_groups = groups; h->key_seed = seed; h->have_key = true;
+        }
+    } else {
+        MD2_CHECK(cudaGraphLaunch(h->exec, h->s_run));
+        ctx->launches += 3 * groups;
+        MD2_CHECK(cudaStreamSynchronize(h->s_run));
+    }
+    double loss = 0.0;
+    for (int k = 0; k < groups; ++k) loss += (double)h->hloss[k];
+    *d->loss = (float)loss;
+    return 0;
+}
+
+}  // namespace md2
+
+extern "C" int md2_view_synthesis_loss_fwdbwd_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int32_t groups) {
+    MD2_REQUIRE(ctx != nullptr, "null ctx");
+    return md2::run_host(ctx, d, seed, groups);
+}

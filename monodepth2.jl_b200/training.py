@@ -152,6 +152,66 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
     return out
 
 
+class HostViewSynthesisLoss:
+    """Value and gradients of the train_loss tail for a caller whose batch lives in HOST memory -- the
+    reference's per-step `x = device(x)` ... `cpu(loss)` (src/Monodepth.jl:156-176) folded into one call of
+    md2_view_synthesis_loss_fwdbwd_host: image groups are pipelined over copy and compute streams and the
+    pipeline is replayed as a CUDA graph.  The object owns pinned input / output buffers of one shape
+    (`inputs`, `grads`); fill `inputs` in place (or pass tensors to `__call__`, which copies them in) and
+    read `loss` / `grads` after the call.
+
+    x (N,3,C,H,W); disparities (N,1,h_i,w_i) per scale; rvecs / tvecs (N,3) per source; K, invK (3,3)."""
+
+    def __init__(self, N, C_, H, W, disp_sizes, K, invK, *, device=None, target_id=1, source_ids=(0, 2),
+                 scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3,
+                 automask=False, normalize_disparity=True, grad_x=False, groups=2):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ctx = Context.get(dev)
+        self.groups, self.S, self.L = int(groups), len(source_ids), len(disp_sizes)
+        pin = lambda *shape: torch.zeros(*shape, dtype=_F32).pin_memory()
+        self.inputs = dict(x=pin(N, 3, C_, H, W), disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes],
+                           rvecs=[pin(N, 3) for _ in source_ids], tvecs=[pin(N, 3) for _ in source_ids],
+                           automask=pin(N, 1, H, W) if automask else None)
+        self.grads = dict(disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes], rvecs=[pin(N, 3) for _ in source_ids],
+                          tvecs=[pin(N, 3) for _ in source_ids], x=pin(N, 3, C_, H, W) if grad_x else None)
+        self._loss = pin(1)
+        self._K = _cm(_f32c(K.reshape(3, 3).cpu())).pin_memory()
+        self._invK = _cm(_f32c(invK.reshape(3, 3).cpu())).pin_memory()
+        x, gx = self.inputs["x"], self.grads["x"]
+        self.desc = L.make_vsl_desc(
+            target=x[:, target_id], target_stride=x.stride(0), sources=[x[:, i] for i in source_ids],
+            source_strides=[x.stride(0)] * self.S, disparities=self.inputs["disparities"], K_cm=self._K, invK_cm=self._invK,
+            rot=self.inputs["rvecs"], trans=self.inputs["tvecs"], pose_mode=1, invert=[i < target_id for i in source_ids],
+            automask=self.inputs["automask"], min_depth=min_depth, max_depth=max_depth,
+            smooth_weight=[disparity_smoothness * s for s in list(scales)[:self.L]], loss_scale=1.0 / self.L,
+            normalize_disparity=normalize_disparity, loss=self._loss, grad_disparity=self.grads["disparities"],
+            grad_rot=self.grads["rvecs"], grad_trans=self.grads["tvecs"],
+            grad_source=[gx[:, i] for i in source_ids] if grad_x else None, zero_grad_source=True, shape=(N, C_, H, W))
+        self.h2d_bytes = 4 * sum(t.numel() for t in [x] + self.inputs["disparities"] + self.inputs["rvecs"] + self.inputs["tvecs"]
+                                 + ([self.inputs["automask"]] if automask else [])) + 72
+        self.d2h_bytes = 4 + 4 * sum(t.numel() for t in self.grads["disparities"] + self.grads["rvecs"] + self.grads["tvecs"]) \
+            + (8 * N * C_ * H * W if grad_x else 0)
+
+    def __call__(self, x=None, disparities=None, rvecs=None, tvecs=None, automask=None):
+        """copies any given (CPU) tensors into the pinned inputs, runs one step, returns the loss as a float"""
+        if x is not None:
+            self.inputs["x"].copy_(x)
+        for name, vals in (("disparities", disparities), ("rvecs", rvecs), ("tvecs", tvecs)):
+            if vals is not None:
+                for dst, src in zip(self.inputs[name], vals):
+                    dst.copy_(src.reshape(dst.shape))
+        if automask is not None:
+            self.inputs["automask"].copy_(automask.reshape(self.inputs["automask"].shape))
+        lib = self.ctx.lib
+        if lib.md2_view_synthesis_loss_fwdbwd_host(self.ctx.handle, C.byref(self.desc), 1.0, self.groups):
+            raise L.Md2Error(lib.md2_last_error().decode())
+        return float(self._loss[0])
+
+    @property
+    def loss(self):
+        return float(self._loss[0])
+
+
 class _Warp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, disp, x, *poses):

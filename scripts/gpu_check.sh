@@ -12,6 +12,6 @@ timeout 600 python bench.py --steps 2000 --warmup 20 > gpurun_out/${TAG}_bench.j
 cat gpurun_out/${TAG}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 30 -c 2 -o gpurun_out/${TAG}_fused \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 30 -c 1 -o gpurun_out/${TAG}_fused \
   python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out/

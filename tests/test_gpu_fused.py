@@ -202,3 +202,43 @@ def test_error_behaviour():
                               K.to(d), invK.to(d))
     with pytest.raises(M.Md2Error):
         M.SSIM()(torch.rand(1, 1, 4, 4), torch.rand(1, 1, 4, 4))   # CPU tensors: no fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups,automask,grad_x", [(1, False, False), (3, True, True), (4, False, True)])
+def test_host_entry_point_matches_device_path(groups, automask, grad_x):
+    """md2_view_synthesis_loss_fwdbwd_host (host pointers, image groups pipelined over streams, CUDA graph
+    replay) gives the results of the device-pointer call on the same batch; repeated calls (graph replay)
+    and a changed input (same descriptor, new data) stay correct."""
+    N, Cc, H, W = 5, 3, 48, 96
+    x, disps, rv, tv = O.synthetic_batch(N, Cc, H, W, seed=21)
+    K, invK = O.make_K(W, H)
+    dev = torch.device("cuda", 0)
+    auto = None
+    if automask:
+        auto = M.automasking_loss(M.SSIM(), x.to(dev), x.to(dev)[:, 1], (0, 2)).cpu()
+
+    def device_path(xh, dh):
+        xg = xh.to(dev).requires_grad_(grad_x)
+        dg = [d.to(dev).requires_grad_(True) for d in dh]
+        rg = [r.to(dev).requires_grad_(True) for r in rv]
+        tg = [t.to(dev).requires_grad_(True) for t in tv]
+        loss = M.view_synthesis_loss(xg, dg, rg, tg, K.to(dev), invK.to(dev), auto_loss=auto.to(dev) if automask else None)
+        loss.backward()
+        return loss.item(), [d.grad.cpu() for d in dg], [r.grad.cpu() for r in rg], [t.grad.cpu() for t in tg], \
+            (xg.grad.cpu() if grad_x else None)
+
+    hv = M.HostViewSynthesisLoss(N, Cc, H, W, [(d.shape[-1], d.shape[-2]) for d in disps], K, invK, device=dev,
+                                 automask=automask, grad_x=grad_x, groups=groups)
+    for rep in range(3):
+        xh = x if rep < 2 else (x * 0.9 + 0.05)
+        dh = disps if rep < 2 else [d * 0.8 + 0.1 for d in disps]
+        loss = hv(xh, dh, rv, tv, auto)
+        rl, rgd, rgr, rgt, rgx = device_path(xh, dh)
+        assert abs(loss - rl) <= 2e-6 * max(1.0, abs(rl)), (rep, loss, rl)
+        for a, b in zip(hv.grads["disparities"], rgd):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-9), rep
+        for a, b in zip(hv.grads["rvecs"] + hv.grads["tvecs"], rgr + rgt):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-8), rep
+        if grad_x:
+            assert torch.allclose(hv.grads["x"], rgx, rtol=1e-4, atol=1e-7), rep
