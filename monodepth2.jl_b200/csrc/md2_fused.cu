@@ -315,15 +315,20 @@ struct MarchCfg {
 
 template <int C, int S, bool BWD>
 __global__ void __maxnreg__((MarchCfg<C, S, BWD>::MAXREG))
-march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
+march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int q_full, int group) {
     extern __shared__ __align__(16) float wsm[];
     using M = March<C, S, BWD>;
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x & 31;
     const int role = threadIdx.x >> 5;      // 0: warp F (forward), 1: warp B (backward)
-    const int ipg = strips * chunks;
+    // segments = (strip, chunk) of a (scale, image); an item is one full-height chunk, or -- when the image
+    // height is not a multiple of the chunk height -- `group` short last chunks of neighbouring strips, so that
+    // all items are about equally long (no tail of short items, more items than full chunks alone)
+    const int ipg = strips * chunks;                     // segments (= partial-sum rows) per (scale, image)
+    const int n_full = strips * q_full;
+    const int ipi = n_full + (chunks > q_full ? (strips + group - 1) / group : 0);   // items per (scale, image)
     const int LN = p.L * p.N;
-    const int items = ipg * LN;
+    const int items = ipi * LN;
     int gslot = 0;
     if (BWD) {
         if (threadIdx.x == 0) {
@@ -334,19 +339,22 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks) {
     }
     // one warp pair per block, item index from blockIdx only, so that everything derived from it is
     // warp-uniform for the compiler (uniform registers / constant-bank operands); the grid is
-    // exactly the number of blocks resident on the whole GPU
+    // at most the number of blocks resident on the whole GPU
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int z = it / ipg, rem = it - z * ipg;
-        const int cy = rem / strips, sx = rem - cy * strips;
-        {
+        const int z = it / ipi, rem = it - z * ipi;
+        int cy, sx, sx_end;
+        if (rem < n_full) { cy = rem / strips; sx = rem - cy * strips; sx_end = sx + 1; }
+        else { cy = q_full; sx = (rem - n_full) * group; sx_end = min(sx + group, strips); }
+        for (; sx < sx_end; ++sx) {
             float v[32];
             if (role == 0) M::run_forward(p, sx, cy, z, lane, wsm, gslot, v);
             else M::run_backward(p, sx, cy, z, lane, wsm, gslot, v);
             const float tot = warp_reduce_32(v);
             // warp F owns the loss sums [0, NSTAT), warp B the pose sums [NSTAT, NP)
-            if (role == 0 ? lane < (BWD ? NSTAT : NP) : (lane >= NSTAT && lane < NP)) p.partial[(long long)it * NP + lane] = tot;
+            if (role == 0 ? lane < (BWD ? NSTAT : NP) : (lane >= NSTAT && lane < NP))
+                p.partial[((long long)z * ipg + cy * strips + sx) * NP + lane] = tot;
+            if (BWD) __syncthreads();   // both warps are done with the ring before the next segment reuses it
         }
-        if (BWD) __syncthreads();   // both warps are done with the ring before the next item reuses it
     }
 }
 
@@ -562,11 +570,12 @@ template <int C, int S, bool BWD>
 static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     using M = March<C, S, BWD>;
     const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
-    const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R);
-    const long long items = (long long)strips * chunks * p.L * p.N;
+    const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R), q_full = p.H / p.m_R;
+    const int group = p.m_group > 0 ? p.m_group : 1;
+    const long long items = ((long long)strips * q_full + (chunks > q_full ? cdiv(strips, group) : 0)) * p.L * p.N;
     const long long cap = (long long)ctx->sm_count * march_resident<C, S, BWD>();
     const int blocks = (int)(items < cap ? items : cap);
-    march_kernel<C, S, BWD><<<blocks, M::THREADS, smem, st>>>(p, strips, chunks);
+    march_kernel<C, S, BWD><<<blocks, M::THREADS, smem, st>>>(p, strips, chunks, q_full, group);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -592,23 +601,37 @@ static int dispatch_march(md2_ctx* ctx, int C, int S, const FusedParams& p, cuda
 // rows per chunk of the marching kernel.  Long chunks amortise the 2*HALO warm-up rows; the item
 // count should fill the resident warps of all SMs evenly (one block per SM, `warps` warps each):
 // time ~ max(throughput term, longest per-warp chain), both in row-iterations.
-static int choose_march_rows(int W, int H, int LN, bool bwd, int sms, int warps) {
+static int choose_march_rows(int W, int H, int LN, bool bwd, int sms, int warps, int& group) {
     static const int env = [] { const char* e = getenv("MD2_MARCH_ROWS"); return e ? atoi(e) : 0; }();
-    if (env > 0) return env < H ? env : H;
+    static const int env_group = [] { const char* e = getenv("MD2_MARCH_GROUP"); return e ? atoi(e) : -1; }();
     const int ow = bwd ? 28 : 30, halo = bwd ? 2 : 1;
-    const long long base = (long long)cdiv(W, ow) * LN;
+    const int strips = cdiv(W, ow);
+    const long long base = (long long)strips * LN;
+    const double over = 2 * halo + 1.5;                      // warm-up rows + set-up of a segment, in row-iterations
     int best_R = H;
     double best = 1e30;
-    for (int chunks = 1; chunks <= H; ++chunks) {
-        const int R = cdiv(H, chunks);
-        if (R < 8 && chunks > 1) break;
-        if (cdiv(H, R) != chunks) continue;
-        const long long per_sm = (base * chunks + sms - 1) / sms;
-        const double rows = R + 2 * halo + 1.5;
-        const double thr = (double)per_sm * rows / warps;
-        const double chain = (double)((per_sm + warps - 1) / warps) * rows;
+    group = 1;
+    for (int R = H; R >= 8 || R == H; --R) {
+        if (env > 0 && R != (env < H ? env : H)) continue;
+        const int q = H / R, rem = H % R;
+        // short last chunks are grouped so that a group is about as long as a full chunk
+        int k = 1;
+        if (rem) {
+            if (rem < 8 && env <= 0) continue;
+            k = (int)((R + over) / (rem + over));
+            if (k < 1) k = 1;
+            if (k > strips) k = strips;
+            if (env_group >= 1) k = env_group;
+        }
+        const long long items = base * q + (rem ? (long long)LN * cdiv(strips, k) : 0);
+        const double longest = rem ? fmax(R + over, k * (rem + over)) : R + over;
+        const double total = (double)base * q * (R + over) + (rem ? (double)base * (rem + over) : 0.0);
+        const long long per_sm = (items + sms - 1) / sms;
+        const double thr = total / ((double)sms * warps);
+        const double chain = (double)((per_sm + warps - 1) / warps) * longest;
         const double cost = thr > chain ? thr : chain;
-        if (cost < best - 1e-9) { best = cost; best_R = R; }
+        if (cost < best - 1e-9) { best = cost; best_R = R; group = k; }
+        if (R == 8) break;
     }
     return best_R;
 }
@@ -708,7 +731,8 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     p.mode = mode;
     fill_pose_io(d, p.pose);
 
-    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, march_resident_of(C, S, bwd));
+    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, march_resident_of(C, S, bwd), p.m_group);
+    if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] chunk height %d, group %d\n", p.m_R, p.m_group);
     const int tiles = cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
     const int NP = NSTAT + 12 * S;
     // this call's pose rows in the constant-memory table: a slot per ctx (re-entrant across ctxs)
