@@ -306,11 +306,13 @@ template <int C, int S, bool BWD>
 struct MarchCfg {
     // register budget per thread; registers are allocated per warp in units of 512, so the useful
     // tiers are 96 (20 resident warps per SM), 112 (18), 128 (16), 144 (14), 160 (12), 192 (10)
-#ifdef MD2_MAXREG_C1   // tuning experiments
-    static constexpr int MAXREG = C == 1 ? MD2_MAXREG_C1 : 192;
-#else
-    static constexpr int MAXREG = C == 1 ? 128 : 192;
+#ifndef MD2_MAXREG_C1   // (overridable for tuning experiments)
+#define MD2_MAXREG_C1 128
 #endif
+#ifndef MD2_MAXREG_C3
+#define MD2_MAXREG_C3 192
+#endif
+    static constexpr int MAXREG = C == 1 ? MD2_MAXREG_C1 : MD2_MAXREG_C3;
 };
 
 template <int C, int S, bool BWD>

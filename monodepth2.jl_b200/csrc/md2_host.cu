@@ -25,7 +25,8 @@ struct HostPath {
                 ev_join_in = nullptr, ev_join_run = nullptr;
     char* dbuf = nullptr;          // device staging of every input and output of one call
     size_t dbytes = 0;
-    float* hloss = nullptr;        // pinned: one partial loss per group
+    float* hsmall = nullptr;       // pinned staging of the small inputs (K, invK, poses) and outputs (pose gradients, partial losses)
+    size_t hsmall_floats = 0;
     cudaGraphExec_t exec = nullptr;
     md2_vsl_desc key;              // descriptor the graph was captured for
     int key_groups = 0;
@@ -39,7 +40,7 @@ static HostPath* host_path(md2_ctx* ctx) {
         bool ok = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaMallocHost(&h->hloss, sizeof(float) * HOST_MAX_GROUPS) == cudaSuccess;
+                  true;
         cudaEvent_t* evs[] = {&h->ev_fork, &h->ev_in0, &h->ev_join_in, &h->ev_join_run};
         for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
         for (int k = 0; k < HOST_MAX_GROUPS; ++k)
@@ -60,7 +61,7 @@ void host_path_destroy(md2_ctx* ctx) {
     if (!h) return;
     if (h->exec) cudaGraphExecDestroy(h->exec);
     if (h->dbuf) cudaFree(h->dbuf);
-    if (h->hloss) cudaFreeHost(h->hloss);
+    if (h->hsmall) cudaFreeHost(h->hsmall);
     cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_run); cudaStreamDestroy(h->s_out);
     cudaEvent_t evs[] = {h->ev_fork, h->ev_in0, h->ev_join_in, h->ev_join_run};
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
@@ -79,25 +80,55 @@ struct Carver {
     }
 };
 
-// device mirror of the host descriptor: dense (N,C,H,W) frames, every scale, poses, outputs
+// device mirror of the host descriptor: frames, every scale, poses, outputs.  The small inputs (K, invK, poses) and
+// the small outputs (pose gradients, one partial loss per group) are contiguous blocks that travel in one copy each
+// through a pinned staging buffer; frames that are adjacent in host memory (the frames of one 5-D `x`) travel as
+// one contiguous copy per image group and are addressed with strides on the device, like on the host.
 struct Mirror {
     float *tgt, *src[MAX_S], *disp[MAX_L], *K, *invK, *rot[MAX_S], *trans[MAX_S], *automask;
     float *loss, *gdisp[MAX_L], *grot[MAX_S], *gtrans[MAX_S], *gsrc[MAX_S];
+    float *small_in, *small_out;
+    size_t small_in_floats, small_out_floats;
+    bool xcontig;                  // frames travel as whole images of `xstride` floats starting at host pointer xbase
+    const float* xbase; float* xall; int64_t xstride;
 };
 
 static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
     Carver c{base};
     const size_t img = (size_t)d->C * d->W * d->H, N = d->N;
     const int pr = d->pose_mode == 0 ? 9 : 3;
-    m.tgt = c.take(N * img);
-    for (int s = 0; s < MAX_S; ++s) {
-        const bool on = s < d->S;
-        m.src[s] = on ? c.take(N * img) : nullptr;
-        m.rot[s] = on ? c.take(N * pr) : nullptr;
-        m.trans[s] = on ? c.take(N * 3) : nullptr;
-        m.grot[s] = on ? c.take(N * pr) : nullptr;
-        m.gtrans[s] = on ? c.take(N * 3) : nullptr;
-        m.gsrc[s] = (on && d->grad_source[s]) ? c.take(N * img) : nullptr;
+    // frames: contiguous mode if target and sources are distinct frames of one block per image
+    {
+        const float* lo = d->target;
+        const float* hi = d->target;
+        bool same = true;
+        for (int s = 0; s < d->S; ++s) {
+            if (d->source[s] < lo) lo = d->source[s];
+            if (d->source[s] > hi) hi = d->source[s];
+            same = same && d->source_image_stride[s] == d->target_image_stride;
+        }
+        const int64_t st = d->target_image_stride;
+        m.xcontig = same && st >= (int64_t)img && (hi - lo) + (int64_t)img <= st && st <= 4 * (int64_t)img * (d->S + 1);
+        m.xbase = lo; m.xstride = st;
+    }
+    if (m.xcontig) {
+        m.xall = c.take(N * (size_t)m.xstride);
+        m.tgt = m.xall ? m.xall + (d->target - m.xbase) : nullptr;
+        for (int s = 0; s < MAX_S; ++s) m.src[s] = (s < d->S && m.xall) ? m.xall + (d->source[s] - m.xbase) : nullptr;
+    } else {
+        m.xall = nullptr;
+        m.tgt = c.take(N * img);
+        for (int s = 0; s < MAX_S; ++s) m.src[s] = s < d->S ? c.take(N * img) : nullptr;
+    }
+    {   // grad_source mirrors use the device stride of the source frames (the kernels address both with one stride)
+        bool any = false;
+        for (int s = 0; s < d->S; ++s) any = any || d->grad_source[s] != nullptr;
+        float* gall = (m.xcontig && any) ? c.take(N * (size_t)m.xstride) : nullptr;
+        for (int s = 0; s < MAX_S; ++s) {
+            const bool on = s < d->S && d->grad_source[s];
+            if (m.xcontig) m.gsrc[s] = (on && gall) ? gall + (d->source[s] - m.xbase) : nullptr;   // (null in the sizing pass)
+            else m.gsrc[s] = on ? c.take(N * img) : nullptr;
+        }
     }
     for (int l = 0; l < MAX_L; ++l) {
         const bool on = l < d->L;
@@ -105,11 +136,42 @@ static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
         m.disp[l] = on ? c.take(N * px) : nullptr;
         m.gdisp[l] = on ? c.take(N * px) : nullptr;
     }
-    m.K = c.take(9); m.invK = c.take(9);
     m.automask = d->automask ? c.take(N * (size_t)d->W * d->H) : nullptr;
-    m.loss = c.take(HOST_MAX_GROUPS);
+    // small inputs: K, invK, then per source rot, trans
+    m.small_in_floats = 18 + (size_t)d->S * (pr + 3) * N;
+    m.small_in = c.take(m.small_in_floats);
+    m.K = m.small_in; m.invK = m.small_in ? m.small_in + 9 : nullptr;
+    // small outputs: per source grot, gtrans, then the partial losses
+    m.small_out_floats = (size_t)d->S * (pr + 3) * N + HOST_MAX_GROUPS;
+    m.small_out = c.take(m.small_out_floats);
+    for (int s = 0; s < MAX_S; ++s) {
+        const bool on = s < d->S && m.small_in;
+        m.rot[s] = on ? m.small_in + 18 + (size_t)s * (pr + 3) * N : nullptr;
+        m.trans[s] = on ? m.rot[s] + (size_t)pr * N : nullptr;
+        m.grot[s] = on ? m.small_out + (size_t)s * (pr + 3) * N : nullptr;
+        m.gtrans[s] = on ? m.grot[s] + (size_t)pr * N : nullptr;
+    }
+    m.loss = m.small_out ? m.small_out + (size_t)d->S * (pr + 3) * N : nullptr;
     return c.off;
 }
+
+// MD2_HOST_TRACE=1 (eager mode only): time stamps of the pipeline stages, printed to stderr
+struct Trace {
+    bool on = false;
+    cudaEvent_t ev[128]; const char* what[128]; int idx[128]; int n = 0;
+    void mark(cudaStream_t s, const char* w, int k) {
+        if (!on || n >= 128) return;
+        cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], s); what[n] = w; idx[n] = k; ++n;
+    }
+    void dump() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (int i = 1; i < n; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[0], ev[i]); fprintf(stderr, "[md2 host trace] %-10s %2d  %8.1f us\n", what[i], idx[i], ms * 1e3f); }
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        n = 0;
+    }
+};
+static Trace g_trace;
 
 #define MD2_H2D(dst, src, bytes) MD2_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, h->s_in))
 #define MD2_D2H(dst, src, bytes) MD2_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, h->s_out))
@@ -120,44 +182,46 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
     const size_t img = (size_t)C * W * H, imgb = img * sizeof(float);
     const int pr = d->pose_mode == 0 ? 9 : 3;
     // fork: the copy streams join the origin stream (s_run)
+    g_trace.mark(h->s_run, "start", 0);
     MD2_CHECK(cudaEventRecord(h->ev_fork, h->s_run));
     MD2_CHECK(cudaStreamWaitEvent(h->s_in, h->ev_fork, 0));
     MD2_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
-    // once per call: intrinsics, poses, the low-resolution disparities (small)
-    MD2_H2D(m.K, d->K, 9 * sizeof(float));
-    MD2_H2D(m.invK, d->invK, 9 * sizeof(float));
-    for (int s = 0; s < S; ++s) {
-        MD2_H2D(m.rot[s], d->rot[s], sizeof(float) * pr * N);
-        MD2_H2D(m.trans[s], d->trans[s], sizeof(float) * 3 * N);
-    }
+    // once per call: intrinsics and poses (one block, staged by run_host), the low-resolution disparities (small)
+    MD2_H2D(m.small_in, h->hsmall, sizeof(float) * m.small_in_floats);
     for (int l = 0; l < L; ++l)
         if (d->disp_w[l] != W || d->disp_h[l] != H)
             MD2_H2D(m.disp[l], d->disparity[l], sizeof(float) * (size_t)N * d->disp_w[l] * d->disp_h[l]);
+    g_trace.mark(h->s_in, "in-small", 0);
     MD2_CHECK(cudaEventRecord(h->ev_in0, h->s_in));
     MD2_CHECK(cudaStreamWaitEvent(h->s_run, h->ev_in0, 0));
     for (int k = 0; k < groups; ++k) {
         const int n0 = (int)((long long)N * k / groups), n1 = (int)((long long)N * (k + 1) / groups), nk = n1 - n0;
-        if (nk == 0) { h->hloss[k] = 0.f; continue; }
         // ---- inputs of group k: frames (strided host views -> dense), full-resolution disparities, automask
-        MD2_CHECK(cudaMemcpy2DAsync(m.tgt + n0 * img, imgb, d->target + (size_t)n0 * d->target_image_stride,
-                                    sizeof(float) * d->target_image_stride, imgb, nk, cudaMemcpyHostToDevice, h->s_in));
-        for (int s = 0; s < S; ++s)
-            MD2_CHECK(cudaMemcpy2DAsync(m.src[s] + n0 * img, imgb, d->source[s] + (size_t)n0 * d->source_image_stride[s],
-                                        sizeof(float) * d->source_image_stride[s], imgb, nk, cudaMemcpyHostToDevice, h->s_in));
+        if (m.xcontig) {
+            MD2_H2D(m.xall + (size_t)n0 * m.xstride, m.xbase + (size_t)n0 * m.xstride, sizeof(float) * (size_t)nk * m.xstride);
+        } else {
+            MD2_CHECK(cudaMemcpy2DAsync(m.tgt + n0 * img, imgb, d->target + (size_t)n0 * d->target_image_stride,
+                                        sizeof(float) * d->target_image_stride, imgb, nk, cudaMemcpyHostToDevice, h->s_in));
+            for (int s = 0; s < S; ++s)
+                MD2_CHECK(cudaMemcpy2DAsync(m.src[s] + n0 * img, imgb, d->source[s] + (size_t)n0 * d->source_image_stride[s],
+                                            sizeof(float) * d->source_image_stride[s], imgb, nk, cudaMemcpyHostToDevice, h->s_in));
+        }
         for (int l = 0; l < L; ++l)
             if (d->disp_w[l] == W && d->disp_h[l] == H)
                 MD2_H2D(m.disp[l] + (size_t)n0 * W * H, d->disparity[l] + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
         if (d->automask) MD2_H2D(m.automask + (size_t)n0 * W * H, d->automask + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
+        g_trace.mark(h->s_in, "in", k);
         MD2_CHECK(cudaEventRecord(h->ev_in[k], h->s_in));
         // ---- kernels of group k: the device descriptor of its images; loss_scale carries the group's share
         md2_vsl_desc g = *d;
         g.N = nk;
-        g.target = m.tgt + n0 * img; g.target_image_stride = (int64_t)img;
+        const int64_t fst = m.xcontig ? m.xstride : (int64_t)img;   // per-image stride of the frames on the device
+        g.target = m.tgt + n0 * fst; g.target_image_stride = fst;
         for (int s = 0; s < S; ++s) {
-            g.source[s] = m.src[s] + n0 * img; g.source_image_stride[s] = (int64_t)img;
+            g.source[s] = m.src[s] + n0 * fst; g.source_image_stride[s] = fst;
             g.rot[s] = m.rot[s] + (size_t)n0 * pr; g.trans[s] = m.trans[s] + (size_t)n0 * 3;
             g.grad_rot[s] = m.grot[s] + (size_t)n0 * pr; g.grad_trans[s] = m.gtrans[s] + (size_t)n0 * 3;
-            g.grad_source[s] = m.gsrc[s] ? m.gsrc[s] + n0 * img : nullptr;
+            g.grad_source[s] = m.gsrc[s] ? m.gsrc[s] + n0 * fst : nullptr;
             g.viz_warped[s] = nullptr;
         }
         for (int l = 0; l < L; ++l) {
@@ -170,7 +234,9 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
         g.loss_scale = d->loss_scale * (float)nk / (float)N;   // mean over the whole batch = sum of the group shares
         g.zero_grad_source = 1;
         MD2_CHECK(cudaStreamWaitEvent(h->s_run, h->ev_in[k], 0));
+        g_trace.mark(h->s_run, "run-begin", k);
         if (run_vsl(ctx, &g, /*MODE_FWDBWD*/ 2, seed, h->s_run)) return 1;
+        g_trace.mark(h->s_run, "run-end", k);
         MD2_CHECK(cudaEventRecord(h->ev_done[k], h->s_run));
         // ---- outputs of group k
         MD2_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[k], 0));
@@ -180,18 +246,16 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
         for (int s = 0; s < S; ++s)
             if (m.gsrc[s])
                 MD2_CHECK(cudaMemcpy2DAsync(d->grad_source[s] + (size_t)n0 * d->source_image_stride[s],
-                                            sizeof(float) * d->source_image_stride[s], m.gsrc[s] + n0 * img, imgb, imgb, nk,
+                                            sizeof(float) * d->source_image_stride[s], m.gsrc[s] + n0 * fst, sizeof(float) * fst, imgb, nk,
                                             cudaMemcpyDeviceToHost, h->s_out));
+        g_trace.mark(h->s_out, "out", k);
     }
     // once per call: the small outputs of all groups
     for (int l = 0; l < L; ++l)
         if (d->disp_w[l] != W || d->disp_h[l] != H)
             MD2_D2H(d->grad_disparity[l], m.gdisp[l], sizeof(float) * (size_t)N * d->disp_w[l] * d->disp_h[l]);
-    for (int s = 0; s < S; ++s) {
-        if (d->grad_rot[s]) MD2_D2H(d->grad_rot[s], m.grot[s], sizeof(float) * pr * N);
-        if (d->grad_trans[s]) MD2_D2H(d->grad_trans[s], m.gtrans[s], sizeof(float) * 3 * N);
-    }
-    MD2_D2H(h->hloss, m.loss, sizeof(float) * groups);
+    MD2_D2H(h->hsmall + m.small_in_floats, m.small_out, sizeof(float) * m.small_out_floats);   // pose gradients + partial losses
+    g_trace.mark(h->s_out, "out-small", 0);
     // join: everything ends on the origin stream
     MD2_CHECK(cudaEventRecord(h->ev_join_in, h->s_in));
     MD2_CHECK(cudaEventRecord(h->ev_join_run, h->s_out));
@@ -223,13 +287,32 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
         h->dbytes = need + need / 4;
     }
     carve(d, h->dbuf, m);
+    const int pr = d->pose_mode == 0 ? 9 : 3;
+    if (m.small_in_floats + m.small_out_floats > h->hsmall_floats) {
+        if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; h->have_key = false; }
+        if (h->hsmall) { MD2_CHECK(cudaDeviceSynchronize()); cudaFreeHost(h->hsmall); h->hsmall = nullptr; }
+        h->hsmall_floats = 2 * (m.small_in_floats + m.small_out_floats);
+        MD2_CHECK(cudaMallocHost(&h->hsmall, sizeof(float) * h->hsmall_floats));
+    }
+    {   // stage the small inputs: K, invK, per source rot, trans
+        float* q = h->hsmall;
+        memcpy(q, d->K, 9 * sizeof(float)); memcpy(q + 9, d->invK, 9 * sizeof(float));
+        q += 18;
+        for (int s = 0; s < d->S; ++s) {
+            memcpy(q, d->rot[s], sizeof(float) * pr * d->N); q += (size_t)pr * d->N;
+            memcpy(q, d->trans[s], sizeof(float) * 3 * d->N); q += (size_t)3 * d->N;
+        }
+    }
     const bool same = h->have_key && h->exec && h->key_groups == groups && h->key_seed == seed && memcmp(&h->key, d, sizeof(*d)) == 0;
     if (!same) {
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
         h->have_key = false;
         // first call for this descriptor: run eagerly (sizes every workspace, validates the arguments) ...
+        g_trace.on = getenv("MD2_HOST_TRACE") != nullptr;
         if (enqueue(ctx, h, d, m, seed, groups)) return 1;
         MD2_CHECK(cudaStreamSynchronize(h->s_run));
+        g_trace.dump();
+        g_trace.on = false;
         // ... then capture the same pipeline for the calls that follow
         if (!getenv("MD2_HOST_NO_GRAPH")) {
             cudaGraph_t graph = nullptr;
@@ -254,9 +337,18 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
         ctx->launches += 3 * groups;
         MD2_CHECK(cudaStreamSynchronize(h->s_run));
     }
-    double loss = 0.0;
-    for (int k = 0; k < groups; ++k) loss += (double)h->hloss[k];
-    *d->loss = (float)loss;
+    {   // un-stage the small outputs: per source grad_rot, grad_trans, then the partial losses
+        const float* q = h->hsmall + m.small_in_floats;
+        for (int s = 0; s < d->S; ++s) {
+            if (d->grad_rot[s]) memcpy(d->grad_rot[s], q, sizeof(float) * pr * d->N);
+            q += (size_t)pr * d->N;
+            if (d->grad_trans[s]) memcpy(d->grad_trans[s], q, sizeof(float) * 3 * d->N);
+            q += (size_t)3 * d->N;
+        }
+        double loss = 0.0;
+        for (int k = 0; k < groups; ++k) loss += (double)q[k];
+        *d->loss = (float)loss;
+    }
     return 0;
 }
 

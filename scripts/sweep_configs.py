@@ -83,6 +83,8 @@ def main():
              (640, 192, 12, 3, 1), (640, 192, 12, 1, 0), (1024, 320, 4, 3, 0), (1024, 320, 4, 3, 1), (1024, 320, 16, 3, 1)]
     if quick:
         cases = cases[:3]
+    if "--c3" in sys.argv:
+        cases = [(416, 128, 8, 3, 0), (640, 192, 12, 3, 1), (1024, 320, 4, 3, 1)]
     for c in cases:
         print(json.dumps(run_case(*c)), flush=True)
 
