@@ -330,7 +330,7 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
             const cudaError_t ie = cudaGraphInstantiate(&h->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ie != cudaSuccess) { h->exec = nullptr; return set_error("host path: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
-            h->key = *d; h->key_groups = groups; h->key_seed = seed; h->have_key = true;
+            memcpy(&h->key, d, sizeof(*d)); h->key_groups = groups; h->key_seed = seed; h->have_key = true;   // (byte copy: the reuse test is a memcmp)
         }
     } else {
         MD2_CHECK(cudaGraphLaunch(h->exec, h->s_run));
