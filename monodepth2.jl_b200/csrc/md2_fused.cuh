@@ -52,7 +52,7 @@ struct FusedParams {
     // marching-warp kernel (md2_march.cuh): rows per chunk, offset of this call's pose rows in the
     // constant-memory pose table, and every scale's disparity / gradient at FULL resolution (the
     // caller's buffer for a native-size scale, ctx scratch for a low-res decoder scale)
-    int m_R, m_group, pose_slot;   // m_group: short last chunks of this many neighbouring strips form one work item
+    int m_R, m_group, pose_slot;   // m_group: the short last chunks of a (scale, image) are cut into this many work items
     const float* dfull[MAX_L];
     float* gfull[MAX_L];
     // fused fwd+bwd call: per-block partial sums (Sx, Sy, sum d, -) of the prep kernel, (L, N, prep_nblk, 4);
