@@ -67,6 +67,7 @@ inline float f_ex2(float x) { return exp2f(x); }
 inline int f_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline float i_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 template <class T> inline void keep(T&) {}
+#define MD2_RARE_BLOCK() ((void)0)
 inline float g_ld(const float* q) { return *q; }
 inline float g_ld1(const float* q) { return q[1]; }
 inline void g_st(float* q, float v) { *q = v; }
@@ -141,6 +142,9 @@ MD2_DEV void keep(float& v) { asm volatile("" : "+f"(v)); }
 MD2_DEV void keep(int& v) { asm volatile("" : "+r"(v)); }
 MD2_DEV void keep(unsigned int& v) { asm volatile("" : "+r"(v)); }
 template <class T> MD2_DEV void keep(T*& v) { asm volatile("" : "+l"(v)); }
+// first statement of a warp-uniform, rarely taken block: keeps the compiler from if-converting it into predicated
+// instructions that are issued on every row (a uniform branch costs two)
+#define MD2_RARE_BLOCK() asm volatile("")
 // global-memory accesses with an explicit state space (pointers pinned by keep() have lost their
 // provenance, so plain dereferences would become generic LD / ATOM with address-space checks)
 MD2_DEV float g_ld(const float* q) { float v; asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(q)); return v; }
@@ -291,13 +295,18 @@ struct March {
         float fx[S], fy[S];          // their bilinear fractions
         float Tc[C], d;              // centred target values / disparity of row i
         float Tn[C], dn;             // raw target values / disparity of row i+1 (loads issued by A(i))
+        int gy;                      // image row of the row whose raw loads are in Tn / dn
     };
 
     // image row read for march row i (reflect-pad(1) above and below the image, clamped beyond)
     static MD2_DEV int image_row(int i, int H) {
-        int gym = i == -1 ? 1 : (i == H ? H - 2 : i);
-        gym = gym < 0 ? 0 : (gym > H - 1 ? H - 1 : gym);
-        return gym;
+        // reflect about row 0 and row H-1 (-1 -> 1, H -> H-2; rows further out are never used by a window of the image),
+        // then clamp (tiny images)
+        const int a = i < 0 ? -i : i;
+        const int r = 2 * (H - 1) - a;
+        int gym = a < r ? a : r;
+        gym = gym < 0 ? 0 : gym;
+        return gym < H - 1 ? gym : H - 1;
     }
 
     static MD2_DEV int slot_vec(Slot t) { return t.idx * (SLOT4 * 32); }   // Vec4 index of a slot's first packet
@@ -306,14 +315,15 @@ struct March {
     // row i and the disparity / target loads of row i+1; BWD: pre-fills the early part of slot `t` ----
     static MD2_DEV void stage_issue(const FusedParams& p, const CtxF& c, PipeF& f, int i, Slot t) {
         const Geo& g = c.g;
-        const int gym = image_row(i, g.H);
+        const int gym = f.gy;
         const float py = (float)(gym + 1);
         const float d = f.dn;
         f.d = d;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) f.Tc[ch] = f.Tn[ch] - c.rc[ch];
         {   // next row
-            const int toff = image_row(i + 1, g.H) * g.W;
+            f.gy = image_row(i + 1, g.H);
+            const int toff = f.gy * g.W;
             f.dn = g_ld(c.dp + toff);
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) f.Tn[ch] = g_ld(c.tg + (ch * g.HW + toff));
@@ -495,18 +505,20 @@ struct March {
         }
         float wlv = pe_best;
         if (c.am) {
+            MD2_RARE_BLOCK();
             const int qc = q < 0 ? 0 : (q > g.H - 1 ? g.H - 1 : q);
             const float am = g_ld(c.am + (qc * g.W + g.gxm));
             if (am <= wlv) { wlv = am; sel = -1; }   // mask is first in the cat: wins ties
         }
         const bool own = row_own && g.pcol;
         acc.warp_sum += own ? wlv : 0.f;
-        if (c.do_viz && own) {
+        if (c.do_viz) {
+            MD2_RARE_BLOCK();
             const long long o = (long long)g.n * g.HW + q * g.W + g.gxm;   // (gxm == gxr on the output columns)
-            if (p.viz_loss) p.viz_loss[o] = wlv;
+            if (p.viz_loss && own) p.viz_loss[o] = wlv;
 #pragma unroll
             for (int s = 0; s < S; ++s)
-                if (p.viz_warped[s]) {
+                if (p.viz_warped[s] && own) {
 #pragma unroll
                     for (int ch = 0; ch < C; ++ch)
                         p.viz_warped[s][((long long)g.n * C + ch) * g.HW + q * g.W + g.gxm] = b.xm[s][ch] + c.rc[ch];
@@ -640,7 +652,8 @@ struct March {
         // the loop is unrolled by 3 so that the three row registers rotate roles without moves
         const int i0 = g.Y0 - HALO, iend = g.Y1 + HALO;
         {   // prime the pipeline: loads of row i0, then A(i0)
-            const int toff = image_row(i0, g.H) * g.W;
+            f.gy = image_row(i0, g.H);
+            const int toff = f.gy * g.W;
             f.dn = g_ld(c.dp + toff);
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) f.Tn[ch] = g_ld(c.tg + (ch * g.HW + toff));
