@@ -46,7 +46,9 @@ def test_strict_on_well_conditioned_inputs(N, C, H, W, am):
 
 
 @pytest.mark.parametrize("N,C,H,W,am", [(2, 1, 32, 64, False), (1, 3, 48, 80, True), (2, 3, 40, 100, True),
-                                        (3, 1, 64, 200, True), (2, 3, 128, 416, False)])
+                                        (3, 1, 64, 200, True), (2, 3, 128, 416, False),
+                                        # odd sizes: grouped short last chunks, ragged strips, more items than resident blocks
+                                        (5, 1, 100, 150, True), (1, 1, 16, 33, False), (24, 1, 60, 120, False), (3, 3, 77, 61, True)])
 def test_statistical_on_arbitrary_inputs(N, C, H, W, am):
     x, disps, rv, tv = O.synthetic_batch(N, C, H, W, seed=3)
     K, invK = O.make_K(W, H)
