@@ -306,6 +306,41 @@ function vsl_fwdbwd(x::CuF, disparities, rvecs, tvecs, K::CuF, invK::CuF; target
     loss, (gd, gr, gt), vw, vl
 end
 
+"""
+    vsl_fwdbwd_host!(loss, grads, x, disparities, rvecs, tvecs, K, invK; groups = 2, kw...)
+
+The same for a batch that lives in (pinned) HOST memory -- `Array{Float32}`s registered with `CUDA.Mem.pin` --: the
+reference's per-step `x = device(x)` ... `cpu(loss)` (src/Monodepth.jl:156-176) folded into one synchronous call of
+`md2_view_synthesis_loss_fwdbwd_host`, which pipelines image groups over copy / compute streams and replays the
+pipeline as a CUDA graph while the arrays stay the same.  `loss::Vector{Float32}` (length 1) and `grads = (gd, gr, gt)`
+are host arrays written in place.
+"""
+function vsl_fwdbwd_host!(loss::Vector{Float32}, grads, x::Array{Float32,5}, disparities, rvecs, tvecs,
+                          K::Matrix{Float32}, invK::Matrix{Float32}; target_id, source_ids, scales, min_depth, max_depth,
+                          disparity_smoothness, normalize = true, groups = 2)
+    W, H, C, Lf, N = size(x); S = length(source_ids); L = length(disparities)
+    gd, gr, gt = grads
+    hp(a) = a === nothing ? P32(0) : reinterpret(P32, pointer(a))
+    fp(id) = reinterpret(P32, pointer(x, (id - 1) * W * H * C + 1))
+    fs = Int64(W * H * C * Lf)
+    desc = Ref(VslDesc(W, H, N, C, S, L, fp(target_id), fs,
+        pad([fp(i) for i in source_ids], MAX_S, P32(0)), pad(fill(fs, S), MAX_S, Int64(0)),
+        pad([hp(d) for d in disparities], MAX_L, P32(0)), pad(Int32[size(d, 1) for d in disparities], MAX_L, Int32(0)),
+        pad(Int32[size(d, 2) for d in disparities], MAX_L, Int32(0)), hp(K), hp(invK), Int32(1),
+        pad([hp(r) for r in rvecs], MAX_S, P32(0)), pad([hp(t) for t in tvecs], MAX_S, P32(0)),
+        pad(Int32[i < target_id for i in source_ids], MAX_S, Int32(0)), P32(0),
+        Float32(min_depth), Float32(max_depth), pad(Float32[disparity_smoothness * s for s in scales[1:L]], MAX_L, 0f0),
+        Float32(1 / L), Int32(normalize), hp(loss),
+        pad([hp(g) for g in gd], MAX_L, P32(0)), pad([hp(g) for g in gr], MAX_S, P32(0)),
+        pad([hp(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
+        pad(P32[], MAX_S, P32(0)), P32(0), P32(0), Int32(1)))
+    GC.@preserve x disparities rvecs tvecs K invK loss gd gr gt begin
+        check(ccall((:md2_view_synthesis_loss_fwdbwd_host, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Cint),
+                    ctx(), desc, 1f0, Cint(groups)))
+    end
+    loss[1]
+end
+
 # the tail of train_loss as one differentiable function of (disparities, rvecs, tvecs)
 function view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK; kw...)
     loss, _, _, _ = vsl_fwdbwd(x, disparities, rvecs, tvecs, K, invK; kw...)

@@ -221,6 +221,7 @@ def test_host_entry_point_matches_device_path(groups, automask, grad_x):
         auto = M.automasking_loss(M.SSIM(), x.to(dev), x.to(dev)[:, 1], (0, 2)).cpu()
 
     def device_path(xh, dh):
+        nonlocal rv, tv
         xg = xh.to(dev).requires_grad_(grad_x)
         dg = [d.to(dev).requires_grad_(True) for d in dh]
         rg = [r.to(dev).requires_grad_(True) for r in rv]
@@ -235,6 +236,9 @@ def test_host_entry_point_matches_device_path(groups, automask, grad_x):
     for rep in range(3):
         xh = x if rep < 2 else (x * 0.9 + 0.05)
         dh = disps if rep < 2 else [d * 0.8 + 0.1 for d in disps]
+        if rep == 2:   # new pose values in the same buffers: the graph replay must pick them up from the staging copy
+            rv = [r * 1.5 for r in rv]
+            tv = [t * 0.5 for t in tv]
         loss = hv(xh, dh, rv, tv, auto)
         rl, rgd, rgr, rgt, rgx = device_path(xh, dh)
         assert abs(loss - rl) <= 2e-6 * max(1.0, abs(rl)), (rep, loss, rl)
