@@ -633,7 +633,7 @@ struct March {
         c.bars = bar_ref_of(wsm + RING_FLOATS);
         c.fill = slot_of(gslot);
         // pin the per-lane invariants in registers (otherwise they are re-derived in every row)
-        keep(c.g.gxm); keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
+        keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.sb[s]);
@@ -901,7 +901,7 @@ struct March {
         }
         c.ring = ring_ref_of(wsm, lane);
         c.bars = bar_ref_of(wsm + RING_FLOATS);
-        keep(c.g.gxm); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); keep(c.ring); keep(c.bars);
+        keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.gb[s]);
