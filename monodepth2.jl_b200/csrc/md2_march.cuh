@@ -278,6 +278,7 @@ struct March {
         const float* sb[S];
         const float* dp;             // full-resolution disparity of this (scale, image) + this lane's column
         const float* am;             // automask of this image or null
+        int has_am;                  // (kept in a register: the null test of the pointer would re-load the launch parameter every row)
         float rc[C];
         float apx[S][3];
         int pb[S];
@@ -504,7 +505,7 @@ struct March {
             }
         }
         float wlv = pe_best;
-        if (c.am) {
+        if (c.has_am) {
             MD2_RARE_BLOCK();
             const int qc = q < 0 ? 0 : (q > g.H - 1 ? g.H - 1 : q);
             const float am = g_ld(c.am + (qc * g.W + g.gxm));
@@ -609,6 +610,7 @@ struct March {
         for (int s = 0; s < S; ++s) c.sb[s] = p.src[s] + (long long)g.n * p.src_ns[s];
         c.dp = p.dfull[g.scale] + (long long)g.n * g.HW + g.gxm;
         c.am = p.automask ? p.automask + (long long)g.n * g.HW : nullptr;
+        c.has_am = p.automask != nullptr;
         // centring constant of the window sums (any constant is exact; a local value keeps the
         // centred squares small): the target at the middle of the strip chunk
         {
@@ -633,7 +635,7 @@ struct March {
         c.bars = bar_ref_of(wsm + RING_FLOATS);
         c.fill = slot_of(gslot);
         // pin the per-lane invariants in registers (otherwise they are re-derived in every row)
-        keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
+        keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.has_am); keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.sb[s]);
@@ -683,6 +685,7 @@ struct March {
     struct CtxB {
         Geo g;
         float* gb[S];
+        int has_gb[S];               // (kept in registers, like has_am)
         float* gd;                   // full-resolution disparity gradient of this (scale, image)
         float apx[S][3];
         int pb[S];
@@ -800,7 +803,7 @@ struct March {
                 acc.P1[s][2] = fmaf(t2, pyr, acc.P1[s][2]);
                 acc.Ph[s][0] += cb0; acc.Ph[s][1] += cb1; acc.Ph[s][2] += cb2;
                 // source-image gradient: scatter with vertical carry + merge with the right-hand lane
-                if (c.gb[s]) {
+                if (c.has_gb[s]) {
                     const bool sval = act;     // (ibar is already 0 outside the output columns)
                     const float gx1 = 1.f - fx, gy1 = 1.f - fy;
                     float tq0[C], tq1[C];
@@ -841,7 +844,7 @@ struct March {
                     }
                     acc.coff[s] = sval ? off : -1;
                 }
-            } else if (c.gb[s]) {
+            } else if (c.has_gb[s]) {
                 // nobody scatters into source s on this row: flush what the previous row carried
                 if (acc.coff[s] >= 0) {
                     float* o = c.gb[s] + (acc.coff[s] + g.W);
@@ -870,6 +873,7 @@ struct March {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             c.gb[s] = p.gsrc[s] ? p.gsrc[s] + (long long)g.n * p.src_ns[s] : nullptr;
+            c.has_gb[s] = p.gsrc[s] != nullptr;
             c.pb[s] = p.pose_slot + (s * p.N + g.n) * 12;
         }
         c.gd = p.gfull[g.scale] + (long long)g.n * g.HW;
@@ -904,7 +908,7 @@ struct March {
         keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            keep(c.gb[s]);
+            keep(c.gb[s]); keep(c.has_gb[s]);
 #pragma unroll
             for (int k = 0; k < 3; ++k) keep(c.apx[s][k]);
         }
