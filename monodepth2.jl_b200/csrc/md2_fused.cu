@@ -149,31 +149,35 @@ __device__ __forceinline__ float sel4(const float (&h)[4], int k) {   // k is wa
     return k == 0 ? h[0] : (k == 1 ? h[1] : (k == 2 ? h[2] : h[3]));
 }
 
-template <int C, int LMAX>
-__global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_constant__ FusedParams p, int strips, int chunks,
-                                                               int nblk, int do_stats, float* __restrict__ pose_ab,
-                                                               float* __restrict__ part, int zero_blocks) {
+// block 0 of an image: poses; blocks beyond the patch blocks: zero-fill of one slice of a source-gradient image
+template <int C>
+__device__ __forceinline__ void prep_pose_or_zero(const FusedParams& p, int nblk, float* __restrict__ pose_ab, int zero_blocks) {
     const int n = blockIdx.y;
     if (blockIdx.x == 0) {
         if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
         return;
     }
-    const int W = p.W, H = p.H, HW = W * H;
-    if ((int)blockIdx.x > nblk) {                            // zero-fill of one slice of a source-gradient image
-        const int zb = blockIdx.x - nblk - 1, s = zb / zero_blocks, sl = zb - s * zero_blocks;
-        if (!p.gsrc[s]) return;
-        float* g = p.gsrc[s] + (long long)n * p.src_ns[s];
-        const int total = C * HW;
-        const int per = ((total + zero_blocks - 1) / zero_blocks + 3) & ~3;
-        const int i0 = sl * per, i1 = min(i0 + per, total);
-        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-            for (int i = i0 + 4 * (int)threadIdx.x; i + 3 < i1; i += 4 * (int)blockDim.x) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = i0 + ((i1 - i0) & ~3) + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
-        } else {
-            for (int i = i0 + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
-        }
-        return;
+    const int zb = blockIdx.x - nblk - 1, s = zb / zero_blocks, sl = zb - s * zero_blocks;
+    if (!p.gsrc[s]) return;
+    float* g = p.gsrc[s] + (long long)n * p.src_ns[s];
+    const int total = C * p.W * p.H;
+    const int per = ((total + zero_blocks - 1) / zero_blocks + 3) & ~3;
+    const int i0 = sl * per, i1 = min(i0 + per, total);
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        for (int i = i0 + 4 * (int)threadIdx.x; i + 3 < i1; i += 4 * (int)blockDim.x) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = i0 + ((i1 - i0) & ~3) + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
+    } else {
+        for (int i = i0 + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
     }
+}
+
+template <int C, int LMAX>
+__global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_constant__ FusedParams p, int strips, int chunks,
+                                                               int nblk, int do_stats, float* __restrict__ pose_ab,
+                                                               float* __restrict__ part, int zero_blocks) {
+    const int n = blockIdx.y;
+    if (blockIdx.x == 0 || (int)blockIdx.x > nblk) { prep_pose_or_zero<C>(p, nblk, pose_ab, zero_blocks); return; }
+    const int W = p.W, H = p.H, HW = W * H;
     __shared__ float red[PREP_WARPS][3 * LMAX];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = (blockIdx.x - 1) * PREP_WARPS + warp;
@@ -288,6 +292,140 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_c
     if (!do_stats) return;
     __syncthreads();
     if ((int)threadIdx.x < 3 * p.L) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < PREP_WARPS; ++k) s += red[k][threadIdx.x];
+        const int l = threadIdx.x / 3, k = threadIdx.x - 3 * l;
+        part[(((long long)l * p.N + n) * nblk + (blockIdx.x - 1)) * 4 + k] = s;
+    }
+}
+
+// Transpose-reduce of 16 values per lane: afterwards lanes k and k + 16 hold the warp total of value k (17 shuffles)
+__device__ __forceinline__ float warp_reduce_16(float (&v)[16]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// The same patch work for the usual decoder layout, specialised and written lean (the generic kernel above spends most
+// of its instructions on per-scale bookkeeping): scales 0 .. NLOW-1 are low-resolution, scale NLOW (the last) is at
+// full resolution, the call is the fused fwd+bwd one (statistics wanted), 3 (NLOW + 1) <= 16.
+template <int C, int NLOW>
+__global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __grid_constant__ FusedParams p, int strips, int chunks,
+                                                                    int nblk, float* __restrict__ pose_ab,
+                                                                    float* __restrict__ part, int zero_blocks) {
+    constexpr int NS = NLOW + 1;
+    static_assert(3 * NS <= 16, "one transpose-reduce of 16 values");
+    const int n = blockIdx.y;
+    if (blockIdx.x == 0 || (int)blockIdx.x > nblk) { prep_pose_or_zero<C>(p, nblk, pose_ab, zero_blocks); return; }
+    __shared__ float red[PREP_WARPS][16];
+    const int W = p.W, H = p.H, HW = W * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = (blockIdx.x - 1) * PREP_WARPS + warp;
+    const bool active = w < strips * chunks;
+    const int cy = w / strips, sx = w - cy * strips;
+    const int gx = sx * PREP_COLS + lane;
+    const int gxc = gx < W ? gx : W - 1;
+    const bool own_col = active && lane < PREP_COLS && gx < W;
+    const bool has_right = own_col && gx + 1 < W;
+    const int Y0 = active ? cy * PREP_ROWS : 0;
+    int yo[PREP_ROWS + 1];                                   // clamped row offsets
+    float rowm[PREP_ROWS + 1];                               // 1 for rows of this patch that are inside the image
+#pragma unroll
+    for (int r = 0; r <= PREP_ROWS; ++r) { yo[r] = min(Y0 + r, H - 1) * W; rowm[r] = (Y0 + r < H) ? 1.f : 0.f; }
+
+    // ---- every load of the patch ----
+    const float* tg = p.tgt + ((long long)n * p.tgt_ns + gxc);
+    float t[PREP_ROWS + 1][C], dnat[PREP_ROWS + 1];
+#pragma unroll
+    for (int r = 0; r <= PREP_ROWS; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) t[r][c] = __ldg(tg + (c * HW + yo[r]));
+    {
+        const float* dp = p.disp[NLOW] + ((long long)n * HW + gxc);
+#pragma unroll
+        for (int r = 0; r <= PREP_ROWS; ++r) dnat[r] = __ldg(dp + yo[r]);
+    }
+    float q[NLOW > 0 ? NLOW : 1][8], fxu[NLOW > 0 ? NLOW : 1];
+    int yb[NLOW > 0 ? NLOW : 1];
+#pragma unroll
+    for (int l = 0; l < NLOW; ++l) {
+        const int dw = p.dw[l], dh = p.dh[l];
+        int xa0, xa1, yb1; float fy0;
+        up_taps(gxc, p.usx[l], dw, xa0, xa1, fxu[l]);
+        up_taps(min(Y0, H - 1), p.usy[l], dh, yb[l], yb1, fy0);
+        const float* dp = p.disp[l] + (long long)n * dw * dh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ro = min(yb[l] + k, dh - 1) * dw;
+            q[l][2 * k] = __ldg(dp + (ro + xa0)); q[l][2 * k + 1] = __ldg(dp + (ro + xa1));
+        }
+    }
+
+    // ---- edge weights (shared by the scales), ownership masks folded in ----
+    float wx[PREP_ROWS], wy[PREP_ROWS + 1];
+    const float mcol = own_col ? 1.f : 0.f, mright = has_right ? 1.f : 0.f;
+#pragma unroll
+    for (int r = 0; r <= PREP_ROWS; ++r) {
+        float gxv = 0.f, gyv = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (r < PREP_ROWS) gxv += fabsf(t[r][c] - __shfl_down_sync(0xffffffffu, t[r][c], 1));
+            if (r > 0) gyv += fabsf(t[r - 1][c] - t[r][c]);
+        }
+        if (r < PREP_ROWS) wx[r] = __expf(-gxv * (1.0f / C)) * (mright * rowm[r]);
+        wy[r] = r > 0 ? __expf(-gyv * (1.0f / C)) * (mcol * rowm[r]) : 0.f;
+    }
+
+    // ---- per scale: full-resolution disparities of the patch, scratch, sums ----
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int l = 0; l < NS; ++l) {
+        float d[PREP_ROWS + 1];
+        if (l == NLOW) {
+#pragma unroll
+            for (int r = 0; r <= PREP_ROWS; ++r) d[r] = dnat[r];
+        } else {
+            const int dh = p.dh[l];
+            const float usy = p.usy[l];
+            float h[4];                                      // low-res rows yb .. yb+3, interpolated horizontally
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = fmaf(fxu[l], q[l][2 * k + 1] - q[l][2 * k], q[l][2 * k]);
+            float* out = const_cast<float*>(p.dfull[l]) + ((long long)n * HW + gx);
+#pragma unroll
+            for (int r = 0; r <= PREP_ROWS; ++r) {
+                int ya0, ya1; float fyu;
+                up_taps(min(Y0 + r, H - 1), usy, dh, ya0, ya1, fyu);
+                const float top = sel4(h, ya0 - yb[l]), bot = sel4(h, ya1 - yb[l]);
+                d[r] = fmaf(fyu, bot - top, top);
+                if (r < PREP_ROWS && Y0 + r < H && own_col) out[yo[r]] = d[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r <= PREP_ROWS; ++r) {
+            if (r < PREP_ROWS) {
+                const float dr = __shfl_down_sync(0xffffffffu, d[r], 1);
+                v[3 * l] = fmaf(fabsf(d[r] - dr), wx[r], v[3 * l]);
+                v[3 * l + 2] = fmaf(d[r], mcol * rowm[r], v[3 * l + 2]);
+            }
+            if (r > 0) v[3 * l + 1] = fmaf(fabsf(d[r - 1] - d[r]), wy[r], v[3 * l + 1]);   // rows r-1 (owned) and r
+        }
+    }
+    const float tot = warp_reduce_16(v);
+    if (lane < 16) red[warp][lane] = tot;
+    __syncthreads();
+    if ((int)threadIdx.x < 3 * NS) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < PREP_WARPS; ++k) s += red[k][threadIdx.x];
@@ -765,9 +903,16 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     {   // prep: poses, upsampled low-res disparities (+ smoothness sums for the fused fwd+bwd, + zero-fill)
         const int nb = (do_stats || n_low) ? prep_nblk : 0;
         dim3 g(1 + nb + S * zero_blocks, N);
+        // usual decoder layout (low-res scales first, one full-resolution scale last, fused fwd+bwd): the lean kernel
+        bool usual = do_stats && nb > 0 && L >= 1 && L <= 4 && n_low == L - 1 && d->disp_w[L - 1] == W && d->disp_h[L - 1] == H;
+        if (getenv("MD2_PREP_GENERIC")) usual = false;
+#define MD2_PREPF(CC, NL) prep_fast_kernel<CC, NL><<<g, 32 * PREP_WARPS, 0, st>>>(p, prep_strips, prep_chunks, nb, pose_ab, part2, zero_blocks)
 #define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 32 * PREP_WARPS, 0, st>>>(p, prep_strips, prep_chunks, nb, do_stats, pose_ab, part2, zero_blocks)
-        if (C == 1) { if (L == 1) MD2_PREP(1, 1); else if (L <= 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
+        if (usual && C == 1)      { if (L == 1) MD2_PREPF(1, 0); else if (L == 2) MD2_PREPF(1, 1); else if (L == 3) MD2_PREPF(1, 2); else MD2_PREPF(1, 3); }
+        else if (usual)           { if (L == 1) MD2_PREPF(3, 0); else if (L == 2) MD2_PREPF(3, 1); else if (L == 3) MD2_PREPF(3, 2); else MD2_PREPF(3, 3); }
+        else if (C == 1) { if (L == 1) MD2_PREP(1, 1); else if (L <= 4) MD2_PREP(1, 4); else MD2_PREP(1, 8); }
         else        { if (L == 1) MD2_PREP(3, 1); else if (L <= 4) MD2_PREP(3, 4); else MD2_PREP(3, 8); }
+#undef MD2_PREPF
 #undef MD2_PREP
         MD2_LAUNCH_CHECK(ctx);
     }
