@@ -22,7 +22,7 @@ struct Workspace {
 }  // namespace md2
 
 enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, MD2_WS_GDISP,
-       MD2_WS_POSEIN, MD2_WS_MISC, MD2_WS_COUNT };
+       MD2_WS_MISC, MD2_WS_COUNT };
 
 #include <vector>
 struct md2_ctx {

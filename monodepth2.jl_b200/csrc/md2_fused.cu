@@ -893,7 +893,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
     float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)prep_nblk * L * N * 4);
     if (!pose_ab || !partial || !stats || !part2) return 1;
-    p.pose_ab = pose_ab; p.partial = partial; p.sums = nullptr; p.counters = nullptr;
+    p.pose_ab = pose_ab; p.partial = partial;
     p.stats = stats; p.stats_out = stats; p.saved = (mode == MODE_BWD) ? nullptr : d->saved;
     if (mode == MODE_BWD && d->saved) p.stats = d->saved;   // else the ctx holds the last forward's statistics
     p.loss = (mode == MODE_BWD) ? nullptr : d->loss;

@@ -33,7 +33,7 @@ struct FusedParams {
     const float* automask;              // (N,H,W) or null   (src/training.jl:60-62)
     const float* pose_ab;               // (S,N,12) pre-composed A|b
     const float* stats;                 // (L,N,NSTAT) forward sums, needed by the backward pass
-    float* partial;                     // (blocks, NPART) per-block partial sums
+    float* partial;                     // (L*N, segments, NPART) per-segment partial sums of the marching kernel
     float depth_a, depth_b;             // z = 1/(a d + b)   (src/utils.jl:175-179)
     float smooth_w[MAX_L];              // disparity_smoothness * scale_i  (src/training.jl:66-67)
     float loss_scale;                   // 1/L  (src/training.jl:77)
@@ -41,10 +41,8 @@ struct FusedParams {
     int normalize_disp;                 // 1: d / (mean d + 1e-7) before smoothness (src/training.jl:64-65)
     float* viz_warped[MAX_S];           // optional (N,C,H,W) contiguous, last scale only
     float* viz_loss;                    // optional (N,H,W), last scale only
-    // device-side finalisation by the last block (md2_fused.cu)
+    // finalisation (finish kernel, md2_fused.cu)
     int mode;                           // 0 fwd, 1 bwd, 2 fwdbwd
-    unsigned int* counters;             // [L*N + 1], zero on entry, left zero on exit
-    float* sums;                        // (L*N, NPART)
     float* stats_out;                   // (L*N, NSTAT) written in modes 0 and 2
     float* saved;                       // nullable copy of stats_out for a later bwd
     float* loss;                        // nullable device scalar

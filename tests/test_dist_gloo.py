@@ -36,7 +36,9 @@ def _worker(rank, world, port, q):
     ms = D.max_over_ranks(10.0 + rank)
     shared = [torch.full((3,), float(rank + 1), dtype=torch.float64)]
     D.allreduce_mean_(shared)
-    q.put((rank, gl.item(), ms, shared[0].tolist(), [d.grad.clone() for d in ds], D.shard_bounds(N, rank, world)))
+    # (numpy arrays travel by value; torch tensors would be shared through the worker's resource sharer, which is
+    # gone if the worker exits before the parent unpickles them)
+    q.put((rank, gl.item(), ms, shared[0].tolist(), [d.grad.numpy().copy() for d in ds], D.shard_bounds(N, rank, world)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -75,4 +77,4 @@ def test_two_rank_sharding_matches_full_batch():
         assert shared == [1.5, 1.5, 1.5]               # all-reduce average of a replicated parameter gradient
         for g, gf in zip(grads, dfull):
             # a rank's per-image gradient is for the mean over ITS images: 1/world of it is the global one
-            assert torch.allclose(g / world, gf.grad[lo:hi], atol=1e-14)
+            assert torch.allclose(torch.from_numpy(g) / world, gf.grad[lo:hi], atol=1e-14)
