@@ -42,6 +42,17 @@ namespace md2 {
 
 struct alignas(16) Vec4 { float x, y, z, w; };
 
+// source-gradient scatter of warp B.  0: both tap rows of a pixel are issued at once, the right taps merged into the
+// right-hand lane's left taps (~2.2 atomics per pixel and source); 1: the lower tap pair is additionally carried in
+// registers to the next row (~1.6 atomics, but ~20 more instructions per row and source).  Measured at 416x128x8:
+// 71.9 us (0) vs 75.6 us (1): the kernel is bound by issue slots, not by the atomics.
+#ifndef MD2_SCATTER_CARRY
+#define MD2_SCATTER_CARRY 0
+#endif
+#ifndef MD2_SCATTER_MERGE
+#define MD2_SCATTER_MERGE 1   // merge a pixel's right taps into the right-hand lane's left taps (warp shuffles)
+#endif
+
 #if defined(MD2_WARP_EMU)
 #define MD2_DEV inline
 // emu_xchg / emu_ballot / emu_bar: tests/emul/warp_emu.h, included before this file
@@ -802,6 +813,7 @@ struct March {
                 acc.P1[s][0] = fmaf(t0, pyr, acc.P1[s][0]); acc.P1[s][1] = fmaf(t1, pyr, acc.P1[s][1]);
                 acc.P1[s][2] = fmaf(t2, pyr, acc.P1[s][2]);
                 acc.Ph[s][0] += cb0; acc.Ph[s][1] += cb1; acc.Ph[s][2] += cb2;
+#if MD2_SCATTER_CARRY
                 // source-image gradient: scatter with vertical carry + merge with the right-hand lane
                 if (c.has_gb[s]) {
                     const bool sval = act;     // (ibar is already 0 outside the output columns)
@@ -844,7 +856,39 @@ struct March {
                     }
                     acc.coff[s] = sval ? off : -1;
                 }
-            } else if (c.has_gb[s]) {
+#else
+                // source-image gradient: both tap rows now, right taps merged into the right-hand lane's left taps
+                if (c.has_gb[s]) {
+                    const bool sval = act;     // (ibar is already 0 outside the output columns)
+                    const float gx1 = 1.f - fx, gy1 = 1.f - fy;
+#if MD2_SCATTER_MERGE
+                    const int key = sval ? off : -2;
+                    const int key_r = w_dn(key, lane), key_l = w_up(key, lane);
+                    const bool absorbed = sval && lane < 31 && key_r == key + 1;
+                    const bool absorb = sval && lane > 0 && key_l >= 0 && key_l + 1 == key;
+#else
+                    const bool absorbed = false;
+#endif
+                    float* o = c.gb[s] + off;
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        const float wl = gx1 * ibar[ch], wr = fx * ibar[ch];
+                        float t0 = wl * gy1, t1 = wr * gy1, b0 = wl * fy, b1 = wr * fy;
+#if MD2_SCATTER_MERGE
+                        const float flt = w_up(t1, lane), flb = w_up(b1, lane);
+                        if (absorb) { t0 += flt; b0 += flb; }
+#endif
+                        if (sval) {
+                            g_red(o + ch * g.HW, t0);
+                            g_red(o + (ch * g.HW + g.W), b0);
+                            if (!absorbed) { g_red1(o + ch * g.HW, t1); g_red1(o + (ch * g.HW + g.W), b1); }
+                        }
+                    }
+                }
+#endif
+            }
+#if MD2_SCATTER_CARRY
+            else if (c.has_gb[s]) {
                 // nobody scatters into source s on this row: flush what the previous row carried
                 if (acc.coff[s] >= 0) {
                     float* o = c.gb[s] + (acc.coff[s] + g.W);
@@ -856,6 +900,7 @@ struct March {
                 }
                 acc.coff[s] = -1;
             }
+#endif
         }
         // depth -> disparity:  dz/dd = -a z^2
         float gd = c.nega * zr * zr * dbar_z;
@@ -972,7 +1017,7 @@ struct March {
         // flush the carried lower tap pairs of the last row
 #pragma unroll
         for (int s = 0; s < S; ++s)
-            if (c.gb[s] && acc.coff[s] >= 0) {
+            if (MD2_SCATTER_CARRY && c.gb[s] && acc.coff[s] >= 0) {
                 float* o = c.gb[s] + (acc.coff[s] + g.W);
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
