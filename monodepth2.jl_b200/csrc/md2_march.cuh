@@ -49,6 +49,11 @@ struct alignas(16) Vec4 { float x, y, z, w; };
 #ifndef MD2_SCATTER_CARRY
 #define MD2_SCATTER_CARRY 0
 #endif
+// which warp forms the smoothness gradient of a pixel (balances the pair): 0 = warp F (sends ghat with the window
+// packet), 1 = warp B (reads the target values / disparity of row r+1 from the next slot)
+#ifndef MD2_SMOOTH_IN_B
+#define MD2_SMOOTH_IN_B 0   // measured at 416x128x8: 72.3 us (0) vs 73.9 us (1)
+#endif
 #ifndef MD2_SCATTER_MERGE
 #define MD2_SCATTER_MERGE 1   // merge a pixel's right taps into the right-hand lane's left taps (warp shuffles)
 #endif
@@ -560,7 +565,8 @@ struct March {
             wp[3 * C] = i_as_float(sel);
             // smoothness gradient of pixel row q before the mean-normalisation (warp B applies A ghat - B):
             // ghat = (ex(q) - ex(q)[left lane]) + (ey(q) - ey(q-1)), e = sign(d - d') exp(-mean_c |T - T'|) / count
-            {
+            if (MD2_SMOOTH_IN_B) wp[3 * C + 1] = 0.f;
+            else {
                 const float Dr = w_dn(b.D, lane);
                 float gxs = 0.f, gys = 0.f;
 #pragma unroll
@@ -712,6 +718,7 @@ struct March {
     // three windows around this column, z = the part of t selected for source 0, sel = this column's selection
     struct WinRow { float t[3 * C], z[3 * C]; int sel; float gh; };
     struct AccB {
+        float ey_prev;               // vertical smoothness edge between the previous row and this one (MD2_SMOOTH_IN_B)
         float P0[S][3], P1[S][3], Ph[S][3];
         float car0[S][C], car1[S][C];
         int coff[S];
@@ -746,7 +753,25 @@ struct March {
     }
 
     // ---- P(r): slot t0 = row r (pixel packet); wa, wb, wc = window rows r-1, r, r+1 ----
-    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, const WinRow& wa,
+    // vertical smoothness edge between rows y and y+1 (own target values / disparities of both rows)
+    static MD2_DEV float edge_y(const CtxB& c, int y, const float* ymA, float DA, const float* ymB, float DB) {
+        float gsum = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gsum += fabsf(ymA[ch] - ymB[ch]);
+        const float w = f_ex2(gsum * (-1.4426950408889634f / C)) * c.cyn;
+        return (y >= 0 && y + 1 < c.g.H) ? sgn_scaled(DA - DB, w) : 0.f;
+    }
+    // ym[C], D of the row in slot t
+    static MD2_DEV void load_ym_d(const CtxB& c, Slot t, float (&yd)[NYD4 * 4]) {
+        const int sv = slot_vec(t);
+#pragma unroll
+        for (int k = 0; k < NYD4; ++k) {
+            const Vec4 q = s_ld4(c.ring, sv + k * 32);
+            yd[4 * k] = q.x; yd[4 * k + 1] = q.y; yd[4 * k + 2] = q.z; yd[4 * k + 3] = q.w;
+        }
+    }
+
+    static MD2_DEV void stage_pixels(const FusedParams& p, const CtxB& c, AccB& acc, int r, Slot t0, Slot t1, const WinRow& wa,
                                      const WinRow& wb, const WinRow& wc) {
         const Geo& g = c.g;
         const int lane = g.lane;
@@ -906,7 +931,23 @@ struct March {
         float gd = c.nega * zr * zr * dbar_z;
         // smoothness gradient (src/utils.jl:159-173 with the mean-normalisation of
         // src/training.jl:64-65 folded in):  A ghat_j - B   (ghat comes from warp F with the window row)
-        gd += fmaf(c.sA, wb.gh, -c.sB);
+        float gh = wb.gh;
+        if (MD2_SMOOTH_IN_B) {
+            float nx[NYD4 * 4];
+            load_ym_d(c, t1, nx);
+            const float Da = pk[O_D];
+            const float ey = edge_y(c, r, pk + O_YM, Da, nx + O_YM, nx[O_D]);
+            const float Dr = w_dn(Da, lane);
+            float gsum = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) gsum += fabsf(pk[O_YM + ch] - w_dn(pk[O_YM + ch], lane));
+            const float w = f_ex2(gsum * (-1.4426950408889634f / C)) * c.cxn;
+            const float ex = g.has_right ? sgn_scaled(Da - Dr, w) : 0.f;
+            const float exl = w_up(ex, lane);
+            gh = (ex - exl) + (ey - acc.ey_prev);
+            acc.ey_prev = ey;
+        }
+        gd += fmaf(c.sA, gh, -c.sB);
         if (g.pcol) g_st(c.gd + (r * g.W + g.gxm), gd);   // (gxm == gxr on the output columns)
     }
 
@@ -974,6 +1015,13 @@ struct March {
         acquire(c, ta);                                            // row Y0-1
         Slot tb = next_slot(ta);
         acquire(c, tb);                                            // row Y0
+        acc.ey_prev = 0.f;
+        if (MD2_SMOOTH_IN_B) {   // the "up" edge of the first row
+            float ya[NYD4 * 4], yb[NYD4 * 4];
+            load_ym_d(c, ta, ya);
+            load_ym_d(c, tb, yb);
+            acc.ey_prev = edge_y(c, g.Y0 - 1, ya + O_YM, ya[O_D], yb + O_YM, yb[O_D]);
+        }
         release(c, ta);
         ta = tb;                                                   // ta = slot of row r, tb = slot of row r+1
         tb = next_slot(tb);
@@ -989,7 +1037,7 @@ struct March {
             const Slot tc = next_slot(tb);                                                            \
             acquire(c, tc);                                        /* row r+2: carries window row r+1 */ \
             load_window_row(c, tc, WC);                                                               \
-            stage_pixels(p, c, acc, r, ta, WA, WB, WC);                                           \
+            stage_pixels(p, c, acc, r, ta, tb, WA, WB, WC);                                           \
             release(c, ta);                                                                           \
             ta = tb; tb = tc;                                                                         \
             ++r;                                                                                      \
