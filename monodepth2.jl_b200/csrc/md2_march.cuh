@@ -54,6 +54,9 @@ struct alignas(16) Vec4 { float x, y, z, w; };
 #ifndef MD2_SMOOTH_IN_B
 #define MD2_SMOOTH_IN_B 0   // measured at 416x128x8: 72.3 us (0) vs 73.9 us (1)
 #endif
+#ifndef MD2_SKIP_IDLE_SOURCE
+#define MD2_SKIP_IDLE_SOURCE 1   // warp B skips the adjoint of a source that no lane selected around this row (warp vote)
+#endif
 #ifndef MD2_SCATTER_MERGE
 #define MD2_SCATTER_MERGE 1   // merge a pixel's right taps into the right-hand lane's left taps (warp shuffles)
 #endif
@@ -814,7 +817,7 @@ struct March {
                 act = act || (ibar[ch] != 0.f);
             }
             // sources not selected anywhere in the 3x3 neighbourhood of any lane skip all of this
-            if (w_any(act)) {
+            if (!MD2_SKIP_IDLE_SOURCE || w_any(act)) {
                 const float q = st[0], u = st[1], vv = st[2];
                 const float fx = st[3], fy = st[4];
                 const int off = f_as_int(st[5]);
