@@ -57,6 +57,9 @@ struct alignas(16) Vec4 { float x, y, z, w; };
 #ifndef MD2_SKIP_IDLE_SOURCE
 #define MD2_SKIP_IDLE_SOURCE 1   // warp B skips the adjoint of a source that no lane selected around this row (warp vote)
 #endif
+#ifndef MD2_PIN_MORE_C3
+#define MD2_PIN_MORE_C3 0
+#endif
 #ifndef MD2_SCATTER_MERGE
 #define MD2_SCATTER_MERGE 1   // merge a pixel's right taps into the right-hand lane's left taps (warp shuffles)
 #endif
@@ -234,6 +237,9 @@ MD2_DEV Slot next_slot(Slot t) {
 template <int C, int S, bool BWD>
 struct March {
     static constexpr int HALO = BWD ? 2 : 1;
+    // pin more loop invariants in registers (saves re-reading %tid / launch parameters in the row loops); only where the
+    // register budget has room: with C = 3 it turns into spills
+    static constexpr bool PIN_MORE = (C == 1) || (MD2_PIN_MORE_C3 != 0);
     static constexpr int OW = 32 - 2 * HALO;             // output columns per strip
     static constexpr int NPART = NSTAT + 12 * S;
     // ---- ring slot layout (floats per lane) ----
@@ -655,7 +661,7 @@ struct March {
         c.bars = bar_ref_of(wsm + RING_FLOATS);
         c.fill = slot_of(gslot);
         // pin the per-lane invariants in registers (otherwise they are re-derived in every row)
-        keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.has_am); keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
+        keep(c.g.gxm); if (PIN_MORE) { keep(c.g.lane); keep(c.g.W); keep(c.has_am); } keep(c.tg); keep(c.dp); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             keep(c.sb[s]);
@@ -994,10 +1000,10 @@ struct March {
         }
         c.ring = ring_ref_of(wsm, lane);
         c.bars = bar_ref_of(wsm + RING_FLOATS);
-        keep(c.g.gxm); keep(c.g.lane); keep(c.g.W); keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); keep(c.ring); keep(c.bars);
+        keep(c.g.gxm); if (PIN_MORE) { keep(c.g.lane); keep(c.g.W); } keep(c.gd); keep(c.cl1); keep(c.mp); keep(c.sA); keep(c.sB); keep(c.ring); keep(c.bars);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            keep(c.gb[s]); keep(c.has_gb[s]);
+            keep(c.gb[s]); if (PIN_MORE) keep(c.has_gb[s]);
 #pragma unroll
             for (int k = 0; k < 3; ++k) keep(c.apx[s][k]);
         }
