@@ -521,7 +521,6 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 constexpr int FIN_MAXROWS = 64;   // contributing full-resolution rows handled per pass of phase A
 constexpr int FIN_THREADS = 128;  // small blocks: the whole grid is resident at once (one latency chain, no waves)
-constexpr int FIN_PJ = FIN_THREADS / 12;
 
 __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd, int low_rows) {
     extern __shared__ __align__(16) float vrow[];   // [W rounded up to 4] (adjoint blocks)
@@ -530,27 +529,34 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
     int b = blockIdx.x;
     if (b == 0) {
         if (p.mode == 1) return;
-        // eight lanes per (scale, image) group: strided partial sums (all loads in flight at once),
-        // then a fixed-order butterfly over the eight lanes
-        const int sub = threadIdx.x & 7;
-        for (int z0 = 0; z0 < LN; z0 += FIN_THREADS / 8) {
-            const int z = z0 + (threadIdx.x >> 3);
+        // FIN_THREADS / 32 ... lanes per (scale, image) group: strided partial sums with the loads issued in unrolled batches
+        // (a rolled loop would pay one L2 round trip per iteration), then a fixed-order butterfly over the lanes of a group
+        constexpr int GL = 4;                                 // lanes per group
+        const int sub = threadIdx.x & (GL - 1);
+        for (int z0 = 0; z0 < LN; z0 += FIN_THREADS / GL) {
+            const int z = z0 + (threadIdx.x / GL);
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (z < LN) {
                 const float* pp = p.partial + (long long)z * ipg * NP;
-                const int nv = p.mode == 0 ? 4 : 1;          // forward-only: warp F also carries the smoothness sums
-                for (int it = sub; it < ipg; it += 8)
-                    for (int k = 0; k < nv; ++k) v[k] += __ldcg(pp + (long long)it * NP + k);
-                if (p.mode == 2) {
+                if (p.mode == 0) {                            // forward-only: warp F also carries the smoothness sums
+#pragma unroll 4
+                    for (int it = sub; it < ipg; it += GL) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[k] += __ldcg(pp + (long long)it * NP + k);
+                    }
+                } else {
+#pragma unroll 8
+                    for (int it = sub; it < ipg; it += GL) v[0] += __ldcg(pp + (long long)it * NP);
                     const float4* q = reinterpret_cast<const float4*>(p.prep_part) + (long long)z * p.prep_nblk;
-                    for (int it = sub; it < p.prep_nblk; it += 8) {
+#pragma unroll 8
+                    for (int it = sub; it < p.prep_nblk; it += GL) {
                         const float4 t = __ldcg(q + it);
                         v[1] += t.x; v[2] += t.y; v[3] += t.z;
                     }
                 }
             }
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1)
+            for (int o = GL / 2; o > 0; o >>= 1)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
             if (z < LN && sub == 0) {
@@ -583,25 +589,29 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
     b -= 1;
     if (!bwd) return;
     if (b < p.S * p.N) {
-        // pose gradient of (source s, image nn): 12 sums over all scales and items; thread (j, k) adds
-        // every FIN_PJ-th row of column k in double, then 12 threads add the partials in order
-        __shared__ double pacc[FIN_PJ][12];
+        // pose gradient of (source s, image nn): 12 sums over all scales and segments.  Three lanes per row (one float4
+        // each; NP and NSTAT are multiples of 4), FIN_PR row groups, loads issued in unrolled batches; then 12 threads add
+        // the row-group partials in order, in double
+        constexpr int FIN_PR = FIN_THREADS / 3;
+        __shared__ double pacc[FIN_PR][12];
         const int s = b / p.N, nn = b % p.N;
-        const int k = threadIdx.x % 12, j = threadIdx.x / 12;
-        if (j < FIN_PJ) {
-            double a = 0.0;
+        const int q4 = threadIdx.x % 3, j = threadIdx.x / 3;
+        if (j < FIN_PR) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const int rows = p.L * ipg;
-            for (int r = j; r < rows; r += FIN_PJ) {
+#pragma unroll 4
+            for (int r = j; r < rows; r += FIN_PR) {
                 const int l = r / ipg, it = r - l * ipg;
-                a += (double)__ldcg(p.partial + (((long long)l * p.N + nn) * ipg + it) * NP + NSTAT + 12 * s + k);
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(p.partial + (((long long)l * p.N + nn) * ipg + it) * NP + NSTAT + 12 * s) + q4);
+                a0 += (double)t.x; a1 += (double)t.y; a2 += (double)t.z; a3 += (double)t.w;
             }
-            pacc[j][k] = a;
+            pacc[j][4 * q4] = a0; pacc[j][4 * q4 + 1] = a1; pacc[j][4 * q4 + 2] = a2; pacc[j][4 * q4 + 3] = a3;
         }
         __syncthreads();
         if (threadIdx.x < 12) {
             double a = 0.0;
-#pragma unroll
-            for (int q = 0; q < FIN_PJ; ++q) a += pacc[q][threadIdx.x];
+#pragma unroll 6
+            for (int q = 0; q < FIN_PR; ++q) a += pacc[q][threadIdx.x];
             pacc[0][threadIdx.x] = a;
         }
         __syncthreads();
