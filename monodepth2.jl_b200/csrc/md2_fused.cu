@@ -440,6 +440,9 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
 // partial sums in a fixed order, the very last one finalises the loss and the pose gradients
 // (deterministic loss).
 // ------------------------------------------------------------------------------------------
+#ifndef MD2_ROLE_SWAP
+#define MD2_ROLE_SWAP 1
+#endif
 template <int C, int S, bool BWD>
 struct MarchCfg {
     // register budget per thread; registers are allocated per warp in units of 512, so the useful
@@ -460,7 +463,7 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int 
     using M = March<C, S, BWD>;
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x & 31;
-    const int role = threadIdx.x >> 5;      // 0: warp F (forward), 1: warp B (backward)
+    int role = threadIdx.x >> 5;            // 0: warp F (forward), 1: warp B (backward)
     // segments = (strip, chunk) of a (scale, image); an item is one full-height chunk, or -- when the image
     // height is not a multiple of the chunk height -- a group of short last chunks of neighbouring strips (the
     // `strips` short chunks of a (scale, image) are cut into `lgroups` groups), so that all items are about
@@ -472,11 +475,19 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int 
     const int items = ipi * LN;
     int gslot = 0;
     if (BWD) {
+        // The two warps of a block sit on neighbouring schedulers (warp slots 2k, 2k+1 of the SM).  With a fixed role per
+        // warp index every warp F (the heavier role) would land on an even scheduler: swap the roles in every other pair
+        // of blocks on an SM (bit 2 of the hardware warp slot), so that each scheduler gets as many F as B warps.
+        int* swap_flag = reinterpret_cast<int*>(wsm + M::SMEM_FLOATS - 2);
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int b = 0; b < MARCH_NBAR; ++b) mb_init(bar_ref_of(wsm + M::RING_FLOATS), b, 32);
+            unsigned int wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            *swap_flag = MD2_ROLE_SWAP ? (int)((wid >> 2) & 1u) : 0;
         }
         __syncthreads();
+        role ^= *swap_flag;
     }
     // one warp pair per block, item index from blockIdx only, so that everything derived from it is
     // warp-uniform for the compiler (uniform registers / constant-bank operands); the grid is
