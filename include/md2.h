@@ -43,7 +43,7 @@ int md2_create(int device, md2_ctx** out);
 int md2_destroy(md2_ctx* ctx);
 /* number of kernels launched through this ctx since creation (bench's gpu_launches) */
 int64_t md2_launch_count(const md2_ctx* ctx);
-/* device-side timing of the dominant kernel (the fused tile kernel of
+/* device-side timing of the dominant kernel (the marching kernel of
  * md2_view_synthesis_loss_*): while enabled, every such launch is bracketed by CUDA events on
  * the launch stream; md2_profile_read waits for them, returns the summed duration and the
  * number of launches, and resets the counters.  Used by bench.py for the roofline figure. */

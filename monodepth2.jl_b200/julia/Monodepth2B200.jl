@@ -274,7 +274,7 @@ frameptr(x::CuF, id) = pointer(x, (id - 1) * size(x, 1) * size(x, 2) * size(x, 3
 """
     view_synthesis_loss(x, disparities, poses, K, invK; target_id, source_ids, scales, ...)
 
-Everything of `train_loss` after `model(...)` (src/training.jl:29-77) in two kernel launches.
+Everything of `train_loss` after `model(...)` (src/training.jl:29-77) in three kernel launches.
 Returns `(loss::CuArray{Float32,1}, grads)` where `grads = (disparities, rvecs, tvecs)` are the
 gradients for a unit cotangent (the pullback scales them).
 """
