@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmd2_b200.so")
 SOURCES = ["md2_fused.cu", "md2_ops.cu", "md2_host.cu"]
-HEADERS = ["md2_math.cuh", "md2_fused.cuh", "md2_march.cuh", "md2_common.cuh", os.path.join("..", "..", "include", "md2.h")]
+HEADERS = ["md2_math.cuh", "md2_fused.cuh", "md2_march.cuh", "md2_march2.cuh", "md2_common.cuh", os.path.join("..", "..", "include", "md2.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--cudart", "shared"]
 

@@ -8,6 +8,7 @@
 #include "md2_common.cuh"
 #include "md2_fused.cuh"
 #include "md2_march.cuh"
+#include "md2_march2.cuh"
 
 namespace md2 {
 
@@ -511,6 +512,36 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// the single-warp marching kernel (md2_march2.cuh): value + gradient.  Persistent one-warp blocks, as many as are
+// resident on the whole GPU; block b walks the work items b, b + grid, ... (same items / partial-sum rows as above)
+// ------------------------------------------------------------------------------------------
+template <int C, int S, bool AM>
+__global__ void __maxnreg__((March2<C, S, AM>::MAXREG))
+march2_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int q_full, int lgroups) {
+    extern __shared__ __align__(16) float wsm[];
+    using M = March2<C, S, AM>;
+    constexpr int NP = M::NPART;
+    const int lane = threadIdx.x;
+    const int ipg = strips * chunks;                     // segments (= partial-sum rows) per (scale, image)
+    const int n_full = strips * q_full;
+    const int ipi = n_full + (chunks > q_full ? lgroups : 0);   // items per (scale, image)
+    const int items = ipi * p.L * p.N;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int z = it / ipi, rem = it - z * ipi;
+        int cy, sx, sx_end;
+        if (rem < n_full) { cy = rem / strips; sx = rem - cy * strips; sx_end = sx + 1; }
+        else { cy = q_full; sx = (rem - n_full) * strips / lgroups; sx_end = (rem - n_full + 1) * strips / lgroups; }
+        for (; sx < sx_end; ++sx) {
+            float v[32];
+            M::run(p, sx, cy, z, lane, wsm, v);
+            const float tot = warp_reduce_32(v);
+            if (lane == 0 || (lane >= NSTAT && lane < NP))
+                p.partial[((long long)z * ipg + cy * strips + sx) * NP + lane] = tot;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // finish kernel (one launch after the marching kernel); every block is independent, all sums
 // are taken in a fixed order (deterministic), nothing is atomic:
 //   block 0             per-(scale, image) loss sums from the per-item partials (and, for the fused
@@ -742,6 +773,60 @@ static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     return 0;
 }
 
+template <int C, int S, bool AM>
+static int march2_resident() {
+    using M = March2<C, S, AM>;
+    static int resident = 0;
+    if (!resident) {
+        const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
+        int occ = 0;
+        if (cudaFuncSetAttribute(march2_kernel<C, S, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
+        cudaFuncSetAttribute(march2_kernel<C, S, AM>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2_kernel<C, S, AM>, M::THREADS, smem) != cudaSuccess) occ = 0;
+        resident = occ > 0 ? occ : 8;
+        if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] march2_kernel<%d,%d>: %d resident warps/SM, %zu B smem/warp\n", C, S, resident, smem);
+    }
+    return resident;
+}
+
+template <int C, int S, bool AM>
+static int launch_march2(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
+    using M = March2<C, S, AM>;
+    const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
+    const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R), q_full = p.H / p.m_R;
+    const int lgroups = p.m_group > 0 ? (p.m_group < strips ? p.m_group : strips) : 1;
+    const long long items = ((long long)strips * q_full + (chunks > q_full ? lgroups : 0)) * p.L * p.N;
+    const long long cap = (long long)ctx->sm_count * march2_resident<C, S, AM>();
+    const int blocks = (int)(items < cap ? items : cap);
+    march2_kernel<C, S, AM><<<blocks, M::THREADS, smem, st>>>(p, strips, chunks, q_full, lgroups);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int dispatch_march2(md2_ctx* ctx, int C, int S, const FusedParams& p, cudaStream_t st) {
+    const bool am = p.automask != nullptr;
+    if (C == 1 && S == 1) return am ? launch_march2<1, 1, true>(ctx, p, st) : launch_march2<1, 1, false>(ctx, p, st);
+    if (C == 1 && S == 2) return am ? launch_march2<1, 2, true>(ctx, p, st) : launch_march2<1, 2, false>(ctx, p, st);
+    if (C == 3 && S == 1) return am ? launch_march2<3, 1, true>(ctx, p, st) : launch_march2<3, 1, false>(ctx, p, st);
+    if (C == 3 && S == 2) return am ? launch_march2<3, 2, true>(ctx, p, st) : launch_march2<3, 2, false>(ctx, p, st);
+    return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
+}
+
+static int march2_resident_of(int C, int S, bool am) {
+    if (am) {
+        if (C == 1) return S == 1 ? march2_resident<1, 1, true>() : march2_resident<1, 2, true>();
+        return S == 1 ? march2_resident<3, 1, true>() : march2_resident<3, 2, true>();
+    }
+    if (C == 1) return S == 1 ? march2_resident<1, 1, false>() : march2_resident<1, 2, false>();
+    return S == 1 ? march2_resident<3, 1, false>() : march2_resident<3, 2, false>();
+}
+
+// which kernel runs the value + gradient calls: the single-warp kernel (default) or the two-warp producer / consumer pair
+static bool use_march_v1() {
+    static const bool v1 = [] { const char* e = getenv("MD2_MARCH_V1"); return e && atoi(e) != 0; }();
+    return v1;
+}
+
 static int march_resident_of(int C, int S, bool bwd) {
     if (bwd) {
         if (C == 1) return S == 1 ? march_resident<1, 1, true>() : march_resident<1, 2, true>();
@@ -895,7 +980,8 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     p.mode = mode;
     fill_pose_io(d, p.pose);
 
-    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, march_resident_of(C, S, bwd), p.m_group);
+    const bool v2 = bwd && !use_march_v1();
+    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, v2 ? march2_resident_of(C, S, d->automask != nullptr) : march_resident_of(C, S, bwd), p.m_group);
     if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] chunk height %d, %d groups of short last chunks per (scale, image)\n", p.m_R, p.m_group);
     const int tiles = cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
     const int NP = NSTAT + 12 * S;
@@ -953,7 +1039,17 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
         ctx->prof_used += 2;
         MD2_CHECK(cudaEventRecord(ev0, st));
     }
-    if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
+    if (v2) {
+        // the optional visualisation outputs of train_loss (src/training.jl:34-37,71-74; every 50th step of the reference's
+        // loop) are written by the forward-only kernel; the value + gradient kernel does not carry them
+        if (d->viz_loss || d->viz_warped[0] || (S > 1 && d->viz_warped[S - 1])) {
+            FusedParams pf = p;
+            pf.m_R = choose_march_rows(W, H, L * N, false, ctx->sm_count, march_resident_of(C, S, false), pf.m_group);
+            if (dispatch_march<false>(ctx, C, S, pf, st)) return 1;
+        }
+        if (dispatch_march2(ctx, C, S, p, st)) return 1;
+    }
+    else if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
     else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
     {   // loss / statistics, pose gradients, adjoint of the upsample for the low-res decoder scales

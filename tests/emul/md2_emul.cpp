@@ -15,6 +15,7 @@
 #define MD2_WARP_EMU 1
 #include "warp_emu.h"
 #include "../../monodepth2.jl_b200/csrc/md2_march.cuh"
+#include "../../monodepth2.jl_b200/csrc/md2_march2.cuh"
 
 using namespace md2;
 
@@ -56,6 +57,37 @@ static void run_march(const FusedParams& p, std::vector<float>& sums) {
     }
 }
 
+// single-warp marching kernel (md2_march2.cuh): one warp of lockstep fibers walks all work items of a (scale, image)
+template <int C, int S, bool AM>
+static void run_march2(const FusedParams& p, std::vector<float>& sums) {
+    using M = March2<C, S, AM>;
+    const int NP = M::NPART;
+    const int strips = (p.W + M::OW - 1) / M::OW, chunks = (p.H + p.m_R - 1) / p.m_R;
+    sums.assign((size_t)p.L * p.N * NP, 0.f);
+    std::vector<float> wsm(M::SMEM_FLOATS + 4);
+    float* wsm_al = (float*)(((uintptr_t)wsm.data() + 15) & ~(uintptr_t)15);
+    WarpEmu emu;
+    std::vector<float> lane_v((size_t)32 * 32);
+    for (int z = 0; z < p.L * p.N; ++z) {
+        for (int k = 0; k < M::SMEM_FLOATS; ++k) wsm_al[k] = NAN;   // poison: catches reads of never-written slots
+        float* su = sums.data() + (size_t)z * NP;
+        emu.run(32, [&](int tid) {
+            const int lane = tid & 31;
+            for (int cy = 0; cy < chunks; ++cy)
+                for (int sx = 0; sx < strips; ++sx) {
+                    float v[32];
+                    M::run(p, sx, cy, z, lane, wsm_al, v);
+                    for (int k = 0; k < 32; ++k) lane_v[(size_t)tid * 32 + k] = v[k];
+                    emu_ballot(0);
+                    if (tid == 0)
+                        for (int t = 0; t < 32; ++t)
+                            for (int k = 0; k < NP; ++k) su[k] += lane_v[(size_t)t * 32 + k];
+                    emu_ballot(0);
+                }
+        });
+    }
+}
+
 template <bool BWD>
 static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums, int variant) {
     if (variant == 1) {
@@ -63,6 +95,14 @@ static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums
         if (C == 1 && S == 2) { run_march<1, 2, BWD>(p, sums); return 0; }
         if (C == 3 && S == 1) { run_march<3, 1, BWD>(p, sums); return 0; }
         if (C == 3 && S == 2) { run_march<3, 2, BWD>(p, sums); return 0; }
+        return 1;
+    }
+    if (variant == 2 && BWD) {
+        const bool am = p.automask != nullptr;
+        if (C == 1 && S == 1) { if (am) run_march2<1, 1, true>(p, sums); else run_march2<1, 1, false>(p, sums); return 0; }
+        if (C == 1 && S == 2) { if (am) run_march2<1, 2, true>(p, sums); else run_march2<1, 2, false>(p, sums); return 0; }
+        if (C == 3 && S == 1) { if (am) run_march2<3, 1, true>(p, sums); else run_march2<3, 1, false>(p, sums); return 0; }
+        if (C == 3 && S == 2) { if (am) run_march2<3, 2, true>(p, sums); else run_march2<3, 2, false>(p, sums); return 0; }
         return 1;
     }
     return 1;
@@ -137,6 +177,11 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
     p.stats = stats.data();
     std::vector<float> sums;
     const int NP = NSTAT + 12 * S;
+    if (bwd && variant == 2 && (p.viz_loss || p.viz_warped[0] || p.viz_warped[1])) {
+        // as run_vsl on the device: the visualisation outputs come from the forward-only kernel
+        std::vector<float> tmp;
+        if (dispatch<false>(C, S, p, tmp, 1)) return 1;
+    }
     if (bwd ? dispatch<true>(C, S, p, sums, variant) : dispatch<false>(C, S, p, sums, variant)) return 1;
     if (bwd)   // adjoint of the upsample for the low-res scales (down_adjoint_kernel on the device)
         for (int l = 0; l < L; ++l) {
@@ -173,3 +218,4 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
 
 extern "C" int md2_emul_vsl(const md2_vsl_desc* d, int mode, float gloss) { return emul_vsl(d, mode, gloss, 0, 0); }
 extern "C" int md2_emul_march(const md2_vsl_desc* d, int mode, float gloss, int R) { return emul_vsl(d, mode, gloss, 1, R); }
+extern "C" int md2_emul_march2(const md2_vsl_desc* d, int mode, float gloss, int R) { return emul_vsl(d, mode, gloss, 2, R); }

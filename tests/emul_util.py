@@ -15,7 +15,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "monodepth2.jl_b200", "csrc")
 
 def build_emul():
     srcs = [os.path.join(EMUL_DIR, "md2_emul.cpp"), os.path.join(EMUL_DIR, "warp_emu.h"), os.path.join(CSRC, "md2_fused.cuh"),
-            os.path.join(CSRC, "md2_march.cuh"), os.path.join(CSRC, "md2_math.cuh")]
+            os.path.join(CSRC, "md2_march.cuh"), os.path.join(CSRC, "md2_march2.cuh"), os.path.join(CSRC, "md2_math.cuh")]
     if os.path.exists(EMUL_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMUL_SO) for s in srcs):
         return EMUL_SO
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", EMUL_SO,
@@ -26,11 +26,12 @@ def build_emul():
 def emul_vsl(x, disps, rvecs, tvecs, K, invK, *, mode=2, gloss=1.0, target_id=1, source_ids=(0, 2),
              scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3,
              automask=None, normalize=True, smooth_weight=None, loss_scale=None, grad_source=True, saved=None,
-             viz=False, variant="march", R=32):
+             viz=False, variant="march2", R=32):
     """CPU float32 tensors in, dict of outputs out (same maths as the CUDA fused path)."""
     lib = C.CDLL(build_emul())
     lib.md2_emul_vsl.argtypes = [C.POINTER(L.VslDesc), C.c_int, C.c_float]
     lib.md2_emul_march.argtypes = [C.POINTER(L.VslDesc), C.c_int, C.c_float, C.c_int]
+    lib.md2_emul_march2.argtypes = [C.POINTER(L.VslDesc), C.c_int, C.c_float, C.c_int]
     N, F, Cc, H, W = x.shape
     S, Ls = len(source_ids), len(disps)
     x = x.contiguous()
@@ -60,7 +61,9 @@ def emul_vsl(x, disps, rvecs, tvecs, K, invK, *, mode=2, gloss=1.0, target_id=1,
         grad_disparity=out["gdisp"], grad_rot=out["grvec"], grad_trans=out["gtvec"],
         grad_source=[out["gx"][:, i] for i in source_ids] if grad_source else None,
         viz_warped=out.get("viz_warped"), viz_loss=out.get("viz_loss"), saved=out["saved"], shape=(N, Cc, H, W))
-    if variant == "march":
+    if variant == "march2" and mode != 0:
+        rc = lib.md2_emul_march2(C.byref(desc), mode, gloss, R)
+    elif variant in ("march", "march2"):
         rc = lib.md2_emul_march(C.byref(desc), mode, gloss, R)
     else:
         rc = lib.md2_emul_vsl(C.byref(desc), mode, gloss)
