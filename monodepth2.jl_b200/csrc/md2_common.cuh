@@ -29,7 +29,7 @@ struct md2_ctx {
     int device;
     int64_t launches;
     int sm_count = 148;
-    int pose_slot = 0;   // this ctx's slot in the constant-memory pose table (md2_march.cuh)
+    int64_t ws_gen = 0;  // bumped whenever a workspace slot is (re)allocated: captured CUDA graphs hold the old pointers
     md2::Workspace ws[MD2_WS_COUNT];
     // optional device timing of the dominant (fused tile) kernel, see md2_profile_*
     int prof_on = 0;
@@ -42,6 +42,20 @@ namespace md2 {
 
 // returns nullptr (and sets the error) on failure
 void* ws_get(md2_ctx* ctx, int slot, size_t bytes);
+
+// the C entry points make the ctx's device current for the duration of the call and restore the caller's device
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device); else if (err == cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define MD2_USE_DEVICE(ctx)                \
+    md2::DeviceGuard _dev_guard((ctx)->device); \
+    MD2_CHECK(_dev_guard.err)
 
 #define MD2_CHECK(expr)                                                                  \
     do {                                                                                 \

@@ -39,6 +39,7 @@ void* ws_get(md2_ctx* ctx, int slot, size_t bytes) {
         w.ptr = nullptr; w.bytes = 0;
     }
     size_t want = bytes + bytes / 4 + 256;
+    ctx->ws_gen++;
     cudaError_t e = cudaMalloc(&w.ptr, want);
     if (e != cudaSuccess) {
         set_error("workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
@@ -104,6 +105,31 @@ int launch_reduce_partials(md2_ctx* ctx, const float* partial, float* out0, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch: the three kernels of a call are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's blocks are scheduled (launch latency, block
+// set-up) while the previous kernel drains; pdl_wait() returns once the previous kernel has completed and its writes are
+// visible, pdl_trigger() lets the next kernel start launching.  MD2_PDL=0 falls back to plain stream order.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// bit 0: the marching kernel may overlap the prep kernel's tail, bit 1: the finish kernel the marching kernel's
+static int pdl_mask() {
+    static const int m = [] { const char* e = getenv("MD2_PDL"); return e ? atoi(e) : 0; }();
+    return m;
+}
+template <class... KArgs, class... Args>
+static cudaError_t launch_after(int pdl_bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() & pdl_bit) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // warp-level helpers
 // ------------------------------------------------------------------------------------------
 // Transpose-reduce: every lane passes 32 values; afterwards lane k holds the warp total of
@@ -150,7 +176,10 @@ __device__ __forceinline__ float sel4(const float (&h)[4], int k) {   // k is wa
     return k == 0 ? h[0] : (k == 1 ? h[1] : (k == 2 ? h[2] : h[3]));
 }
 
-// block 0 of an image: poses; blocks beyond the patch blocks: zero-fill of one slice of a source-gradient image
+// block 0 of an image: poses; blocks beyond the patch blocks: one slice of a source image each -- pull it into the L2
+// (the marching kernel's gathers are the only reads of the source frames: without this they are cold DRAM misses with
+// ~1000 cycles of latency in the middle of its software pipeline), and zero-fill the same slice of the source-gradient
+// image when the call asks for it (zero_blocks < 0: prefetch only)
 template <int C>
 __device__ __forceinline__ void prep_pose_or_zero(const FusedParams& p, int nblk, float* __restrict__ pose_ab, int zero_blocks) {
     const int n = blockIdx.y;
@@ -158,12 +187,20 @@ __device__ __forceinline__ void prep_pose_or_zero(const FusedParams& p, int nblk
         if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
         return;
     }
+    const bool do_zero = zero_blocks > 0;
+    zero_blocks = zero_blocks < 0 ? -zero_blocks : zero_blocks;
     const int zb = blockIdx.x - nblk - 1, s = zb / zero_blocks, sl = zb - s * zero_blocks;
-    if (!p.gsrc[s]) return;
-    float* g = p.gsrc[s] + (long long)n * p.src_ns[s];
     const int total = C * p.W * p.H;
     const int per = ((total + zero_blocks - 1) / zero_blocks + 3) & ~3;
     const int i0 = sl * per, i1 = min(i0 + per, total);
+    {   // one 128-byte line per thread
+        const float* src = p.src[s] + (long long)n * p.src_ns[s];
+        for (int i = i0 + 32 * (int)threadIdx.x; i < i1; i += 32 * (int)blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + i));
+        if (threadIdx.x == 0 && i1 > i0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (i1 - 1)));
+    }
+    if (!do_zero || !p.gsrc[s]) return;
+    float* g = p.gsrc[s] + (long long)n * p.src_ns[s];
     if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
         for (int i = i0 + 4 * (int)threadIdx.x; i + 3 < i1; i += 4 * (int)blockDim.x) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = i0 + ((i1 - i0) & ~3) + (int)threadIdx.x; i < i1; i += blockDim.x) g[i] = 0.f;
@@ -177,6 +214,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_c
                                                                int nblk, int do_stats, float* __restrict__ pose_ab,
                                                                float* __restrict__ part, int zero_blocks) {
     const int n = blockIdx.y;
+    pdl_trigger();
     if (blockIdx.x == 0 || (int)blockIdx.x > nblk) { prep_pose_or_zero<C>(p, nblk, pose_ab, zero_blocks); return; }
     const int W = p.W, H = p.H, HW = W * H;
     __shared__ float red[PREP_WARPS][3 * LMAX];
@@ -327,6 +365,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
     constexpr int NS = NLOW + 1;
     static_assert(3 * NS <= 16, "one transpose-reduce of 16 values");
     const int n = blockIdx.y;
+    pdl_trigger();
     if (blockIdx.x == 0 || (int)blockIdx.x > nblk) { prep_pose_or_zero<C>(p, nblk, pose_ab, zero_blocks); return; }
     __shared__ float red[PREP_WARPS][16];
     const int W = p.W, H = p.H, HW = W * H;
@@ -465,6 +504,8 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int 
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x & 31;
     int role = threadIdx.x >> 5;            // 0: warp F (forward), 1: warp B (backward)
+    pdl_trigger();
+    pdl_wait();
     // segments = (strip, chunk) of a (scale, image); an item is one full-height chunk, or -- when the image
     // height is not a multiple of the chunk height -- a group of short last chunks of neighbouring strips (the
     // `strips` short chunks of a (scale, image) are cut into `lgroups` groups), so that all items are about
@@ -522,6 +563,8 @@ march2_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int
     using M = March2<C, S, AM>;
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();                                          // the prep kernel's outputs (poses, upsampled disparities, sums)
     const int ipg = strips * chunks;                     // segments (= partial-sum rows) per (scale, image)
     const int n_full = strips * q_full;
     const int ipi = n_full + (chunks > q_full ? lgroups : 0);   // items per (scale, image)
@@ -567,6 +610,7 @@ constexpr int FIN_THREADS = 128;  // small blocks: the whole grid is resident at
 __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd, int low_rows) {
     extern __shared__ __align__(16) float vrow[];   // [W rounded up to 4] (adjoint blocks)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
     const int LN = p.L * p.N;
     int b = blockIdx.x;
     if (b == 0) {
@@ -768,7 +812,7 @@ static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     const long long items = ((long long)strips * q_full + (chunks > q_full ? lgroups : 0)) * p.L * p.N;
     const long long cap = (long long)ctx->sm_count * march_resident<C, S, BWD>();
     const int blocks = (int)(items < cap ? items : cap);
-    march_kernel<C, S, BWD><<<blocks, M::THREADS, smem, st>>>(p, strips, chunks, q_full, lgroups);
+    MD2_CHECK(launch_after(1, march_kernel<C, S, BWD>, dim3(blocks), dim3(M::THREADS), smem, st, p, strips, chunks, q_full, lgroups));
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -798,7 +842,7 @@ static int launch_march2(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     const long long items = ((long long)strips * q_full + (chunks > q_full ? lgroups : 0)) * p.L * p.N;
     const long long cap = (long long)ctx->sm_count * march2_resident<C, S, AM>();
     const int blocks = (int)(items < cap ? items : cap);
-    march2_kernel<C, S, AM><<<blocks, M::THREADS, smem, st>>>(p, strips, chunks, q_full, lgroups);
+    MD2_CHECK(launch_after(1, march2_kernel<C, S, AM>, dim3(blocks), dim3(M::THREADS), smem, st, p, strips, chunks, q_full, lgroups));
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -929,7 +973,7 @@ enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FWDBWD = 2 };
 
 int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStream_t st) {
     if (check_desc(d, true)) return 1;
-    MD2_CHECK(cudaSetDevice(ctx->device));
+    MD2_USE_DEVICE(ctx);
     const int W = d->W, H = d->H, N = d->N, L = d->L, S = d->S, C = d->C;
     const bool bwd = mode != MODE_FWD;
 
@@ -985,16 +1029,15 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] chunk height %d, %d groups of short last chunks per (scale, image)\n", p.m_R, p.m_group);
     const int tiles = cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
     const int NP = NSTAT + 12 * S;
-    // this call's pose rows in the constant-memory table: a slot per ctx (re-entrant across ctxs)
-    const int pose_floats = 12 * S * N;
-    MD2_REQUIRE(pose_floats <= POSE_CONST_FLOATS, "S*N too large for one call (max 1024 source-image pairs)");
-    p.pose_slot = pose_floats <= POSE_SLOT_FLOATS ? ctx->pose_slot * POSE_SLOT_FLOATS : 0;
+    p.pose_slot = 0;
     // prep kernel partition: 31-column x 4-row patches, one warp each, eight warps per block
     const int prep_strips = cdiv(W, PREP_COLS), prep_chunks = cdiv(H, PREP_ROWS);
     const int prep_nblk = cdiv((long long)prep_strips * prep_chunks, PREP_WARPS);
     const int do_stats = mode == MODE_FWDBWD;
     const bool zero_gs = bwd && d->zero_grad_source != 0;
-    const int zero_blocks = zero_gs ? max(1, min(64, cdiv((long long)C * W * H, 8192))) : 0;
+    // slices of the source images per (source, image): L2 prefetch (value + gradient calls) and optional zero-fill
+    const int aux_blocks = bwd ? max(1, min(64, cdiv((long long)C * W * H, 8192))) : 0;
+    const int zero_blocks = zero_gs ? aux_blocks : -aux_blocks;
     float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
@@ -1009,7 +1052,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
 
     {   // prep: poses, upsampled low-res disparities (+ smoothness sums for the fused fwd+bwd, + zero-fill)
         const int nb = (do_stats || n_low) ? prep_nblk : 0;
-        dim3 g(1 + nb + S * zero_blocks, N);
+        dim3 g(1 + nb + S * aux_blocks, N);
         // usual decoder layout (low-res scales first, one full-resolution scale last, fused fwd+bwd): the lean kernel
         bool usual = do_stats && nb > 0 && L >= 1 && L <= 4 && n_low == L - 1 && d->disp_w[L - 1] == W && d->disp_h[L - 1] == H;
         if (getenv("MD2_PREP_GENERIC")) usual = false;
@@ -1023,8 +1066,6 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
 #undef MD2_PREP
         MD2_LAUNCH_CHECK(ctx);
     }
-    MD2_CHECK(cudaMemcpyToSymbolAsync(c_pose, pose_ab, sizeof(float) * pose_floats, sizeof(float) * p.pose_slot,
-                                      cudaMemcpyDeviceToDevice, st));
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) {
@@ -1054,7 +1095,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     if (ev1) MD2_CHECK(cudaEventRecord(ev1, st));
     {   // loss / statistics, pose gradients, adjoint of the upsample for the low-res decoder scales
         const int blocks = 1 + (bwd ? S * N + low_rows * N : 0);
-        finish_kernel<<<blocks, FIN_THREADS, sizeof(float) * ((W + 3) & ~3), st>>>(p, NP, tiles, bwd ? 1 : 0, low_rows);
+        MD2_CHECK(launch_after(2, finish_kernel, dim3(blocks), dim3(FIN_THREADS), sizeof(float) * ((W + 3) & ~3), st, p, NP, tiles, bwd ? 1 : 0, low_rows));
         MD2_LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -1167,7 +1208,7 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const __grid_constant__ F
 
 static int run_warp(md2_ctx* ctx, const md2_vsl_desc* d, float* const* out, const float* const* gout, cudaStream_t st) {
     if (check_desc(d, false)) return 1;
-    MD2_CHECK(cudaSetDevice(ctx->device));
+    MD2_USE_DEVICE(ctx);
     const int W = d->W, H = d->H, N = d->N, S = d->S, C = d->C;
     const long long HW = (long long)W * H;
     const bool bwd = gout != nullptr;
@@ -1240,10 +1281,7 @@ int md2_create(int device, md2_ctx** out) {
         return md2::set_error("md2_create: no CUDA device (%s); this library has no CPU fallback",
                               cudaGetErrorString(e));
     if (device < 0 || device >= count) return md2::set_error("md2_create: bad device %d", device);
-    MD2_CHECK(cudaSetDevice(device));
     md2_ctx* c = new md2_ctx();
-    static std::atomic<int> next_slot{0};
-    c->pose_slot = next_slot.fetch_add(1) % (md2::POSE_CONST_FLOATS / md2::POSE_SLOT_FLOATS);
     c->device = device;
     c->launches = 0;
     c->sm_count = 148;
@@ -1254,7 +1292,7 @@ int md2_create(int device, md2_ctx** out) {
 
 int md2_destroy(md2_ctx* ctx) {
     if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
+    md2::DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < MD2_WS_COUNT; ++i)
         if (ctx->ws[i].ptr) cudaFree(ctx->ws[i].ptr);
@@ -1313,7 +1351,7 @@ int md2_warp_bwd(md2_ctx* ctx, const md2_vsl_desc* d, const float* const* gout, 
 int md2_upsample_bilinear_fwd(md2_ctx* ctx, const float* in, float* out, int32_t w, int32_t h, int32_t W, int32_t H,
                               int32_t CN, md2_stream st) {
     MD2_REQUIRE(ctx != nullptr, "null ctx");
-    MD2_CHECK(cudaSetDevice(ctx->device));
+    MD2_USE_DEVICE(ctx);
     MD2_REQUIRE(in && out && w > 0 && h > 0 && W > 0 && H > 0 && CN > 0, "bad arguments");
     md2::upsample_kernel<<<md2::cdiv((long long)W * H * CN, 256), 256, 0, (cudaStream_t)st>>>(in, out, w, h, W, H, CN);
     MD2_LAUNCH_CHECK(ctx);
@@ -1322,7 +1360,7 @@ int md2_upsample_bilinear_fwd(md2_ctx* ctx, const float* in, float* out, int32_t
 int md2_upsample_bilinear_bwd(md2_ctx* ctx, const float* gout, float* gin, int32_t w, int32_t h, int32_t W, int32_t H,
                               int32_t CN, md2_stream st) {
     MD2_REQUIRE(ctx != nullptr, "null ctx");
-    MD2_CHECK(cudaSetDevice(ctx->device));
+    MD2_USE_DEVICE(ctx);
     MD2_REQUIRE(gout && gin && w > 0 && h > 0 && W > 0 && H > 0 && CN > 0, "bad arguments");
     md2::upsample_bwd_kernel<<<md2::cdiv((long long)w * h * CN, 128), 128, 0, (cudaStream_t)st>>>(gout, gin, w, h, W, H, CN);
     MD2_LAUNCH_CHECK(ctx);

@@ -31,6 +31,7 @@ struct HostPath {
     md2_vsl_desc key;              // descriptor the graph was captured for
     int key_groups = 0;
     float key_seed = 0.f;
+    int64_t key_ws_gen = -1;       // ctx workspace generation the graph was captured with (the graph holds those pointers)
     bool have_key = false;
 };
 
@@ -91,6 +92,7 @@ struct Mirror {
     size_t small_in_floats, small_out_floats;
     bool xcontig;                  // frames travel as whole images of `xstride` floats starting at host pointer xbase
     const float* xbase; float* xall; int64_t xstride;
+    int64_t xspan;                 // floats from xbase to the end of the last frame in use of one image
 };
 
 static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
@@ -109,7 +111,7 @@ static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
         }
         const int64_t st = d->target_image_stride;
         m.xcontig = same && st >= (int64_t)img && (hi - lo) + (int64_t)img <= st && st <= 4 * (int64_t)img * (d->S + 1);
-        m.xbase = lo; m.xstride = st;
+        m.xbase = lo; m.xstride = st; m.xspan = (hi - lo) + (int64_t)img;
     }
     if (m.xcontig) {
         m.xall = c.take(N * (size_t)m.xstride);
@@ -198,7 +200,10 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
         const int n0 = (int)((long long)N * k / groups), n1 = (int)((long long)N * (k + 1) / groups), nk = n1 - n0;
         // ---- inputs of group k: frames (strided host views -> dense), full-resolution disparities, automask
         if (m.xcontig) {
-            MD2_H2D(m.xall + (size_t)n0 * m.xstride, m.xbase + (size_t)n0 * m.xstride, sizeof(float) * (size_t)nk * m.xstride);
+            // (not nk * xstride: xbase need not be the first frame of the per-image block, and the host buffer ends with
+            // the last frame of the last image)
+            MD2_H2D(m.xall + (size_t)n0 * m.xstride, m.xbase + (size_t)n0 * m.xstride,
+                    sizeof(float) * ((size_t)(nk - 1) * m.xstride + (size_t)m.xspan));
         } else {
             MD2_CHECK(cudaMemcpy2DAsync(m.tgt + n0 * img, imgb, d->target + (size_t)n0 * d->target_image_stride,
                                         sizeof(float) * d->target_image_stride, imgb, nk, cudaMemcpyHostToDevice, h->s_in));
@@ -274,7 +279,7 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
     if (groups < 1) groups = 1;
     if (groups > HOST_MAX_GROUPS) groups = HOST_MAX_GROUPS;
     if (groups > d->N) groups = d->N;
-    MD2_CHECK(cudaSetDevice(ctx->device));
+    MD2_USE_DEVICE(ctx);
     MD2_REQUIRE(!ctx->prof_on, "kernel profiling (md2_profile_enable) is not available on the host entry point");
     HostPath* h = host_path(ctx);
     if (!h) return 1;
@@ -303,7 +308,8 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
             memcpy(q, d->trans[s], sizeof(float) * 3 * d->N); q += (size_t)3 * d->N;
         }
     }
-    const bool same = h->have_key && h->exec && h->key_groups == groups && h->key_seed == seed && memcmp(&h->key, d, sizeof(*d)) == 0;
+    const bool same = h->have_key && h->exec && h->key_groups == groups && h->key_seed == seed && h->key_ws_gen == ctx->ws_gen &&
+                      memcmp(&h->key, d, sizeof(*d)) == 0;
     if (!same) {
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
         h->have_key = false;
@@ -331,6 +337,7 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
             cudaGraphDestroy(graph);
             if (ie != cudaSuccess) { h->exec = nullptr; return set_error("host path: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
             memcpy(&h->key, d, sizeof(*d)); h->key_groups = groups; h->key_seed = seed; h->have_key = true;   // (byte copy: the reuse test is a memcmp)
+            h->key_ws_gen = ctx->ws_gen;   // any later growth of a ctx workspace (a device call with a larger shape) invalidates the graph
         }
     } else {
         MD2_CHECK(cudaGraphLaunch(h->exec, h->s_run));

@@ -99,12 +99,9 @@ inline void g_pf(const float*) {}
 #define MD2_POSE(p, idx) ((p).pose_ab[(idx)])
 #else
 #define MD2_DEV __device__ __forceinline__
-// pre-composed pose rows (A | b per source and image), read through the constant cache so that the
-// warp-uniform values live in uniform registers / constant operands instead of 24 vector registers
-constexpr int POSE_CONST_FLOATS = 12288;   // 48 KB: S*N <= 1024 per call
-constexpr int POSE_SLOT_FLOATS = 3072;     // per-ctx slot (S*N <= 256); larger calls use the whole table
-__constant__ float c_pose[POSE_CONST_FLOATS];
-#define MD2_POSE(p, idx) (c_pose[(idx)])
+// pre-composed pose rows (A | b per source and image) of the forward-only marching kernel: warp-uniform loads from the
+// ctx's pose table (L1-resident; one table per ctx, so calls on different ctxs / streams never share state)
+#define MD2_POSE(p, idx) (__ldg((p).pose_ab + (idx)))
 MD2_DEV float w_shfl(float v, int src, int) { return __shfl_sync(0xffffffffu, v, src); }
 MD2_DEV int w_shfl(int v, int src, int) { return __shfl_sync(0xffffffffu, v, src); }
 MD2_DEV float w_up(float v, int) { return __shfl_up_sync(0xffffffffu, v, 1); }

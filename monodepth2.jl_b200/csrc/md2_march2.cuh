@@ -112,10 +112,10 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 #endif
 
 #ifndef MD2_M2_MAXREG_C1
-#define MD2_M2_MAXREG_C1 168
+#define MD2_M2_MAXREG_C1 128
 #endif
 #ifndef MD2_M2_MAXREG_C3
-#define MD2_M2_MAXREG_C3 255
+#define MD2_M2_MAXREG_C3 192
 #endif
 
 // AM: the call has an automask map (src/training.jl:60-62)
@@ -140,9 +140,11 @@ struct March2 {
     static constexpr int H_X = 0, H_XX = S * C, H_XY = 2 * S * C, H_Y = 3 * S * C, H_YY = H_Y + C;
     static constexpr int NHF = H_YY + C;
     static constexpr int NH4 = (NHF + 3) / 4;
-    static constexpr int SLOT4 = NP4 + NH4;              // Vec4 per lane and slot
-    static constexpr int NSLOT = 4;                      // rows i-2 .. i+1 are in flight
-    static constexpr int SMEM_FLOATS = NSLOT * SLOT4 * 32 * 4;
+    static constexpr int NSLOT = 4;                      // pixel packets of rows i-2 .. i+1 are in flight
+    static constexpr int NHIST = 2;                      // window sums of rows i-2, i-1 (row i takes the slot of row i-2 once that has been read)
+    static constexpr int HIST0 = NSLOT * NP4 * 32;       // Vec4 index of the history region
+    static constexpr int TOTAL4 = NSLOT * NP4 + NHIST * NH4;   // Vec4 per lane
+    static constexpr int SMEM_FLOATS = TOTAL4 * 32 * 4;
     static constexpr int THREADS = 32;
     static constexpr int MAXREG = C == 1 ? MD2_M2_MAXREG_C1 : MD2_M2_MAXREG_C3;
     static_assert(P_U + S <= NE4 * 4 && P_V + S <= NE4 * 4 && P_OFF + S <= NE4 * 4, "u, v, off must fit the early words");
@@ -194,7 +196,8 @@ struct March2 {
         float warp_sum;
     };
 
-    static MD2_DEV int slot_vec(int row) { return (row & (NSLOT - 1)) * (SLOT4 * 32); }   // Vec4 index of a slot's first word
+    static MD2_DEV int slot_vec(int row) { return (row & (NSLOT - 1)) * (NP4 * 32); }           // Vec4 index of the first word of a row's pixel packet
+    static MD2_DEV int hist_vec(int row) { return HIST0 + (row & (NHIST - 1)) * (NH4 * 32); }   // ... of a row's window sums
 
     // ---- A(row): geometry of a row from the disparity / target loaded one iteration ago; issues the gathers of that row
     // and the raw loads of the next one; writes the early part of the row's pixel packet into slot `it_row` ----
@@ -282,7 +285,7 @@ struct March2 {
         // window-sum history of rows i-2, i-1 (for W)
         float ha[NH4 * 4], hb[NH4 * 4];
         {
-            const int sa = slot_vec(it - 2) + NP4 * 32, sb = slot_vec(it - 1) + NP4 * 32;
+            const int sa = hist_vec(it - 2), sb = hist_vec(it - 1);
 #pragma unroll
             for (int w4 = 0; w4 < NH4; ++w4) {
                 const Vec4 a4 = s_ld4(c.rr, sa + w4 * 32), b4 = s_ld4(c.rr, sb + w4 * 32);
@@ -343,7 +346,7 @@ struct March2 {
 #pragma unroll
                 for (int s = 0; s < S; ++s) { hs[H_X + ch * S + s] = hx[ch].v[s]; hs[H_XX + ch * S + s] = hxx[ch].v[s]; hs[H_XY + ch * S + s] = hxy[ch].v[s]; }
             }
-            const int sc = slot_vec(it) + NP4 * 32;
+            const int sc = hist_vec(it);   // (= the slot of row i-2, which was read at the top of this iteration)
 #pragma unroll
             for (int w4 = 0; w4 < NH4; ++w4) {
                 Vec4 c4; c4.x = hs[4 * w4]; c4.y = hs[4 * w4 + 1]; c4.z = hs[4 * w4 + 2]; c4.w = hs[4 * w4 + 3];
@@ -561,6 +564,8 @@ struct March2 {
 #pragma unroll
                     for (int s = 0; s < S; ++s) act[s] = act[s] || (ibar[ch].v[s] != 0.f);
                 }
+                // (merging a pixel's right taps into the right-hand lane's left taps by shuffle -- two atomics per pixel and
+                // source instead of four -- was measured slower here, as in the two-warp kernel: 62.2 vs 59.5 us at 416x128x8)
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     if (act[s]) {   // (ptxas turns predicated atomics into one branch each: one region per source instead)
@@ -667,7 +672,7 @@ struct March2 {
         {   // the ring starts out as zeros: warm-up rows read slots that this item has not written yet
             Vec4 z4; z4.x = z4.y = z4.z = z4.w = 0.f;
 #pragma unroll 4
-            for (int w4 = 0; w4 < NSLOT * SLOT4; ++w4) s_st4(c.rr, w4 * 32, z4);
+            for (int w4 = 0; w4 < TOTAL4; ++w4) s_st4(c.rr, w4 * 32, z4);
         }
         Carry k;
 #pragma unroll

@@ -539,7 +539,7 @@ __global__ void smooth_bwd_kernel(const float* __restrict__ disp, const float* _
 // ------------------------------------------------------------------------------------------
 using namespace md2;
 #define ST ((cudaStream_t)st)
-#define CTX_OK() do { MD2_REQUIRE(ctx != nullptr, "null ctx"); MD2_CHECK(cudaSetDevice(ctx->device)); } while (0)
+#define CTX_OK() MD2_REQUIRE(ctx != nullptr, "null ctx"); MD2_USE_DEVICE(ctx)
 
 static inline void depth_ab(float min_depth, float max_depth, float& a, float& b) {
     const float mind = (float)(1.0 / (double)max_depth), maxd = (float)(1.0 / (double)min_depth);
