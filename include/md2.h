@@ -160,6 +160,15 @@ typedef struct md2_vsl_desc {
     float* viz_loss;                        /* nullable (W,H,1,N): warp-loss map, last scale */
     float* saved;                           /* nullable (4,N,L): fwd -> bwd statistics */
     int32_t zero_grad_source;               /* != 0: the library zero-fills grad_source first (no caller memset) */
+    /* Optional test hook (NULL in production; value + gradient calls with S = 2 only): the discrete decisions the
+     * kernel took at every pixel of every scale, int32 (1+S, W, H, N, L) in Julia order, i.e. word k of pixel (x,y) of
+     * image n at scale l is debug_choices[(((l*N + n)*H + y)*W + x)*(1+S) + k]:
+     *   word 0: bits 0-1 selected source + 1 (0 = automask won); bit 2 + s*C + c: the SSIM clamp passed the gradient;
+     *           bits 8 + 2*(s*C + c): sign of (warped - target) used by the L1 term (0: zero, 1: +, 2: -);
+     *           bits 20-21 / 22-23: sign of d(x,y) - d(x+1,y) / d(x,y) - d(x,y+1) used by the smoothness term
+     *   word 1+s: x0 | y0 << 14 | mask_x << 29 | mask_y << 30 of source s (0-based gather cell, clip-gradient masks)
+     * A parity test evaluates the float64 oracle with exactly these decisions forced (tests/test_gpu_forced.py). */
+    int32_t* debug_choices;
 } md2_vsl_desc;
 
 int md2_view_synthesis_loss_fwd(md2_ctx*, const md2_vsl_desc*, md2_stream);

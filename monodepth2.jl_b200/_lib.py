@@ -39,6 +39,7 @@ class VslDesc(C.Structure):
         ("viz_warped", c_void * MAX_S), ("viz_loss", c_void),
         ("saved", c_void),
         ("zero_grad_source", C.c_int32),
+        ("debug_choices", c_void),
     ]
 
 
@@ -64,7 +65,7 @@ def frame_view(x, idx):
 def make_vsl_desc(*, target, target_stride, sources, source_strides, disparities, K_cm, invK_cm, rot, trans,
                   pose_mode, invert, automask=None, min_depth=0.1, max_depth=100.0, smooth_weight, loss_scale,
                   normalize_disparity=True, loss=None, grad_disparity=None, grad_rot=None, grad_trans=None,
-                  grad_source=None, viz_warped=None, viz_loss=None, saved=None, zero_grad_source=False, shape):
+                  grad_source=None, viz_warped=None, viz_loss=None, saved=None, zero_grad_source=False, debug_choices=None, shape):
     """shape = (N, C, H, W).  `target`/`sources` are tensors whose data_ptr() is element
     (n=0,c=0,y=0,x=0) of an (N,C,H,W) view with per-image stride *_stride and dense C,H,W."""
     N, Cc, H, W = shape
@@ -109,6 +110,10 @@ def make_vsl_desc(*, target, target_stride, sources, source_strides, disparities
     d.viz_loss = _ptr(viz_loss)
     d.saved = _ptr(saved)
     d.zero_grad_source = int(bool(zero_grad_source))
+    if debug_choices is not None:
+        if debug_choices.dtype != torch.int32 or not debug_choices.is_contiguous():
+            raise TypeError("debug_choices: expected a contiguous int32 tensor")
+        d.debug_choices = debug_choices.data_ptr()
     return d
 
 

@@ -61,8 +61,8 @@ __global__ void upsample_kernel(const float* __restrict__ in, float* __restrict_
     const long long cn = i / ((long long)W * H);
     const float sx = up_scale(w, W), sy = up_scale(h, H);
     int x0, x1, y0, y1; float fx, fy;
-    up_taps(x, sx, w, x0, x1, fx);
-    up_taps(y, sy, h, y0, y1, fy);
+    up_taps(x, w, W, x0, x1, fx);
+    up_taps(y, h, H, y0, y1, fy);
     const float* b = in + cn * w * h;
     out[i] = bilerp(b[y0 * w + x0], b[y0 * w + x1], b[y1 * w + x0], b[y1 * w + x1], fx, fy);
 }
@@ -184,7 +184,9 @@ template <int C>
 __device__ __forceinline__ void prep_pose_or_zero(const FusedParams& p, int nblk, float* __restrict__ pose_ab, int zero_blocks) {
     const int n = blockIdx.y;
     if (blockIdx.x == 0) {
-        if ((int)threadIdx.x < p.S) prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12);
+        if ((int)threadIdx.x < p.S)
+            prepare_pose_one(p.pose, threadIdx.x, n, pose_ab + ((long long)threadIdx.x * p.N + n) * 12,
+                             pose_ab + ((long long)(p.S + threadIdx.x) * p.N + n) * 12);   // (the displacement table follows the A | b table)
         return;
     }
     const bool do_zero = zero_blocks > 0;
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_c
                 }
             } else {
                 int xa0, xa1, yb1; float fy0;
-                up_taps(gxc, p.usx[l], dw, xa0, xa1, fxu[l]);
-                up_taps(min(Y0, H - 1), p.usy[l], dh, yb[l], yb1, fy0);
+                up_taps(gxc, dw, W, xa0, xa1, fxu[l]);
+                up_taps(min(Y0, H - 1), dh, H, yb[l], yb1, fy0);
                 const float* dp = p.disp[l] + (long long)n * dw * dh;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -299,7 +301,6 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_c
             for (int r = 0; r <= PREP_ROWS; ++r) d[r] = q[l][r];
         } else {
             const int dh = p.dh[l];
-            const float usy = p.usy[l];
             float h[4];                                      // low-res rows yb .. yb+3, interpolated horizontally
 #pragma unroll
             for (int k = 0; k < 4; ++k) h[k] = fmaf(fxu[l], q[l][2 * k + 1] - q[l][2 * k], q[l][2 * k]);
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_kernel(const __grid_c
 #pragma unroll
             for (int r = 0; r <= PREP_ROWS; ++r) {
                 int ya0, ya1; float fyu;
-                up_taps(min(Y0 + r, H - 1), usy, dh, ya0, ya1, fyu);
+                up_taps(min(Y0 + r, H - 1), dh, H, ya0, ya1, fyu);
                 const float top = sel4(h, ya0 - yb[l]), bot = sel4(h, ya1 - yb[l]);
                 d[r] = fmaf(fyu, bot - top, top);
                 if (r < PREP_ROWS && Y0 + r < H && own_col) out[yo[r]] = d[r];
@@ -401,8 +402,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
     for (int l = 0; l < NLOW; ++l) {
         const int dw = p.dw[l], dh = p.dh[l];
         int xa0, xa1, yb1; float fy0;
-        up_taps(gxc, p.usx[l], dw, xa0, xa1, fxu[l]);
-        up_taps(min(Y0, H - 1), p.usy[l], dh, yb[l], yb1, fy0);
+        up_taps(gxc, dw, W, xa0, xa1, fxu[l]);
+        up_taps(min(Y0, H - 1), dh, H, yb[l], yb1, fy0);
         const float* dp = p.disp[l] + (long long)n * dw * dh;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -438,7 +439,6 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
             for (int r = 0; r <= PREP_ROWS; ++r) d[r] = dnat[r];
         } else {
             const int dh = p.dh[l];
-            const float usy = p.usy[l];
             float h[4];                                      // low-res rows yb .. yb+3, interpolated horizontally
 #pragma unroll
             for (int k = 0; k < 4; ++k) h[k] = fmaf(fxu[l], q[l][2 * k + 1] - q[l][2 * k], q[l][2 * k]);
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
 #pragma unroll
             for (int r = 0; r <= PREP_ROWS; ++r) {
                 int ya0, ya1; float fyu;
-                up_taps(min(Y0 + r, H - 1), usy, dh, ya0, ya1, fyu);
+                up_taps(min(Y0 + r, H - 1), dh, H, ya0, ya1, fyu);
                 const float top = sel4(h, ya0 - yb[l]), bot = sel4(h, ya1 - yb[l]);
                 d[r] = fmaf(fyu, bot - top, top);
                 if (r < PREP_ROWS && Y0 + r < H && own_col) out[yo[r]] = d[r];
@@ -556,11 +556,11 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int 
 // the single-warp marching kernel (md2_march2.cuh): value + gradient.  Persistent one-warp blocks, as many as are
 // resident on the whole GPU; block b walks the work items b, b + grid, ... (same items / partial-sum rows as above)
 // ------------------------------------------------------------------------------------------
-template <int C, int S, bool AM>
-__global__ void __maxnreg__((March2<C, S, AM>::MAXREG))
+template <int C, int S, bool AM, bool DBG>
+__global__ void __maxnreg__((March2<C, S, AM, DBG>::MAXREG))
 march2_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int q_full, int lgroups) {
     extern __shared__ __align__(16) float wsm[];
-    using M = March2<C, S, AM>;
+    using M = March2<C, S, AM, DBG>;
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x;
     pdl_trigger();
@@ -727,8 +727,8 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
     // trim the conservative row range to the rows that really contribute (weight != 0)
     {
         int y0, y1; float fy;
-        while (ylo < yhi) { up_taps(ylo, sy, h, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; ++ylo; }
-        while (yhi > ylo) { up_taps(yhi, sy, h, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; --yhi; }
+        while (ylo < yhi) { up_taps(ylo, h, H, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; ++ylo; }
+        while (yhi > ylo) { up_taps(yhi, h, H, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; --yhi; }
     }
     const int ny = yhi - ylo + 1;
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
         __syncthreads();
         if ((int)threadIdx.x < FIN_MAXROWS && base + (int)threadIdx.x < ny) {
             int y0, y1; float fy;
-            up_taps(ylo + base + threadIdx.x, sy, h, y0, y1, fy);
+            up_taps(ylo + base + threadIdx.x, h, H, y0, y1, fy);
             wys[threadIdx.x] = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
         }
         __syncthreads();
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
         float acc = 0.f;
         for (int x = xlo; x <= xhi; ++x) {
             int x0, x1; float fx;
-            up_taps(x, sx, w, x0, x1, fx);
+            up_taps(x, w, W, x0, x1, fx);
             const float wx = (x0 == xi ? 1.f - fx : 0.f) + (x1 == xi ? fx : 0.f);
             acc = fmaf(wx, vrow[x], acc);
         }
@@ -817,38 +817,43 @@ static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <int C, int S, bool AM>
+template <int C, int S, bool AM, bool DBG = false>
 static int march2_resident() {
-    using M = March2<C, S, AM>;
+    using M = March2<C, S, AM, DBG>;
     static int resident = 0;
     if (!resident) {
         const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
         int occ = 0;
-        if (cudaFuncSetAttribute(march2_kernel<C, S, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
-        cudaFuncSetAttribute(march2_kernel<C, S, AM>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2_kernel<C, S, AM>, M::THREADS, smem) != cudaSuccess) occ = 0;
+        if (cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
+        cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2_kernel<C, S, AM, DBG>, M::THREADS, smem) != cudaSuccess) occ = 0;
         resident = occ > 0 ? occ : 8;
         if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] march2_kernel<%d,%d>: %d resident warps/SM, %zu B smem/warp\n", C, S, resident, smem);
     }
     return resident;
 }
 
-template <int C, int S, bool AM>
+template <int C, int S, bool AM, bool DBG = false>
 static int launch_march2(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
-    using M = March2<C, S, AM>;
+    using M = March2<C, S, AM, DBG>;
     const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
     const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R), q_full = p.H / p.m_R;
     const int lgroups = p.m_group > 0 ? (p.m_group < strips ? p.m_group : strips) : 1;
     const long long items = ((long long)strips * q_full + (chunks > q_full ? lgroups : 0)) * p.L * p.N;
-    const long long cap = (long long)ctx->sm_count * march2_resident<C, S, AM>();
+    const long long cap = (long long)ctx->sm_count * march2_resident<C, S, AM, DBG>();
     const int blocks = (int)(items < cap ? items : cap);
-    MD2_CHECK(launch_after(1, march2_kernel<C, S, AM>, dim3(blocks), dim3(M::THREADS), smem, st, p, strips, chunks, q_full, lgroups));
+    MD2_CHECK(launch_after(1, march2_kernel<C, S, AM, DBG>, dim3(blocks), dim3(M::THREADS), smem, st, p, strips, chunks, q_full, lgroups));
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 static int dispatch_march2(md2_ctx* ctx, int C, int S, const FusedParams& p, cudaStream_t st) {
     const bool am = p.automask != nullptr;
+    if (p.dbg) {   // test hook (md2.h: debug_choices): the instantiations that also export the decisions
+        if (S != 2) return set_error("view_synthesis_loss: debug_choices needs S = 2");
+        if (C == 1) return am ? launch_march2<1, 2, true, true>(ctx, p, st) : launch_march2<1, 2, false, true>(ctx, p, st);
+        if (C == 3) return am ? launch_march2<3, 2, true, true>(ctx, p, st) : launch_march2<3, 2, false, true>(ctx, p, st);
+    }
     if (C == 1 && S == 1) return am ? launch_march2<1, 1, true>(ctx, p, st) : launch_march2<1, 1, false>(ctx, p, st);
     if (C == 1 && S == 2) return am ? launch_march2<1, 2, true>(ctx, p, st) : launch_march2<1, 2, false>(ctx, p, st);
     if (C == 3 && S == 1) return am ? launch_march2<3, 1, true>(ctx, p, st) : launch_march2<3, 1, false>(ctx, p, st);
@@ -988,6 +993,8 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     }
     p.viz_loss = d->viz_loss;
     p.automask = d->automask;
+    p.dbg = (bwd && !use_march_v1()) ? d->debug_choices : nullptr;
+    if (d->debug_choices) MD2_REQUIRE(p.dbg != nullptr, "debug_choices is served by the value + gradient calls only");
     {   // the reference rounds min_disp and max_disp to T first (src/utils.jl:176-178)
         const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
         p.depth_a = maxd - mind; p.depth_b = mind;
@@ -1038,12 +1045,12 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     // slices of the source images per (source, image): L2 prefetch (value + gradient calls) and optional zero-fill
     const int aux_blocks = bwd ? max(1, min(64, cdiv((long long)C * W * H, 8192))) : 0;
     const int zero_blocks = zero_gs ? aux_blocks : -aux_blocks;
-    float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 12 * S * N);
+    float* pose_ab = (float*)ws_get(ctx, MD2_WS_POSE, sizeof(float) * 24 * S * N);
     float* partial = (float*)ws_get(ctx, MD2_WS_PARTIAL, sizeof(float) * (size_t)tiles * L * N * NP);
     float* stats = (float*)ws_get(ctx, MD2_WS_STATS, sizeof(float) * (size_t)L * N * NSTAT);
     float* part2 = (float*)ws_get(ctx, MD2_WS_MISC, sizeof(float) * (size_t)prep_nblk * L * N * 4);
     if (!pose_ab || !partial || !stats || !part2) return 1;
-    p.pose_ab = pose_ab; p.partial = partial;
+    p.pose_ab = pose_ab; p.pose_e = pose_ab + (size_t)12 * S * N; p.partial = partial;
     p.stats = stats; p.stats_out = stats; p.saved = (mode == MODE_BWD) ? nullptr : d->saved;
     if (mode == MODE_BWD && d->saved) p.stats = d->saved;   // else the ctx holds the last forward's statistics
     p.loss = (mode == MODE_BWD) ? nullptr : d->loss;

@@ -32,6 +32,7 @@ struct FusedParams {
     float* gdisp[MAX_L];                // (N,dh,dw): written (full-res) / accumulated (low-res, pre-zeroed)
     const float* automask;              // (N,H,W) or null   (src/training.jl:60-62)
     const float* pose_ab;               // (S,N,12) pre-composed A|b
+    const float* pose_e;                // (S,N,12) the same as a displacement: E = A - I | b (precompose_e)
     const float* stats;                 // (L,N,NSTAT) forward sums, needed by the backward pass
     float* partial;                     // (L*N, segments, NPART) per-segment partial sums of the marching kernel
     float depth_a, depth_b;             // z = 1/(a d + b)   (src/utils.jl:175-179)
@@ -58,6 +59,7 @@ struct FusedParams {
     const float* prep_part;
     int prep_nblk;
     float usx[MAX_L], usy[MAX_L];       // up_scale(dw, W), up_scale(dh, H) of every scale (host-computed: no device divisions)
+    int* dbg;                           // optional test hook: the discrete decisions per pixel and scale (md2.h: debug_choices)
 };
 
 #if defined(__CUDA_ARCH__)
@@ -89,12 +91,11 @@ MD2_HD float sgnf(float v) { return (float)(v > 0.f) - (float)(v < 0.f); }
 
 // disparity of scale `l` at full-resolution pixel (gx,gy): direct read or on-the-fly
 // align-corners bilinear upsample (A17)
-MD2_HD float disp_fullres(const float* __restrict__ dp, int dw, int dh, bool native, float usx, float usy,
-                          int W, int gx, int gy) {
+MD2_HD float disp_fullres(const float* __restrict__ dp, int dw, int dh, bool native, int W, int H_, int gx, int gy) {
     if (native) return dp[gy * W + gx];
     int x0, x1, y0, y1; float fx, fy;
-    up_taps(gx, usx, dw, x0, x1, fx);
-    up_taps(gy, usy, dh, y0, y1, fy);
+    up_taps(gx, dw, W, x0, x1, fx);
+    up_taps(gy, dh, H_, y0, y1, fy);
     return bilerp(dp[y0 * dw + x0], dp[y0 * dw + x1], dp[y1 * dw + x0], dp[y1 * dw + x1], fx, fy);
 }
 
@@ -151,13 +152,13 @@ MD2_HD float upsample_adjoint_at(const float* __restrict__ g, int w, int h, int 
     float acc = 0.f;
     for (int y = ylo; y <= yhi; ++y) {
         int y0, y1; float fy;
-        up_taps(y, sy, h, y0, y1, fy);
+        up_taps(y, h, H, y0, y1, fy);
         const float wy = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
         if (wy == 0.f) continue;
         float row = 0.f;
         for (int x = xlo; x <= xhi; ++x) {
             int x0, x1; float fx;
-            up_taps(x, sx, w, x0, x1, fx);
+            up_taps(x, w, W, x0, x1, fx);
             const float wx = (x0 == xi ? 1.f - fx : 0.f) + (x1 == xi ? fx : 0.f);
             row = fmaf(wx, g[y * W + x], row);
         }
@@ -189,10 +190,10 @@ MD2_HD void stats_pixel_all(const FusedParams& p, int n, int gx, int gy, float* 
         const bool native = (dw == p.W && dh == p.H);
         const float* dp = p.disp[l] + (long long)n * dw * dh;
         const float usx = up_scale(dw, p.W), usy = up_scale(dh, p.H);
-        const float d = disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy);
+        const float d = disp_fullres(dp, dw, dh, native, p.W, p.H, gx, gy);
         v[3 * l + 2] += d;
-        if (hx) v[3 * l + 0] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx + 1, gy)) * wx;
-        if (hy) v[3 * l + 1] += fabsf(d - disp_fullres(dp, dw, dh, native, usx, usy, p.W, gx, gy + 1)) * wy;
+        if (hx) v[3 * l + 0] += fabsf(d - disp_fullres(dp, dw, dh, native, p.W, p.H, gx + 1, gy)) * wx;
+        if (hy) v[3 * l + 1] += fabsf(d - disp_fullres(dp, dw, dh, native, p.W, p.H, gx, gy + 1)) * wy;
     }
 }
 
@@ -260,7 +261,7 @@ MD2_HD void finalize_pose(const PoseIO& io, int s, int n, const double* G, const
 }
 
 // [composeT] + pre-composition of one (source, image)
-MD2_HD void prepare_pose_one(const PoseIO& io, int s, int n, float* ab) {
+MD2_HD void prepare_pose_one(const PoseIO& io, int s, int n, float* ab, float* eb = nullptr) {
     double K[9], Ki[9], R[9], t[3];
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) { K[3 * i + j] = (double)io.K[3 * j + i]; Ki[3 * i + j] = (double)io.invK[3 * j + i]; }
@@ -274,6 +275,7 @@ MD2_HD void prepare_pose_one(const PoseIO& io, int s, int n, float* ab) {
         compose_T(r, tv, io.invert[s], R, t);
     }
     precompose(K, Ki, R, t, ab);
+    if (eb) precompose_e(K, Ki, R, t, eb);
 }
 
 }  // namespace md2

@@ -101,6 +101,16 @@ template <int S> MD2_DEV SV<S> sv_rcp_acc(SV<S> x) {
 }
 
 MD2_DEV float f_fma_sat(float a, float b, float c) { return f_sat(fmaf(a, b, c)); }
+// floor to int32, saturating, NaN -> 0 (cvt.rmi.s32.f32)
+#if defined(MD2_WARP_EMU)
+MD2_DEV int f_floor_i(float x) {
+    if (!(x == x)) return 0;
+    const float f = floorf(x);
+    return f >= 2147483648.0f ? 2147483647 : (f <= -2147483648.0f ? (-2147483647 - 1) : (int)f);
+}
+#else
+MD2_DEV int f_floor_i(float x) { return __float2int_rd(x); }
+#endif
 
 // predicated global accesses of the row loop (no branch, no reconvergence point: the predicate rides on the instruction)
 #if defined(MD2_WARP_EMU)
@@ -111,6 +121,9 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 }
 #endif
 
+#ifndef MD2_M2_RC
+#define MD2_M2_RC 0
+#endif
 #ifndef MD2_M2_MAXREG_C1
 #define MD2_M2_MAXREG_C1 128
 #endif
@@ -118,8 +131,9 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 #define MD2_M2_MAXREG_C3 192
 #endif
 
-// AM: the call has an automask map (src/training.jl:60-62)
-template <int C, int S, bool AM>
+// AM: the call has an automask map (src/training.jl:60-62); DBG: test hook, also exports the discrete decisions of every
+// pixel (FusedParams::dbg, md2.h: debug_choices) -- a separate instantiation, the production kernels carry none of it
+template <int C, int S, bool AM, bool DBG = false>
 struct March2 {
     using V = SV<S>;
     static constexpr int HALO = 2;
@@ -169,7 +183,9 @@ struct March2 {
         float* gb[S];
         int has_gb;
         float rc[C];        // centring constant of the window sums
-        V apx[3], a1[3], bb[3];   // lane-constant part of A p, A[:,1], b   (cam = z (A p) + b per source)
+        V epx[3], e1[3], bb[3];   // lane-constant part of E p, E[:,1], b (+ eps in bb[2])   (cam = z (p + E p) + b per source, precompose_e)
+        float pxf;          // this lane's 1-based pixel column
+        int gx;             // ... 0-based
         float Wf, Hf, da, db;
         float kq;           // window column valid ? up_photo * alpha / C * (-1/2) * 2 : 0   (the coefficients carry a factor 1/2)
         float cl1;          // up_photo * (1 - alpha) / C
@@ -178,6 +194,7 @@ struct March2 {
         float wl, wr;       // horizontal reflect-pad adjoint weights of this pixel column
         float sA, sB, nega; // smoothness gradient A ghat - B (appendix A.6), -depth_a
         ring_ref rr;        // this lane's Vec4 column of the warp's ring
+        int* dbg;           // DBG: decisions of this (scale, image) + this lane's column
     };
 
     struct Carry {          // loop-carried state
@@ -217,31 +234,36 @@ struct March2 {
         }
         const float zv = rcp_acc(fmaf(d, c.da, c.db));
         k.zc = zv;
-        V cam[3];
+        // Projection as a displacement (precompose_e): cam = z (p + E p) + b, so
+        //   u - px = (z e0 + b0 - px w) / (z + w),  w = z e2 + b2 + eps,  e = E p
+        // and the gather cell / bilinear fraction come from floor(u - px) and the integer pixel position: the sampling
+        // position is accurate to float32 rounding of the displacement, not of the coordinate (hundreds of pixels).
+        V e[3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) cam[j] = sv_fma(sv_bc<S>(zv), sv_fma(c.a1[j], sv_bc<S>(py), c.apx[j]), c.bb[j]);
-        const V q = sv_rcp_acc(sv_add(cam[2], sv_bc<S>(PROJ_EPS)));
-        const V u = sv_mul(cam[0], q), v = sv_mul(cam[1], q);
-        // border taps (NNlib grid_sample :border, align-corners); the 2x2 cell is kept inside the image
-        V cu, cv, x0f, y0f;
-        int off[S];
+        for (int j = 0; j < 3; ++j) e[j] = sv_fma(c.e1[j], sv_bc<S>(py), c.epx[j]);
+        const V w = sv_fma(sv_bc<S>(zv), e[2], c.bb[2]);                       // (PROJ_EPS is folded into bb[2])
+        const V q = sv_rcp_acc(sv_add(w, sv_bc<S>(zv)));
+        const V du = sv_mul(sv_fma(sv_bc<S>(-c.pxf), w, sv_fma(sv_bc<S>(zv), e[0], c.bb[0])), q);
+        const V dv = sv_mul(sv_fma(sv_bc<S>(-py), w, sv_fma(sv_bc<S>(zv), e[1], c.bb[1])), q);
+        const V u = sv_add(du, sv_bc<S>(c.pxf)), v = sv_add(dv, sv_bc<S>(py));   // full coordinates (adjoint of the perspective divide)
+        // border taps (NNlib grid_sample :border, align-corners); the 2x2 cell is kept inside the image.  Inside the image
+        // 1 < u < W, i.e. 1 - px < du < W - px; beyond, the coordinate is clipped to the border (and its gradient masked)
+        const float xlo = 1.0f - c.pxf, xhi = c.Wf - c.pxf, ylo = 1.0f - py, yhi = c.Hf - py;
+        const int cxl = -c.gx, cxh = c.W - 2 - c.gx, cyl = -gym, cyh = c.H - 2 - gym;   // cell range relative to this pixel
+        V flx, fly, adx, ady;
+        int off[S], x0s[S], y0s[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            cu.v[s] = fminf(fmaxf(u.v[s], 1.0f), c.Wf);
-            cv.v[s] = fminf(fmaxf(v.v[s], 1.0f), c.Hf);
-        }
-        cu = sv_add(cu, sv_bc<S>(-1.0f));
-        cv = sv_add(cv, sv_bc<S>(-1.0f));
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            int x0 = (int)cu.v[s], y0 = (int)cv.v[s];
-            x0 = x0 < c.W - 2 ? x0 : c.W - 2;
-            y0 = y0 < c.H - 2 ? y0 : c.H - 2;
-            x0f.v[s] = (float)x0; y0f.v[s] = (float)y0;
+            const int fxi = f_floor_i(du.v[s]), fyi = f_floor_i(dv.v[s]);       // (saturating conversion; NaN -> 0)
+            const int rx = fxi < cxl ? cxl : (fxi > cxh ? cxh : fxi), ry = fyi < cyl ? cyl : (fyi > cyh ? cyh : fyi);
+            const int x0 = c.gx + rx, y0 = gym + ry;                            // 0-based gather cell, inside the image
+            flx.v[s] = (float)fxi; fly.v[s] = (float)fyi;
+            adx.v[s] = (float)(fxi - rx); ady.v[s] = (float)(fyi - ry);         // 0 inside; < 0 / > 0 where clipped left / right
+            x0s[s] = x0; y0s[s] = y0;
             off[s] = y0 * c.W + x0;
             // clip-gradient masks (0 where the un-clipped coordinate is <= 1 or >= size), folded into q
-            k.qa.v[s] = (u.v[s] > 1.0f && u.v[s] < c.Wf) ? q.v[s] : 0.0f;
-            k.qb.v[s] = (v.v[s] > 1.0f && v.v[s] < c.Hf) ? q.v[s] : 0.0f;
+            k.qa.v[s] = (du.v[s] > xlo && du.v[s] < xhi) ? q.v[s] : 0.0f;
+            k.qb.v[s] = (dv.v[s] > ylo && dv.v[s] < yhi) ? q.v[s] : 0.0f;
             const float* r0 = c.sb[s] + off[s];
             const float* r1 = c.sb[s] + (off[s] + c.W);
 #pragma unroll
@@ -250,8 +272,19 @@ struct March2 {
                 k.G[ch][2].v[s] = g_ld(r1 + ch * c.HW); k.G[ch][3].v[s] = g_ld1(r1 + ch * c.HW);
             }
         }
-        k.fx = sv_sub(cu, x0f);
-        k.fy = sv_sub(cv, y0f);
+        {   // bilinear fractions: the fraction of the displacement inside the image, 0 / 1 where the coordinate is clipped
+            const V sx_ = sv_add(sv_sub(du, flx), adx), sy_ = sv_add(sv_sub(dv, fly), ady);
+#pragma unroll
+            for (int s = 0; s < S; ++s) { k.fx.v[s] = f_sat(sx_.v[s]); k.fy.v[s] = f_sat(sy_.v[s]); }
+        }
+        if (DBG) {
+            if ((unsigned)(row - c.Y0) < (unsigned)(c.Y1 - c.Y0) && c.mp != 0.f) {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    c.dbg[(row * c.W) * (1 + S) + 1 + s] = x0s[s] | (y0s[s] << 14) | (k.qa.v[s] != 0.0f || (q.v[s] == 0.0f && du.v[s] > xlo && du.v[s] < xhi) ? (1 << 29) : 0) |
+                                                            (k.qb.v[s] != 0.0f || (q.v[s] == 0.0f && dv.v[s] > ylo && dv.v[s] < yhi) ? (1 << 30) : 0);
+            }
+        }
         if (NE4 > 0) {   // early words of the pixel packet (the rest is carried in registers until stage C stores it)
             float pk[NE4 > 0 ? NE4 * 4 : 4];
 #pragma unroll
@@ -381,6 +414,7 @@ struct March2 {
         V ssum, lsum;
         V cs[3 * C];
         V passv = sv_bc<S>(1.f);
+        int dbgw = 0;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
             const float sy = ha[H_Y + ch] + hb[H_Y + ch] + hy[ch];
@@ -420,6 +454,13 @@ struct March2 {
             for (int s = 0; s < S; ++s) ad.v[s] = fabsf(df.v[s]);
             if (ch == 0) { ssum = sc; lsum = ad; }
             else { ssum = sv_add(ssum, sc); lsum = sv_add(lsum, ad); }
+            if (DBG) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    dbgw |= (pm.v[s] != 0.f ? 1 : 0) << (2 + s * C + ch);
+                    dbgw |= (df.v[s] > 0.f ? 1 : (df.v[s] < 0.f ? 2 : 0)) << (8 + 2 * (s * C + ch));
+                }
+            }
             // dS/dx_j = alpha + beta x'_j + gamma y'_j for CENTRED member values x' = x - rc; all three carry a factor 1/2
             const V rDn = sv_mul(inv, Cc), rC = sv_mul(inv, Dn);
             V beta = sv_mul(sv_mul(Sv, sv_bc<S>(9.0f)), rDn);
@@ -479,6 +520,11 @@ struct March2 {
             const float exl = w_up(ex, lane);
             gh = (ex - exl) + (ey - k.ey_prev);
             k.ey_prev = ey;
+            if (DBG) {
+                const float dx_ = k.Dp - Dr, dy_ = k.Dp - curD;
+                dbgw |= (sel + 1) | ((dx_ > 0.f ? 1 : (dx_ < 0.f ? 2 : 0)) << 20) | ((dy_ > 0.f ? 1 : (dy_ < 0.f ? 2 : 0)) << 22);
+                if (row_own && c.mp != 0.f) c.dbg[(q * c.W) * (1 + S)] = dbgw;
+            }
         }
         // =========================== H(i-1): horizontal adjoint 3-sums, routed per source ===========================
         V hw[3 * C];
@@ -541,9 +587,10 @@ struct March2 {
                 else { cb0 = sv_fma(gv, dxq, cb0); cb1 = sv_fma(gv, dyq, cb1); }
             }
             const V ncb2 = sv_fma(cb0, u, sv_mul(cb1, v));    // -cbar_3
-            V ap[3];
+            V ap[3];                                            // A p = p + E p
 #pragma unroll
-            for (int j = 0; j < 3; ++j) ap[j] = sv_fma(c.a1[j], sv_bc<S>(pyr), c.apx[j]);
+            for (int j = 0; j < 3; ++j) ap[j] = sv_fma(c.e1[j], sv_bc<S>(pyr), c.epx[j]);
+            ap[0] = sv_add(ap[0], sv_bc<S>(c.pxf)); ap[1] = sv_add(ap[1], sv_bc<S>(pyr)); ap[2] = sv_add(ap[2], sv_bc<S>(1.0f));
             const V dz = sv_sub(sv_fma(cb0, ap[0], sv_mul(cb1, ap[1])), sv_mul(ncb2, ap[2]));
             const float dbar_z = sv_hsum(dz);
             const float zp = zr * pyr;
@@ -619,21 +666,39 @@ struct March2 {
             c.gb[s] = p.gsrc[s] ? p.gsrc[s] + (long long)n * p.src_ns[s] : nullptr;
             if (p.gsrc[s]) c.has_gb = 1;
         }
-        {   // centring constant of the window sums: the target at the middle of the strip chunk
+        {   // Centring constant of the window sums (any constant is exact; it keeps the centred squares small).  It must not
+            // depend on the work item: windows on the border between two items are computed by both, and only with the same
+            // constant are the two computations bit-identical -- otherwise a near-tie of the two sources' photometric errors can
+            // be decided differently by the two items, and the window's gradient is routed to source 0 in one pixel row and
+            // to source 1 in the next.  MD2_M2_RC: 0 = mean of nine target samples of the image, 1 = middle of the strip chunk
+            // (the item-dependent choice, for comparison only)
+#if MD2_M2_RC == 1
             const int ym = (c.Y0 + c.Y1) >> 1;
             const int xm = sx * OW + OW / 2 < c.W ? sx * OW + OW / 2 : c.W - 1;
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) c.rc[ch] = tgn[ch * c.HW + ym * c.W + xm];
+#else
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 1; j <= 3; ++j)
+#pragma unroll
+                    for (int i = 1; i <= 3; ++i) acc += tgn[ch * c.HW + (j * c.H / 4) * c.W + i * c.W / 4];
+                c.rc[ch] = acc * (1.0f / 9.0f);
+            }
+#endif
         }
         const float px = (float)(gxm + 1);
+        c.pxf = px; c.gx = gxm;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            const float* ab = p.pose_ab + (long long)(s * p.N + n) * 12;
+            const float* eb = p.pose_e + (long long)(s * p.N + n) * 12;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                c.apx[j].v[s] = fmaf(ab[3 * j], px, ab[3 * j + 2]);    // A[:,0] px + A[:,2]: the lane-constant part of A p
-                c.a1[j].v[s] = ab[3 * j + 1];
-                c.bb[j].v[s] = ab[9 + j];
+                c.epx[j].v[s] = fmaf(eb[3 * j], px, eb[3 * j + 2]);    // E[:,0] px + E[:,2]: the lane-constant part of E p
+                c.e1[j].v[s] = eb[3 * j + 1];
+                c.bb[j].v[s] = eb[9 + j] + (j == 2 ? PROJ_EPS : 0.0f);
             }
         }
         c.Wf = (float)c.W; c.Hf = (float)c.H;
@@ -660,6 +725,7 @@ struct March2 {
             }
         }
         c.rr = ring_ref_of(wsm, lane);
+        c.dbg = DBG ? p.dbg + ((long long)(scale * p.N + n) * c.HW + gxm) * (1 + S) : nullptr;
         // pin the per-lane invariants in registers (otherwise they are re-derived from launch parameters / special
         // registers inside the row loop, with a scoreboard wait each)
         keep(c.lane); keep(c.W); keep(c.H); keep(c.rr); keep(c.mp); keep(c.kq); keep(c.da); keep(c.db);

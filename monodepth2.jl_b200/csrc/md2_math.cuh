@@ -143,12 +143,20 @@ MD2_HD SsimWin ssim_window(float xc, float yc, float sx, float sy, float sxx, fl
 
 // align-corners bilinear resize taps (NNlib.upsample_bilinear, call src/training.jl:45):
 // source coordinate = x * (w-1)/(W-1)
-MD2_HD void up_taps(int x, float scale, int w, int& x0, int& x1, float& fx) {
-    const float sx = scale * (float)x;
-    x0 = (int)sx;
-    if (x0 > w - 1) x0 = w - 1;
+// The source coordinate is formed in exact integer arithmetic (x (w-1) = x0 (W-1) + rem, fx = rem / (W-1)): in float32 the
+// product scale * x is only good to 3e-5 at x ~ 300, and that error of the interpolation weight moves the upsampled disparity
+// -- and through it the sampling position of the warp -- by more than float32 rounding of the disparity itself.
+MD2_HD void up_taps(int x, int w, int W, int& x0, int& x1, float& fx) {
+    if (W <= 1) { x0 = 0; x1 = w > 1 ? 1 : 0; fx = 0.f; return; }
+    const int den = W - 1, num = x * (w - 1);              // (< 2^31: W <= 12288, w <= W)
+    int k = (int)((float)num * (1.0f / (float)den));       // within +-1 of the quotient
+    int rem = num - k * den;
+    if (rem < 0) { --k; rem += den; }
+    if (rem >= den) { ++k; rem -= den; }
+    x0 = k;
+    fx = (float)rem / (float)den;
+    if (x0 > w - 1) { x0 = w - 1; fx = 0.f; }
     x1 = x0 + 1 < w ? x0 + 1 : w - 1;
-    fx = sx - (float)x0;
 }
 MD2_HD float up_scale(int w, int W) { return W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f; }
 
@@ -279,6 +287,19 @@ MD2_HD void precompose(const double* K, const double* Kinv, const double* R, con
     mat3_mul(KR, Kinv, A);
     for (int i = 0; i < 9; ++i) ab[i] = (float)A[i];
     for (int i = 0; i < 3; ++i) ab[9 + i] = (float)(K[3 * i] * t[0] + K[3 * i + 1] * t[1] + K[3 * i + 2] * t[2]);
+}
+
+// The same, as a displacement: E = K R K^-1 - I (formed in double, so that the small entries of E keep their relative
+// accuracy when rounded to float32) and b.  The hot kernel projects with cam = z (p + E p) + b and forms u - px directly:
+// the projected coordinate is then accurate to float32 rounding of the DISPLACEMENT (a few pixels), not of the
+// coordinate itself (hundreds of pixels: 3e-5 px at W = 416, 6e-5 at 1024 -- which shows up as 1e-4 .. 4e-3 relative
+// errors of the pose gradients, sums of per-pixel terms with heavy cancellation).
+MD2_HD void precompose_e(const double* K, const double* Kinv, const double* R, const double* t, float* eb) {
+    double KR[9], A[9];
+    mat3_mul(K, R, KR);
+    mat3_mul(KR, Kinv, A);
+    for (int i = 0; i < 9; ++i) eb[i] = (float)(A[i] - ((i % 4 == 0) ? 1.0 : 0.0));
+    for (int i = 0; i < 3; ++i) eb[9 + i] = (float)(K[3 * i] * t[0] + K[3 * i + 1] * t[1] + K[3 * i + 2] * t[2]);
 }
 
 // adjoint of the pre-composition: G = sum cbar (z p)^T (3x3 row-major), h = sum cbar

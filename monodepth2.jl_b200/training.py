@@ -95,7 +95,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             loss_scale=cfg["loss_scale"], normalize_disparity=cfg["normalize"], loss=loss,
             grad_disparity=gd, grad_rot=gr, grad_trans=gt,
             grad_source=[gx[:, i] for i in sid] if need_x else None,
-            viz_warped=viz_w, viz_loss=viz_l, shape=(N, Cc, H, W))
+            viz_warped=viz_w, viz_loss=viz_l, debug_choices=cfg.get("debug_choices") if any_grad else None, shape=(N, Cc, H, W))
         if any_grad:
             c.call("md2_view_synthesis_loss_fwdbwd", C.byref(desc), 1.0)
             ctx.grads = (gd, gr, gt, gx)
@@ -120,7 +120,7 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
                         scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0,
                         disparity_smoothness=1e-3, auto_loss=None, normalize_disparity=True,
                         smooth_weight=None, loss_scale=None, poses_are_rvec=True, invert=None,
-                        return_viz=False, K_cm=None, invK_cm=None):
+                        return_viz=False, K_cm=None, invK_cm=None, debug_choices=None):
     """Everything of train_loss after `model(...)` (src/training.jl:29-77) in fused kernels.
 
     x (N,L,C,H,W); disparities: list of (N,1,h_i,w_i) at the decoder's native sizes (smaller ones
@@ -128,7 +128,9 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
     rvec/tvec (N,3) [poses_are_rvec=True: composeT is fused, invert = source_id < target_id]
     or R (N,3,3)/t (N,3) as returned by composeT.  auto_loss (N,1,H,W) enables automasking.
     Returns the scalar loss (and, if return_viz, the last scale's warp-loss map and warped
-    images, which the reference copies out for logging)."""
+    images, which the reference copies out for logging).
+    debug_choices: optional int32 (L,N,H,W,1+S) test hook that receives the kernel's discrete decisions
+    (include/md2.h: md2_vsl_desc.debug_choices)."""
     S, Lc = len(source_ids), len(disparities)
     if invert is None:
         invert = [sid < target_id for sid in source_ids]
@@ -143,7 +145,7 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
                smooth_weight=smooth_weight if smooth_weight is not None else
                [disparity_smoothness * s for s in list(scales)[:Lc]],
                loss_scale=loss_scale if loss_scale is not None else 1.0 / Lc,
-               normalize=normalize_disparity, viz=return_viz)
+               normalize=normalize_disparity, viz=return_viz, debug_choices=debug_choices)
     trans = [t.reshape(-1, 3) for t in trans]
     out = _ViewSynthesisLoss.apply(cfg, x, *disparities, *rot, *trans)
     if return_viz:

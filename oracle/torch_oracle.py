@@ -333,3 +333,108 @@ def synthetic_batch(N, C, H, W, scales=(0.125, 0.25, 0.5, 1.0), seed=42, full_re
         rvecs.append(r.to(dtype))
         tvecs.append((pose_sigma * torch.randn(N, 3, generator=g, dtype=torch.float64)).to(dtype))
     return x.to(dtype), disps, rvecs, tvecs
+
+
+# ----------------------------------------------------------------------------
+# Forced-decision evaluation (test infrastructure for the flip-controlled parity tests).
+#
+# The loss is only piecewise smooth: the bilinear sampler switches cell at integer coordinates, the border
+# clip switches its gradient mask at 1 / size, min-over-sources / automask switch at ties, |.| and the SSIM
+# clamp have kinks.  A float32 evaluation lands on either side of such a switch whenever the float64
+# quantity is within float32 rounding of it, and both sides are valid sub-gradients.  To compare EVERY
+# gradient element strictly, the float64 oracle below takes the discrete decisions from the implementation
+# under test (md2.h: md2_vsl_desc.debug_choices) and evaluates the same piece of the piecewise-smooth
+# function: values are computed exactly as in view_synthesis_loss, only the branch of each kink is forced.
+# ----------------------------------------------------------------------------
+
+
+def decode_choices(choices, C, S):
+    """choices int32 (L,N,H,W,1+S) -> dict of per-scale decisions (see include/md2.h)."""
+    w0 = choices[..., 0].long()
+    code = lambda v: torch.where(v == 1, 1.0, torch.where(v == 2, -1.0, 0.0)).double()
+    out = {"sel": (w0 & 3) - 1,
+           "pass": torch.stack([torch.stack([((w0 >> (2 + s * C + c)) & 1).bool() for c in range(C)], 2) for s in range(S)], 2),
+           "l1": torch.stack([torch.stack([code((w0 >> (8 + 2 * (s * C + c))) & 3) for c in range(C)], 2) for s in range(S)], 2),
+           "smx": code((w0 >> 20) & 3), "smy": code((w0 >> 22) & 3)}   # pass / l1: (L,N,S,C,H,W)
+    ws = choices[..., 1:].long()                                       # (L,N,H,W,S)
+    out["x0"], out["y0"] = ws & 0x3fff, (ws >> 14) & 0x7fff
+    out["mx"], out["my"] = ((ws >> 29) & 1).bool(), ((ws >> 30) & 1).bool()
+    return out
+
+
+def _forced_abs(d, sgn):
+    """|d| whose derivative is the given sign (-1, 0, +1)"""
+    lin = d * sgn
+    return lin + (d.abs() - lin).detach()
+
+
+def _forced_grid_sample_border(inp, grid, x0, y0, mx, my):
+    """bilinear border sampling with the gather cell (x0, y0) and the clip-gradient masks given"""
+    N, C, H, W = inp.shape
+
+    def coord(g, size, m):
+        i = ((g + 1.0) / 2.0) * (size - 1)
+        ic = i + (i.clamp(0, size - 1) - i).detach()       # value of the clip, derivative 1 ...
+        return torch.where(m, ic, ic.detach())              # ... where the implementation's mask says so
+    fx = (coord(grid[..., 0], W, mx) - x0).unsqueeze(1)
+    fy = (coord(grid[..., 1], H, my) - y0).unsqueeze(1)
+    flat = inp.reshape(N, C, H * W)
+    idx = (y0 * W + x0).reshape(N, 1, H * W).expand(N, C, H * W)
+    tap = lambda o: torch.gather(flat, 2, idx + o).reshape(N, C, H, W)
+    v00, v01, v10, v11 = tap(0), tap(1), tap(W), tap(W + 1)
+    return v00 * (1 - fx) * (1 - fy) + v01 * fx * (1 - fy) + v10 * (1 - fx) * fy + v11 * fx * fy
+
+
+def _forced_ssim(x, y, passm):
+    pool = lambda a: F.avg_pool2d(a, 3, 1)
+    x_ref = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    y_ref = F.pad(y, (1, 1, 1, 1), mode="reflect")
+    mu_x, mu_y = pool(x_ref), pool(y_ref)
+    sigma_x = pool(x_ref * x_ref) - mu_x * mu_x
+    sigma_y = pool(y_ref * y_ref) - mu_y * mu_y
+    sigma_xy = pool(x_ref * y_ref) - mu_x * mu_y
+    ssim_n = (2.0 * mu_x * mu_y + 0.01 ** 2) * (2.0 * sigma_xy + 0.03 ** 2)
+    ssim_d = (mu_x * mu_x + mu_y * mu_y + 0.01 ** 2) * (sigma_x + sigma_y + 0.03 ** 2)
+    raw = (1.0 - ssim_n / ssim_d) * 0.5
+    val = raw.clamp(0.0, 1.0)
+    return torch.where(passm, raw + (val - raw).detach(), val.detach())
+
+
+def view_synthesis_loss_forced(x, disparities, rvecs, tvecs, K, invK, choices, *, target_id=1, source_ids=(0, 2),
+                               scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0,
+                               disparity_smoothness=1e-3, auto_loss=None, alpha=0.85):
+    """view_synthesis_loss with every discrete decision taken from `choices` (int32 (L,N,H,W,1+S))."""
+    dt = x.dtype
+    N, L, C, H, W = x.shape
+    S = len(source_ids)
+    ch = decode_choices(choices, C, S)
+    target_x = x[:, target_id]
+    backproject, project = Backproject(W, H, dt), Project(W, H, dt)
+    Ps = [composeT(r, t, sid < target_id) for r, t, sid in zip(rvecs, tvecs, source_ids)]
+    loss = torch.zeros((), dtype=dt)
+    for i, (disparity, scale) in enumerate(zip(disparities, scales)):
+        if disparity.shape[-1] != W or disparity.shape[-2] != H:
+            disparity = upsample_bilinear(disparity, (W, H))
+        depth = disparity_to_depth(disparity, min_depth, max_depth)
+        coords = backproject(depth.reshape(N, H * W), invK)
+        pes = []
+        for s, ((R, t), sid) in enumerate(zip(Ps, source_ids)):
+            uvs = project(coords, K, R, t).reshape(N, H, W, 2)
+            warped = _forced_grid_sample_border(x[:, sid], uvs, ch["x0"][i, ..., s], ch["y0"][i, ..., s],
+                                                ch["mx"][i, ..., s], ch["my"][i, ..., s])
+            l1 = _forced_abs(warped - target_x, ch["l1"][i, :, s].to(dt)).mean(1, keepdim=True)
+            sv = _forced_ssim(warped, target_x, ch["pass"][i, :, s]).mean(1, keepdim=True)
+            pes.append(alpha * sv + (1.0 - alpha) * l1)
+        sel = ch["sel"][i].unsqueeze(1)                                   # (N,1,H,W): -1 = automask
+        stack = torch.cat(pes, 1)
+        warp_loss = torch.gather(stack, 1, sel.clamp(min=0))
+        if auto_loss is not None:
+            warp_loss = torch.where(sel < 0, auto_loss.to(dt), warp_loss)
+        norm_disp = (disparity / (disparity.mean(dim=(2, 3), keepdim=True) + 1e-7))[:, 0]
+        ddx = _forced_abs(norm_disp[:, :, :-1] - norm_disp[:, :, 1:], ch["smx"][i][:, :, :-1].to(dt))
+        ddy = _forced_abs(norm_disp[:, :-1, :] - norm_disp[:, 1:, :], ch["smy"][i][:, :-1, :].to(dt))
+        idx = (target_x[:, :, :, :-1] - target_x[:, :, :, 1:]).abs().mean(1)
+        idy = (target_x[:, :, :-1, :] - target_x[:, :, 1:, :]).abs().mean(1)
+        disp_loss = ((ddx * torch.exp(-idx)).mean() + (ddy * torch.exp(-idy)).mean()) * disparity_smoothness * scale
+        loss = loss + warp_loss.mean() + disp_loss
+    return loss / len(scales)

@@ -23,18 +23,18 @@ using namespace md2;
 // producer/consumer pair) warps of lockstep fibers walks all work items of one (scale, image), like
 // a persistent block of the CUDA kernel does
 template <int C, int S, bool BWD>
-static void run_march(const FusedParams& p, std::vector<float>& sums) {
+static void run_march(const FusedParams& p, std::vector<double>& sums) {
     using M = March<C, S, BWD>;
     const int NP = M::NPART;
     const int strips = (p.W + M::OW - 1) / M::OW, chunks = (p.H + p.m_R - 1) / p.m_R;
-    sums.assign((size_t)p.L * p.N * NP, 0.f);
+    sums.assign((size_t)p.L * p.N * NP, 0.0);
     std::vector<float> wsm(M::SMEM_FLOATS + 4);
     float* wsm_al = (float*)(((uintptr_t)wsm.data() + 15) & ~(uintptr_t)15);
     WarpEmu emu;
     std::vector<float> lane_v((size_t)M::THREADS * 32);
     for (int z = 0; z < p.L * p.N; ++z) {
         for (int k = 0; k < M::SMEM_FLOATS; ++k) wsm_al[k] = NAN;   // poison: catches reads of never-written slots
-        float* su = sums.data() + (size_t)z * NP;
+        double* su = sums.data() + (size_t)z * NP;
         emu.run(M::THREADS, [&](int tid) {
             const int warp = tid >> 5, lane = tid & 31;
             int gslot = 0;
@@ -49,8 +49,13 @@ static void run_march(const FusedParams& p, std::vector<float>& sums) {
                     for (int k = 0; k < 32; ++k) lane_v[(size_t)tid * 32 + k] = v[k];
                     if (BWD) emu_bar(0, 64, 1); else emu_ballot(0);
                     if (tid == 0)
-                        for (int t = 0; t < M::THREADS; ++t)
-                            for (int k = 0; k < NP; ++k) su[k] += lane_v[(size_t)t * 32 + k];
+                        for (int k = 0; k < NP; ++k) {   // float over the lanes of a warp (device: warp reduction), double across items (finish kernel)
+                            for (int w = 0; w < M::THREADS / 32; ++w) {
+                                float part = 0.f;
+                                for (int t = 0; t < 32; ++t) part += lane_v[(size_t)(w * 32 + t) * 32 + k];
+                                su[k] += (double)part;
+                            }
+                        }
                     if (BWD) emu_bar(0, 64, 1); else emu_ballot(0);
                 }
         });
@@ -58,19 +63,19 @@ static void run_march(const FusedParams& p, std::vector<float>& sums) {
 }
 
 // single-warp marching kernel (md2_march2.cuh): one warp of lockstep fibers walks all work items of a (scale, image)
-template <int C, int S, bool AM>
-static void run_march2(const FusedParams& p, std::vector<float>& sums) {
-    using M = March2<C, S, AM>;
+template <int C, int S, bool AM, bool DBG = false>
+static void run_march2(const FusedParams& p, std::vector<double>& sums) {
+    using M = March2<C, S, AM, DBG>;
     const int NP = M::NPART;
     const int strips = (p.W + M::OW - 1) / M::OW, chunks = (p.H + p.m_R - 1) / p.m_R;
-    sums.assign((size_t)p.L * p.N * NP, 0.f);
+    sums.assign((size_t)p.L * p.N * NP, 0.0);
     std::vector<float> wsm(M::SMEM_FLOATS + 4);
     float* wsm_al = (float*)(((uintptr_t)wsm.data() + 15) & ~(uintptr_t)15);
     WarpEmu emu;
     std::vector<float> lane_v((size_t)32 * 32);
     for (int z = 0; z < p.L * p.N; ++z) {
         for (int k = 0; k < M::SMEM_FLOATS; ++k) wsm_al[k] = NAN;   // poison: catches reads of never-written slots
-        float* su = sums.data() + (size_t)z * NP;
+        double* su = sums.data() + (size_t)z * NP;
         emu.run(32, [&](int tid) {
             const int lane = tid & 31;
             for (int cy = 0; cy < chunks; ++cy)
@@ -80,8 +85,11 @@ static void run_march2(const FusedParams& p, std::vector<float>& sums) {
                     for (int k = 0; k < 32; ++k) lane_v[(size_t)tid * 32 + k] = v[k];
                     emu_ballot(0);
                     if (tid == 0)
-                        for (int t = 0; t < 32; ++t)
-                            for (int k = 0; k < NP; ++k) su[k] += lane_v[(size_t)t * 32 + k];
+                        for (int k = 0; k < NP; ++k) {   // float over the lanes (device: warp reduction), double across items (finish kernel)
+                            float part = 0.f;
+                            for (int t = 0; t < 32; ++t) part += lane_v[(size_t)t * 32 + k];
+                            su[k] += (double)part;
+                        }
                     emu_ballot(0);
                 }
         });
@@ -89,7 +97,7 @@ static void run_march2(const FusedParams& p, std::vector<float>& sums) {
 }
 
 template <bool BWD>
-static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums, int variant) {
+static int dispatch(int C, int S, const FusedParams& p, std::vector<double>& sums, int variant) {
     if (variant == 1) {
         if (C == 1 && S == 1) { run_march<1, 1, BWD>(p, sums); return 0; }
         if (C == 1 && S == 2) { run_march<1, 2, BWD>(p, sums); return 0; }
@@ -99,6 +107,11 @@ static int dispatch(int C, int S, const FusedParams& p, std::vector<float>& sums
     }
     if (variant == 2 && BWD) {
         const bool am = p.automask != nullptr;
+        if (p.dbg) {   // test hook: the instantiations that also export the discrete decisions (S = 2)
+            if (C == 1 && S == 2) { if (am) run_march2<1, 2, true, true>(p, sums); else run_march2<1, 2, false, true>(p, sums); return 0; }
+            if (C == 3 && S == 2) { if (am) run_march2<3, 2, true, true>(p, sums); else run_march2<3, 2, false, true>(p, sums); return 0; }
+            return 1;
+        }
         if (C == 1 && S == 1) { if (am) run_march2<1, 1, true>(p, sums); else run_march2<1, 1, false>(p, sums); return 0; }
         if (C == 1 && S == 2) { if (am) run_march2<1, 2, true>(p, sums); else run_march2<1, 2, false>(p, sums); return 0; }
         if (C == 3 && S == 1) { if (am) run_march2<3, 1, true>(p, sums); else run_march2<3, 1, false>(p, sums); return 0; }
@@ -122,6 +135,7 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
         p.viz_warped[s] = d->viz_warped[s];
     }
     p.viz_loss = d->viz_loss; p.automask = d->automask;
+    p.dbg = (bwd && variant == 2) ? d->debug_choices : nullptr;
     const float mind = (float)(1.0 / (double)d->max_depth), maxd = (float)(1.0 / (double)d->min_depth);
     p.depth_a = maxd - mind; p.depth_b = mind;
     for (int l = 0; l < L; ++l) {
@@ -141,7 +155,7 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
             for (int gy = 0; gy < H; ++gy)
                 for (int gx = 0; gx < W; ++gx)
                     dscr[l][((size_t)n * H + gy) * W + gx] =
-                        disp_fullres(p.disp[l] + (size_t)n * p.dw[l] * p.dh[l], p.dw[l], p.dh[l], false, usx, usy, W, gx, gy);
+                        disp_fullres(p.disp[l] + (size_t)n * p.dw[l] * p.dh[l], p.dw[l], p.dh[l], false, W, H, gx, gy);
         p.dfull[l] = dscr[l].data();
         p.gfull[l] = bwd ? gscr[l].data() : nullptr;
     }
@@ -152,10 +166,11 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
         p.pose.rot[s] = d->rot[s]; p.pose.trans[s] = d->trans[s]; p.pose.invert[s] = d->invert[s];
         p.pose.grot[s] = d->grad_rot[s]; p.pose.gtrans[s] = d->grad_trans[s];
     }
-    std::vector<float> ab((size_t)12 * S * N);
+    std::vector<float> ab((size_t)24 * S * N);
     for (int s = 0; s < S; ++s)
-        for (int n = 0; n < N; ++n) prepare_pose_one(p.pose, s, n, ab.data() + ((size_t)s * N + n) * 12);
+        for (int n = 0; n < N; ++n) prepare_pose_one(p.pose, s, n, ab.data() + ((size_t)s * N + n) * 12, ab.data() + ((size_t)(S + s) * N + n) * 12);
     p.pose_ab = ab.data();
+    p.pose_e = ab.data() + (size_t)12 * S * N;
     p.pose_slot = 0;
     p.m_R = R > 0 ? R : 32;
 
@@ -175,11 +190,11 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
         }
     }
     p.stats = stats.data();
-    std::vector<float> sums;
+    std::vector<double> sums;
     const int NP = NSTAT + 12 * S;
     if (bwd && variant == 2 && (p.viz_loss || p.viz_warped[0] || p.viz_warped[1])) {
         // as run_vsl on the device: the visualisation outputs come from the forward-only kernel
-        std::vector<float> tmp;
+        std::vector<double> tmp;
         if (dispatch<false>(C, S, p, tmp, 1)) return 1;
     }
     if (bwd ? dispatch<true>(C, S, p, sums, variant) : dispatch<false>(C, S, p, sums, variant)) return 1;
@@ -194,9 +209,9 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
 
     if (mode != 1) {
         for (int z = 0; z < L * N; ++z) {
-            stats[(size_t)z * NSTAT] = sums[(size_t)z * NP];
+            stats[(size_t)z * NSTAT] = (float)sums[(size_t)z * NP];
             if (mode == 0)
-                for (int k = 1; k < 4; ++k) stats[(size_t)z * NSTAT + k] = sums[(size_t)z * NP + k];
+                for (int k = 1; k < 4; ++k) stats[(size_t)z * NSTAT + k] = (float)sums[(size_t)z * NP + k];
         }
         if (d->saved) memcpy(d->saved, stats.data(), sizeof(float) * stats.size());
         if (d->loss) *d->loss = loss_from_stats(stats.data(), W, H, N, L, d->smooth_weight, d->loss_scale, d->normalize_disparity);
@@ -206,7 +221,7 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
             for (int n = 0; n < N; ++n) {
                 double G[9] = {0}, h[3] = {0};
                 for (int l = 0; l < L; ++l) {
-                    const float* su = sums.data() + ((size_t)l * N + n) * NP + NSTAT + 12 * s;
+                    const double* su = sums.data() + ((size_t)l * N + n) * NP + NSTAT + 12 * s;
                     for (int k = 0; k < 9; ++k) G[k] += su[k];
                     for (int k = 0; k < 3; ++k) h[k] += su[9 + k];
                 }

@@ -26,7 +26,7 @@ def build_emul():
 def emul_vsl(x, disps, rvecs, tvecs, K, invK, *, mode=2, gloss=1.0, target_id=1, source_ids=(0, 2),
              scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3,
              automask=None, normalize=True, smooth_weight=None, loss_scale=None, grad_source=True, saved=None,
-             viz=False, variant="march2", R=32):
+             viz=False, variant="march2", R=32, debug_choices=False):
     """CPU float32 tensors in, dict of outputs out (same maths as the CUDA fused path)."""
     lib = C.CDLL(build_emul())
     lib.md2_emul_vsl.argtypes = [C.POINTER(L.VslDesc), C.c_int, C.c_float]
@@ -50,6 +50,8 @@ def emul_vsl(x, disps, rvecs, tvecs, K, invK, *, mode=2, gloss=1.0, target_id=1,
     if viz:
         out["viz_warped"] = [torch.zeros(N, Cc, H, W) for _ in range(S)]
         out["viz_loss"] = torch.zeros(N, 1, H, W)
+    if debug_choices:
+        out["choices"] = torch.zeros(Ls, N, H, W, 1 + S, dtype=torch.int32)
     sw = smooth_weight if smooth_weight is not None else [disparity_smoothness * s for s in scales[:Ls]]
     ls = loss_scale if loss_scale is not None else 1.0 / Ls
     desc = L.make_vsl_desc(
@@ -60,7 +62,8 @@ def emul_vsl(x, disps, rvecs, tvecs, K, invK, *, mode=2, gloss=1.0, target_id=1,
         smooth_weight=sw, loss_scale=ls, normalize_disparity=normalize, loss=out["loss"],
         grad_disparity=out["gdisp"], grad_rot=out["grvec"], grad_trans=out["gtvec"],
         grad_source=[out["gx"][:, i] for i in source_ids] if grad_source else None,
-        viz_warped=out.get("viz_warped"), viz_loss=out.get("viz_loss"), saved=out["saved"], shape=(N, Cc, H, W))
+        viz_warped=out.get("viz_warped"), viz_loss=out.get("viz_loss"), saved=out["saved"], debug_choices=out.get("choices"),
+        shape=(N, Cc, H, W))
     if variant == "march2" and mode != 0:
         rc = lib.md2_emul_march2(C.byref(desc), mode, gloss, R)
     elif variant in ("march", "march2"):

@@ -33,22 +33,39 @@ def oracle_vsl(x, disps, rv, tv, K, invK, *, automask=False, dtype=F64, **kw):
                 gtvec=[t.grad for t in td], gx=xd.grad, auto=auto)
 
 
+def oracle_vsl_forced(x, disps, rv, tv, K, invK, choices, *, auto=None, dtype=F64, **kw):
+    """float64 oracle loss + gradients with the discrete decisions of the implementation under test forced
+    (`choices`: md2_vsl_desc.debug_choices, int32 (L,N,H,W,1+S)); `auto`: the automask map or None"""
+    xd = x.detach().cpu().to(dtype).requires_grad_(True)
+    dd = [d.detach().cpu().to(dtype).requires_grad_(True) for d in disps]
+    rd = [r.detach().cpu().to(dtype).requires_grad_(True) for r in rv]
+    td = [t.detach().cpu().to(dtype).requires_grad_(True) for t in tv]
+    loss = O.view_synthesis_loss_forced(xd, dd, rd, td, K.cpu().to(dtype), invK.cpu().to(dtype), choices.cpu(),
+                                        auto_loss=None if auto is None else auto.detach().cpu().to(dtype), **kw)
+    loss.backward()
+    return dict(loss=loss.item(), gdisp=[d.grad for d in dd], grvec=[r.grad for r in rd], gtvec=[t.grad for t in td],
+                gx=xd.grad, auto=auto)
+
+
 # parity bars of BASELINE.json (fp32): loss 1e-5 relative, gradients 1e-4 relative
 LOSS_RTOL = 1e-5
 GRAD_RTOL = 1e-4
 
 
-def check_vsl(out, ref, source_ids=(0, 2), check_gx=True, tag=""):
+def check_vsl(out, ref, source_ids=(0, 2), check_gx=True, tag="", grad_rtol=None):
+    """EVERY gradient element within grad_rtol (default: BASELINE.json's 1e-4) of the largest element of its array
+    (and the arrays in the L2 norm), loss within 1e-5"""
+    tol = GRAD_RTOL if grad_rtol is None else grad_rtol
     assert abs(out["loss"] - ref["loss"]) <= LOSS_RTOL * abs(ref["loss"]), (tag, out["loss"], ref["loss"])
     for i, (a, b) in enumerate(zip(out["gdisp"], ref["gdisp"])):
-        assert rel_l2(a, b) <= GRAD_RTOL and rel_max(a, b) <= GRAD_RTOL, (tag, "gdisp", i, rel_l2(a, b), rel_max(a, b))
+        assert rel_l2(a, b) <= tol and rel_max(a, b) <= tol, (tag, "gdisp", i, rel_l2(a, b), rel_max(a, b))
     for name in ("grvec", "gtvec"):
         for s, (a, b) in enumerate(zip(out[name], ref[name])):
-            assert rel_max(a, b) <= GRAD_RTOL, (tag, name, s, rel_max(a, b))
+            assert rel_max(a, b) <= tol, (tag, name, s, rel_max(a, b))
     if check_gx and out.get("gx") is not None:
         ids = list(source_ids)
         a, b = out["gx"][:, ids], ref["gx"][:, ids]
-        assert rel_l2(a, b) <= GRAD_RTOL and rel_max(a, b) <= GRAD_RTOL, (tag, "gx", rel_l2(a, b), rel_max(a, b))
+        assert rel_l2(a, b) <= tol and rel_max(a, b) <= tol, (tag, "gx", rel_l2(a, b), rel_max(a, b))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -111,6 +128,51 @@ def conditioning(x, disps, rv, tv, K, invK, automask=False, target_id=1, source_
         worst = min(worst, ((dd[:, :, 1:] - dd[:, :, :-1]).abs().min() / r_dd).item(),
                     ((dd[:, 1:] - dd[:, :-1]).abs().min() / r_dd).item())
     return worst
+
+
+def fragile_pixels(x, disps, rv, tv, K, invK, automask=False, target_id=1, source_ids=(0, 2)):
+    """per scale: (N,H,W) bool, True where the float64 margin to a discontinuity (cell switch, clip border, arg-min / automask
+    tie, |.| kinks) is below the float32 error radius -- the per-pixel form of `conditioning` (the sampling position of the
+    single-warp kernel is accurate to float32 rounding of the displacement: a few 1e-6 pixels, independent of the image size)"""
+    dt = F64
+    x = x.detach().cpu().to(dt)
+    N, L, C, H, W = x.shape
+    K, invK = K.cpu().to(dt), invK.cpu().to(dt)
+    r_cell = 4e-6
+    r_pe, r_l1, r_dd = 4e-6, 3e-6, 1e-6
+    ssim = O.SSIM()
+    tgt = x[:, target_id]
+    auto = O.automasking_loss(ssim, x, tgt, source_ids) if automask else None
+    bp, pj = O.Backproject(W, H, dt), O.Project(W, H, dt)
+    out = []
+    for d in disps:
+        d = d.detach().cpu().to(dt)
+        if d.shape[-1] != W or d.shape[-2] != H:
+            d = O.upsample_bilinear(d, (W, H))
+        pts = bp(O.disparity_to_depth(d, 0.1, 100.0).reshape(N, H * W), invK)
+        frag = torch.zeros(N, H, W, dtype=torch.bool)
+        pes = []
+        for s, sid in enumerate(source_ids):
+            R, t = O.composeT(rv[s].detach().cpu().to(dt), tv[s].detach().cpu().to(dt), sid < target_id)
+            uv = pj(pts, K, R, t).reshape(N, H, W, 2)
+            for k, size in ((0, W), (1, H)):
+                i = ((uv[..., k] + 1) / 2) * (size - 1)
+                f = i - i.floor()
+                inside = (i > -1) & (i < size)
+                frag |= inside & (torch.minimum(f, 1 - f) < r_cell)
+            w = O.grid_sample(x[:, sid], uv, "border")
+            frag |= ((w - tgt).abs() < r_l1).any(1)
+            pes.append(O.photometric_loss(ssim, w, tgt)[:, 0])
+        if len(pes) > 1:
+            frag |= (pes[0] - pes[1]).abs() < r_pe
+        if automask:
+            frag |= (auto[:, 0] - torch.minimum(pes[0], pes[-1])).abs() < r_pe
+        dd = d[:, 0]
+        fx = (dd[:, :, 1:] - dd[:, :, :-1]).abs() < r_dd
+        fy = (dd[:, 1:] - dd[:, :-1]).abs() < r_dd
+        frag[:, :, 1:] |= fx; frag[:, :, :-1] |= fx; frag[:, 1:] |= fy; frag[:, :-1] |= fy
+        out.append(frag)
+    return out
 
 
 def well_conditioned_batch(N, C, H, W, automask=False, start_seed=0, tries=400, **kw):
