@@ -295,6 +295,8 @@ MD2_HD void precompose(const double* K, const double* Kinv, const double* R, con
 // coordinate itself (hundreds of pixels: 3e-5 px at W = 416, 6e-5 at 1024 -- which shows up as 1e-4 .. 4e-3 relative
 // errors of the pose gradients, sums of per-pixel terms with heavy cancellation).
 MD2_HD void precompose_e(const double* K, const double* Kinv, const double* R, const double* t, float* eb) {
+    // (K R Kinv - I with the caller's K and Kinv as they are -- not K (R - I) Kinv: the reference multiplies by the invK it
+    // is given, and a float32 invK is the inverse of K only to 1e-7, which is 4e-5 px at the right-hand image border)
     double KR[9], A[9];
     mat3_mul(K, R, KR);
     mat3_mul(KR, Kinv, A);
