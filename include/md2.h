@@ -33,6 +33,7 @@ extern "C" {
 
 #define MD2_MAX_SOURCES 2
 #define MD2_MAX_SCALES 8
+#define MD2_ADAM_MAX_TENSORS 16
 
 typedef struct md2_ctx md2_ctx;
 typedef void* md2_stream;
@@ -191,6 +192,31 @@ int md2_view_synthesis_loss_fwdbwd_host(md2_ctx*, const md2_vsl_desc* host_desc,
 int md2_warp_fwd(md2_ctx*, const md2_vsl_desc*, float* const* out, md2_stream);
 /* gout[s] (W,H,C,N) -> grad_disparity[0], grad_rot, grad_trans, grad_source (accumulated) */
 int md2_warp_bwd(md2_ctx*, const md2_vsl_desc*, const float* const* gout, md2_stream);
+
+/* ---- F1  Flux.Optimise.update!(ADAM, ...)   call src/Monodepth.jl:165-171, src/simple_depth.jl:20,43 --------------
+ * One multi-tensor launch of the Flux ADAM rule (m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ * p -= lr * m / (1 - b1^t) / (sqrt(v / (1 - b2^t)) + eps)) over n <= MD2_ADAM_MAX_TENSORS device tensors
+ * (params[k], grads[k] with counts[k] elements; the arrays params / grads / counts themselves are HOST arrays).
+ * grads are multiplied by grad_scale first (1 / world size after a SUM all-reduce).
+ * Optimiser state is caller-owned device memory, which is what a checkpoint saves and restores:
+ *   state  2 * sum(counts) floats: [m of the concatenated tensors | v of the concatenated tensors], zero-initialised
+ *   clock  2 int64, zero-initialised: clock[0] = updates applied so far (t - 1; advanced on the device, so the call
+ *          can be replayed from a CUDA graph), clock[1] = internal arrival counter (always 0 between launches) */
+int md2_adam_step(md2_ctx*, int32_t n, float* const* params, const float* const* grads, const int64_t* counts,
+                  float* state, int64_t* clock, float lr, float beta1, float beta2, float eps, float grad_scale, md2_stream);
+
+/* ---- A15  slow_depth   src/simple_depth.jl:1-62 ---------------------------------------------------------------
+ * The reference's single-triplet optimiser: `iters` iterations of { value + gradient of the objective described by
+ * the descriptor; ADAM update of disparity[0] (W,H,1,N), rot[s] = rvec (3,N), trans[s] = tvec (3,1,N) IN PLACE }.
+ * Descriptor: L = 1 with a full-resolution disparity, pose_mode = 1, loss / grad_disparity[0] / grad_rot / grad_trans
+ * are scratch the call overwrites (the reference's objective is normalize_disparity = 0, smooth_weight[0] = 1,
+ * loss_scale = 1: mean(prediction_loss) + smooth_loss).  state / clock as in md2_adam_step for the tensor order
+ * disparity, rvec_0, tvec_0, rvec_1, tvec_1; loss_history (nullable, device, history_len floats) receives the
+ * objective value of update number t at index t = clock[0] at that time (values beyond history_len are dropped).
+ * One iteration is four launches captured once into a CUDA graph and replayed; the loop is ordered after the work
+ * already enqueued on `stream` and before anything enqueued afterwards, and does not synchronise the host. */
+int md2_slow_depth(md2_ctx*, const md2_vsl_desc*, int32_t iters, float lr, float beta1, float beta2, float eps,
+                   float* state, int64_t* clock, float* loss_history, int64_t history_len, md2_stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,9 @@ from ._lib import Context, Md2Error, load_library, EXPORTS, LIB_PATH  # noqa: F4
 from .ops import (SSIM, Backproject, Project, _apply_mask, automasking_loss, composeT,  # noqa: F401
                   disparity_to_depth, grid_sample, hat, photometric_loss, prediction_loss, smooth_loss,
                   so3_exp_map, upsample_bilinear)
-from .training import (HostViewSynthesisLoss, Params, Pose, TrainCache, simple_depth_loss, train_loss,  # noqa: F401
-                       view_synthesis_loss, warp)
+from .training import (Adam, AsyncViz, HostViewSynthesisLoss, Params, Pose, TrainCache, simple_depth_loss, slow_depth,  # noqa: F401
+                       train_loss, view_synthesis_loss, warp)
+
+from .train_step import DataParallelTrainer, GradientBuckets, StandInModel, make_training_setup  # noqa: F401
 
 __version__ = "0.1.0"

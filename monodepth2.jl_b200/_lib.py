@@ -155,7 +155,10 @@ _SIGS = {
     "md2_view_synthesis_loss_fwdbwd_host": [c_void, C.POINTER(VslDesc), _F, _I32],
     "md2_warp_fwd": [c_void, C.POINTER(VslDesc), C.POINTER(_P), _P],
     "md2_warp_bwd": [c_void, C.POINTER(VslDesc), C.POINTER(_P), _P],
+    "md2_adam_step": [c_void, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I64), _P, _P, _F, _F, _F, _F, _F, _P],
+    "md2_slow_depth": [c_void, C.POINTER(VslDesc), _I32, _F, _F, _F, _F, _P, _P, _P, _I64, _P],
 }
+ADAM_MAX_TENSORS = 16
 EXPORTS = ["md2_version", "md2_last_error", "md2_launch_count"] + list(_SIGS)
 
 _lib = None

@@ -36,6 +36,7 @@ struct md2_ctx {
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
     size_t prof_used = 0;
     void* host = nullptr;   // state of the host-buffer entry point (md2_host.cu), created on first use
+    void* opt = nullptr;    // state of md2_slow_depth (md2_optim.cu), created on first use
 };
 
 namespace md2 {

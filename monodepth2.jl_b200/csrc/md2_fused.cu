@@ -13,6 +13,7 @@
 namespace md2 {
 
 void host_path_destroy(md2_ctx* ctx);   // md2_host.cu
+void opt_path_destroy(md2_ctx* ctx);    // md2_optim.cu
 
 // ------------------------------------------------------------------------------------------
 // error / ctx plumbing
@@ -1305,6 +1306,7 @@ int md2_destroy(md2_ctx* ctx) {
         if (ctx->ws[i].ptr) cudaFree(ctx->ws[i].ptr);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     md2::host_path_destroy(ctx);
+    md2::opt_path_destroy(ctx);
     delete ctx;
     return 0;
 }

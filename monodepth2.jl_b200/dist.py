@@ -45,11 +45,23 @@ def max_over_ranks(value_ms: float, device=None) -> float:
     return float(t.item())
 
 
-def allreduce_mean_(grads):
-    """in-place average of (parameter) gradients over ranks: the one collective of a training step"""
+def allreduce_mean_(grads, n_local=None):
+    """in-place average of (parameter) gradients over ranks.  Each rank's gradient is that of the mean over ITS images,
+    so with unequal shards (shard_bounds when N % world != 0) the full-batch mean of src/training.jl:69 is the
+    n_local-weighted average: pass the rank's shard size as `n_local`; None means equal shards.
+    (The training step uses the bucketed, overlapped GradientBuckets of train_step.py; this is the plain form.)"""
     if dist.is_initialized():
         w = dist.get_world_size()
+        if n_local is None:
+            scale_in, scale_out = 1.0, 1.0 / w
+        else:
+            tot = torch.tensor([float(n_local)], dtype=torch.float64, device=grads[0].device if grads else None)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            scale_in, scale_out = float(n_local) / float(tot.item()), 1.0
         for g in grads:
+            if scale_in != 1.0:
+                g.mul_(scale_in)
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            g.div_(w)
+            if scale_out != 1.0:
+                g.mul_(scale_out)
     return grads

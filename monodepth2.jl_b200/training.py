@@ -276,10 +276,55 @@ def warp(disp, x, Ps, backprojections, projections, invKs, Ks, *, min_depth, max
     return list(_Warp.apply(cfg, disp, x, *Rs, *ts))
 
 
-def train_loss(model, x, auto_loss, cache: TrainCache, parameters: Params, do_visualization=False):
+class AsyncViz:
+    """Device -> host copies of the visualisation outputs (src/training.jl:34-37,71-74: `cpu(disparity)`, `cpu.(warped)`,
+    `cpu(warp_loss)`) that do not stall the training stream: the copy runs on a side stream into pinned buffers (one set
+    per shape, reused) and `ticket.get()` waits for it -- normally one step later, when the PNGs are written."""
+
+    class Ticket:
+        def __init__(self, event, tensors, unpack):
+            self._event, self._tensors, self._unpack = event, tensors, unpack
+
+        def ready(self):
+            return self._event.query()
+
+        def get(self):
+            self._event.synchronize()
+            return self._unpack(self._tensors)
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pinned = {}
+
+    def _buf(self, key, t):
+        b = self._pinned.get(key)
+        if b is None or b.shape != t.shape:
+            b = self._pinned[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        return b
+
+    def fetch(self, tensors, unpack=lambda ts: ts):
+        """start copying the (device) tensors; the producer is the current stream"""
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        out = []
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for k, t in enumerate(tensors):
+                t = t.detach()
+                t.record_stream(self.stream)
+                out.append(self._buf(k, t).copy_(t, non_blocking=True))
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return AsyncViz.Ticket(done, out, unpack)
+
+
+def train_loss(model, x, auto_loss, cache: TrainCache, parameters: Params, do_visualization=False, viz: "AsyncViz | None" = None):
     """Drop-in for src/training.jl:21-78.  `model(x, source_ids, target_id)` returns
     (disparities, poses) exactly like the reference's Model (src/model.jl:8-20); everything
-    after it runs in the fused CUDA path.  Returns (loss, vis_disparity, vis_warped, vis_loss)."""
+    after it runs in the fused CUDA path.  Returns (loss, vis_disparity, vis_warped, vis_loss): host copies like the
+    reference's when do_visualization, else None.  With `viz` (an AsyncViz) the copies run on a side stream and the
+    second return value is a ticket whose .get() yields (vis_disparity, vis_warped, vis_loss); the other two are None."""
     disparities, poses = model(x, cache.source_ids, cache.target_id)
     out = view_synthesis_loss(
         x, list(disparities), [p.rvec for p in poses], [p.tvec for p in poses], cache.K, cache.invK,
@@ -290,8 +335,13 @@ def train_loss(model, x, auto_loss, cache: TrainCache, parameters: Params, do_vi
         K_cm=cache.K_cm, invK_cm=cache.invK_cm)
     if do_visualization:
         loss, vis_warped, vis_loss = out
-        # the reference copies these to the host for logging (src/training.jl:34-37,71-74)
-        return loss, disparities[-1].detach().cpu(), [w.cpu() for w in vis_warped], vis_loss.cpu()
+        S = len(vis_warped)
+        fetcher = viz if viz is not None else AsyncViz(x.device)
+        ticket = fetcher.fetch([disparities[-1], vis_loss, *vis_warped], unpack=lambda ts: (ts[0], list(ts[2:2 + S]), ts[1]))
+        if viz is not None:
+            return loss, ticket, None, None
+        vd, vw, vl = ticket.get()      # the reference's synchronous cpu(...) (src/training.jl:34-37,71-74)
+        return loss, vd, vw, vl
     return out, None, None, None
 
 
@@ -302,3 +352,97 @@ def simple_depth_loss(x, disp, poses, K, invK, *, target_id=1, source_ids=(0, 2)
     return view_synthesis_loss(x, [disp], [p.rvec for p in poses], [p.tvec for p in poses], K, invK,
                                target_id=target_id, source_ids=source_ids, min_depth=min_depth,
                                max_depth=max_depth, normalize_disparity=False, smooth_weight=[1.0], loss_scale=1.0)
+
+
+class Adam:
+    """Flux.Optimise.ADAM(eta, (beta1, beta2)) over a fixed list of CUDA float32 parameter tensors, as ONE fused
+    multi-tensor kernel launch per step (md2_adam_step; the reference calls `Flux.Optimise.update!(optimizer, theta,
+    grads)`, src/Monodepth.jl:165-171, src/simple_depth.jl:43).  The moments and the step counter live in two device
+    tensors (`state`, `clock`) that `state_dict()` / `load_state_dict()` save and restore -- the optimiser half of a
+    checkpoint (the reference's BSON dump, src/Monodepth.jl:189-192, keeps the model only and restarts ADAM cold)."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        if not 1 <= len(self.params) <= L.ADAM_MAX_TENSORS:
+            raise ValueError(f"1 .. {L.ADAM_MAX_TENSORS} tensors per optimiser (flatten the parameters into one buffer)")
+        require_cuda(*self.params)
+        for p in self.params:
+            L._chk(p, "parameter")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        dev = self.params[0].device
+        self.counts = [p.numel() for p in self.params]
+        self.state = torch.zeros(2 * sum(self.counts), device=dev, dtype=_F32)
+        self.clock = torch.zeros(2, device=dev, dtype=torch.int64)
+        self._ctx = Context.get(dev)
+        n = len(self.params)
+        self._p = (C.c_void_p * n)(*[p.data_ptr() for p in self.params])
+        self._n = (C.c_int64 * n)(*self.counts)
+
+    def step(self, grads=None, grad_scale=1.0):
+        """one update; grads default to `p.grad` of every parameter"""
+        grads = [p.grad for p in self.params] if grads is None else list(grads)
+        for g, p in zip(grads, self.params):
+            if g is None or g.shape != p.shape or not g.is_contiguous() or g.dtype != _F32:
+                raise ValueError("every parameter needs a contiguous float32 gradient of its own shape")
+        g_arr = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        self._ctx.call("md2_adam_step", len(self.params), self._p, g_arr, self._n, self.state.data_ptr(), self.clock.data_ptr(),
+                       self.lr, self.betas[0], self.betas[1], self.eps, float(grad_scale))
+
+    @property
+    def steps(self):
+        return int(self.clock[0].item())
+
+    def state_dict(self):
+        return dict(state=self.state.detach().cpu(), clock=self.clock.detach().cpu(), lr=self.lr, betas=self.betas, eps=self.eps,
+                    counts=list(self.counts))
+
+    def load_state_dict(self, sd):
+        if list(sd["counts"]) != list(self.counts):
+            raise ValueError("optimiser state belongs to other parameter shapes")
+        self.state.copy_(sd["state"]); self.clock.copy_(sd["clock"])
+        self.lr, self.betas, self.eps = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"])
+
+
+def slow_depth(x, K, invK, *, target_id=1, source_ids=(0, 2), min_depth=0.1, max_depth=100.0, iters=500, lr=3e-4,
+               log_step=5, on_log=None, disp=None, poses=None):
+    """Drop-in for the reference's triplet optimiser (src/simple_depth.jl:1-62): a full-resolution disparity map
+    (initial value 0.5) and one (rvec, tvec) pose per source (initial rvec (0, 0, 0.01), tvec 0) are fitted to one frame
+    triplet x (N=1,3,C,H,W) with ADAM(3e-4) on  mean(prediction_loss(warp(...))) + smooth_loss(disp, target).
+    The whole loop stays on the device (md2_slow_depth: one CUDA-graph launch per iteration); `on_log(iter, disp, poses)`
+    is called every `log_step` iterations and on the first, where the reference writes its PNG / prints the poses
+    (src/simple_depth.jl:23,46-60).  Returns (disp (N,1,H,W), [Pose, ...], loss history (iters,) on the device)."""
+    x = _f32c(x)
+    require_cuda(x)
+    N, Lf, Cc, H, W = x.shape
+    dev = x.device
+    S = len(source_ids)
+    disp = torch.full((N, 1, H, W), 0.5, device=dev, dtype=_F32) if disp is None else _f32c(disp).clone()
+    if poses is None:
+        poses = [Pose(torch.tensor([[0.0, 0.0, 0.01]] * N, device=dev, dtype=_F32), torch.zeros(N, 3, device=dev, dtype=_F32)) for _ in source_ids]
+    else:
+        poses = [Pose(_f32c(p.rvec).clone(), _f32c(p.tvec).reshape(N, 3).clone()) for p in poses]
+    loss = torch.empty((), device=dev, dtype=_F32)
+    gd = torch.empty_like(disp)
+    gr = [torch.empty_like(p.rvec) for p in poses]
+    gt = [torch.empty_like(p.tvec) for p in poses]
+    Kc, iKc = _cm(_f32c(K.reshape(3, 3))), _cm(_f32c(invK.reshape(3, 3)))   # (column-major copies; they outlive the calls)
+    desc = L.make_vsl_desc(
+        target=x[:, target_id], target_stride=x.stride(0), sources=[x[:, i] for i in source_ids], source_strides=[x.stride(0)] * S,
+        disparities=[disp], K_cm=Kc, invK_cm=iKc, rot=[p.rvec for p in poses],
+        trans=[p.tvec for p in poses], pose_mode=1, invert=[i < target_id for i in source_ids], min_depth=min_depth, max_depth=max_depth,
+        smooth_weight=[1.0], loss_scale=1.0, normalize_disparity=False, loss=loss, grad_disparity=[gd], grad_rot=gr, grad_trans=gt,
+        shape=(N, Cc, H, W))
+    state = torch.zeros(2 * (N * H * W + 6 * N * S), device=dev, dtype=_F32)
+    clock = torch.zeros(2, device=dev, dtype=torch.int64)
+    history = torch.zeros(max(iters, 1), device=dev, dtype=_F32)
+    ctx = Context.get(dev)
+    done = 0
+    while done < iters:
+        # the reference logs on iteration 1 and on every multiple of log_step
+        nxt = iters if on_log is None else min(iters, 1 if done == 0 else (done // log_step + 1) * log_step)
+        ctx.call("md2_slow_depth", C.byref(desc), nxt - done, float(lr), 0.9, 0.999, 1e-8, state.data_ptr(), clock.data_ptr(),
+                 history.data_ptr(), history.numel())
+        done = nxt
+        if on_log is not None and (done == 1 or done % log_step == 0):
+            on_log(done, disp, poses)
+    return disp, poses, history[:iters]

@@ -438,3 +438,47 @@ def view_synthesis_loss_forced(x, disparities, rvecs, tvecs, K, invK, choices, *
         disp_loss = ((ddx * torch.exp(-idx)).mean() + (ddy * torch.exp(-idy)).mean()) * disparity_smoothness * scale
         loss = loss + warp_loss.mean() + disp_loss
     return loss / len(scales)
+
+
+# ----------------------------------------------------------------------------
+# Flux.Optimise.ADAM (Flux v0.12 optimise/optimisers.jl, `apply!(o::ADAM, x, Δ)`; third-party, restated from its
+# published rule) and the triplet optimiser loop of src/simple_depth.jl:1-62
+# ----------------------------------------------------------------------------
+
+
+class FluxAdam:
+    """mt = b1 mt + (1-b1) g;  vt = b2 vt + (1-b2) g^2;  x -= mt / (1-b1^t) / (sqrt(vt / (1-b2^t)) + eps) * eta"""
+
+    def __init__(self, params, eta=1e-3, beta=(0.9, 0.999), eps=1e-8):
+        self.params, self.eta, self.beta, self.eps = list(params), eta, beta, eps
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.bp = [beta[0], beta[1]]
+
+    def step(self, grads):
+        b1, b2 = self.beta
+        with torch.no_grad():
+            for p, g, m, v in zip(self.params, grads, self.m, self.v):
+                m.mul_(b1).add_(g, alpha=1 - b1)
+                v.mul_(b2).add_(g * g, alpha=1 - b2)
+                p.sub_(m / (1 - self.bp[0]) / ((v / (1 - self.bp[1])).sqrt() + self.eps) * self.eta)
+        self.bp = [self.bp[0] * b1, self.bp[1] * b2]
+
+
+def slow_depth(x, K, invK, *, target_id=1, source_ids=(0, 2), min_depth=0.1, max_depth=100.0, iters=500, eta=3e-4):
+    """src/simple_depth.jl:1-62 without the PNG dumps: x (1,L,C,H,W).  Returns (disp, rvecs, tvecs, loss history)."""
+    dt = x.dtype
+    N, L, C, H, W = x.shape
+    disp = torch.full((N, 1, H, W), 0.5, dtype=dt, requires_grad=True)
+    rvecs = [torch.tensor([[0.0, 0.0, 0.01]] * N, dtype=dt, requires_grad=True) for _ in source_ids]
+    tvecs = [torch.zeros(N, 3, dtype=dt, requires_grad=True) for _ in source_ids]
+    theta = [disp] + [t for pair in zip(rvecs, tvecs) for t in pair]
+    opt = FluxAdam(theta, eta=eta)
+    hist = []
+    for _ in range(iters):
+        loss = simple_depth_loss(x, disp, rvecs, tvecs, K, invK, target_id=target_id, source_ids=source_ids,
+                                 min_depth=min_depth, max_depth=max_depth)
+        grads = torch.autograd.grad(loss, theta)
+        opt.step(grads)
+        hist.append(float(loss.detach()))
+    return disp.detach(), [r.detach() for r in rvecs], [t.detach() for t in tvecs], hist
