@@ -1,21 +1,31 @@
-# Monodepth2B200.jl -- Julia binding of libmd2_b200.so (include/md2.h): drop-in replacements, with
-# ChainRulesCore rrules, for the view-synthesis loss entry points of pxl-th/Monodepth2.jl
-# (src/utils.jl, src/training.jl, and the `warp` that src/simple_depth.jl:30-32 calls but the
-# reference never defines).
+# Monodepth2B200.jl -- Julia binding of libmd2_b200.so (include/md2.h) for pxl-th/Monodepth2.jl.
 #
-# STATUS: written against include/md2.h and reviewed, but NOT executed -- there is no Julia in the
-# build image or on the GPU box.  The same C ABI is exercised end to end by the Python ctypes
-# binding (monodepth2.jl_b200/_lib.py) and the -m gpu tests.
+# The file is `include`d INSIDE `module Monodepth`, after the reference's own sources (INTEGRATION.md):
 #
-# Usage inside the reference (see INTEGRATION.md):
-#     include("Monodepth2B200.jl"); using .Monodepth2B200
-#     # src/utils.jl / src/training.jl definitions of the functions below are then shadowed for
-#     # CuArray{Float32} arguments; CPU / Float64 arrays keep using the reference's own methods.
-module Monodepth2B200
+#     # src/Monodepth.jl, after  include("training.jl")
+#     include(joinpath(ENV["MD2_B200_DIR"], "julia", "Monodepth2B200.jl"))   # submodule Monodepth.B200
+#     using .B200: warp                      # the function src/simple_depth.jl:30 calls and the reference never defines
+#
+# It does NOT define functions of its own for the reference's entry points: it `import`s the reference's generic
+# functions and callable structs from the enclosing module and ADDS METHODS to them that are more specific in the array
+# type (`CuArray{Float32}`), plus `ChainRulesCore.rrule`s for those methods, exactly as the reference does for `hat`
+# (src/utils.jl:130-141).  Dispatch then sends every Float32 GPU call of train() / slow_depth() to the CUDA kernels,
+# while CPU arrays, Float64 arrays and the reference's tests (test/runtests.jl, which run on Array{Float64}) keep the
+# reference's own methods.  Cotangents of vector / tuple arguments are returned as plain Vectors / Tuples.
+#
+# STATUS: written against include/md2.h and the reference's signatures and statically reviewed; NOT executed -- there is
+# no Julia toolchain in the build image or on the GPU box.  The very same C ABI is exercised end to end from C
+# (tests/cabi/harness.c) and from Python ctypes (monodepth2.jl_b200/_lib.py) by the -m gpu tests.
+module B200
 
 using CUDA
 using ChainRulesCore
+using Statistics: mean
 import ChainRulesCore: rrule
+# the reference's generics and types this file extends (src/utils.jl, src/training.jl, src/simple_depth.jl, src/Monodepth.jl)
+import ..Monodepth: disparity_to_depth, so3_exp_map, hat, composeT, photometric_loss, prediction_loss, automasking_loss,
+                    _apply_mask, smooth_loss, train_loss, slow_depth, save_disparity
+import ..Monodepth: SSIM, Backproject, Project, TrainCache, Params, Pose
 
 const LIB = get(ENV, "MD2_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libmd2_b200.so"))
 const CuF = CuArray{Float32}

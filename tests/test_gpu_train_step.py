@@ -1,0 +1,154 @@
+"""Row F1 on the GPU: the training step around the loss (src/Monodepth.jl:156-176) -- stand-in model -> fused loss ->
+backward -> [bucketed NCCL all-reduce] -> fused ADAM; visualisation copies on a side stream; checkpoint / resume."""
+import os
+import socket
+
+import pytest
+import torch
+
+import monodepth2_jl_b200 as M
+from oracle import torch_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def batch(n, c, h, w, seed):
+    x, _, _, _ = O.synthetic_batch(n, c, h, w, seed=seed)
+    return x.to(dev())
+
+
+def test_step_trains_and_matches_autograd_plus_torch_adam():
+    """one step of the trainer == the same model / loss with torch.autograd and torch.optim.Adam (the Flux rule and
+    torch's coincide for eps = 1e-8 up to where eps is added; checked to 1e-6)"""
+    W, H = 128, 64
+    trainer, model, cache, hp = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=3)
+    torch.manual_seed(3)
+    ref_model = M.StandInModel(3).to(dev()).train()
+    ref_model.load_state_dict(model.state_dict())
+    ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-4, eps=1e-8)
+    x = batch(2, 3, H, W, 1)
+    losses = []
+    for _ in range(3):
+        loss, _ = trainer.step(x)
+        losses.append(loss.item())
+        ref_opt.zero_grad()
+        l2, *_ = M.train_loss(ref_model, x, None, cache, hp, False)
+        l2.backward()
+        ref_opt.step()
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert trainer.opt.steps == 3
+    # (ADAM's early steps are sign-like: an element whose gradient is rounding noise may step the other way, 2 lr apart)
+    close, total = 0, 0
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert n1 == n2
+        assert (p1 - p2).abs().max().item() <= 2 * 1e-4 * 3 + 1e-6, n1
+        close += torch.isclose(p1, p2, rtol=1e-4, atol=3e-6).sum().item(); total += p1.numel()
+    assert close / total > 0.995, close / total
+    assert losses[-1] != losses[0]
+
+
+def test_visualisation_ticket_and_automasking():
+    W, H = 96, 48
+    trainer, model, cache, hp = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, automasking=True, seed=1)
+    x = batch(2, 3, H, W, 2)
+    loss, ticket = trainer.step(x, do_visualization=True)
+    vd, vw, vl = ticket.get()
+    assert not vd.is_cuda and vd.shape == (2, 1, H, W) and len(vw) == 2 and vw[0].shape == (2, 3, H, W) and vl.shape == (2, 1, H, W)
+    assert vd.is_pinned() and torch.isfinite(vl).all() and 0.0 <= vd.min() and vd.max() <= 1.0
+    # the warp-loss map of the step averages to its photometric share of the loss: mean(vis_loss) is what src/training.jl:66 adds
+    assert 0.0 < vl.mean().item() < loss.item() * 4 * 1.5
+
+
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
+    W, H = 96, 48
+    xs = [batch(2, 3, H, W, 10 + k) for k in range(5)]
+    a, ma, _, _ = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=5)
+    for k in range(3):
+        a.step(xs[k])
+    path = str(tmp_path / "ckpt.pt")
+    a.save_checkpoint(path)                    # model + ADAM moments + step counter
+    for k in range(3, 5):
+        a.step(xs[k])
+    b, mb, _, _ = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=99)    # different initial weights
+    b.load_checkpoint(path)
+    assert b.steps == 3 and b.opt.steps == 3
+    for k in range(3, 5):
+        b.step(xs[k])
+    frac = lambda m1, m2: sum(torch.isclose(p1, p2, rtol=1e-4, atol=2e-6).sum().item() for p1, p2 in zip(m1.parameters(), m2.parameters())) / \
+        sum(p.numel() for p in m1.parameters())
+    assert frac(ma, mb) > 0.995
+    # a cold optimiser (what resuming from the reference's model-only BSON dump does) does NOT reproduce the trajectory
+    c, mc, _, _ = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=99)
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    with torch.no_grad():
+        mc.load_state_dict(sd["model"])
+    for k in range(3, 5):
+        c.step(xs[k])
+    assert frac(ma, mc) < 0.9
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    d = torch.device("cuda", rank)
+    torch.cuda.set_device(d)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=d)
+    from monodepth2_jl_b200 import dist as D
+    W, H, NB = 96, 48, 4
+    x, _, _, _ = O.synthetic_batch(NB, 3, H, W, seed=31)
+    xs = D.shard_batch(x, rank, world).to(d)
+    res = {}
+    for overlap in (True, False):
+        trainer, model, _, _ = M.make_training_setup(W, H, d, channels=3, batch_size=NB, seed=7, overlap=overlap, bucket_bytes=1 << 20)
+        for m in model.modules():               # batch statistics are per rank (as in any data-parallel BatchNorm): freeze them
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+        loss, _ = trainer.step(xs)
+        res[overlap] = (trainer.flat.grad.cpu().numpy().copy(), trainer.flat.data.cpu().numpy().copy(), float(D.global_loss(loss, xs.shape[0])),
+                        len(trainer.flat.buckets), trainer.flat.calls)
+    g = [torch.full((3,), float(rank + 1), device=d)]
+    D.allreduce_mean_(g)
+    q.put((rank, res, g[0].cpu().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_two_rank_nccl_step_equals_the_full_batch_step():
+    """data-parallel step over NCCL at world size 2: the all-reduced gradient (sum over ranks x 1/2) and the updated
+    parameters equal those of ONE process stepping on the whole batch; overlapped and blocking all-reduce agree"""
+    import numpy as np
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    W, H, NB = 96, 48, 4
+    x, _, _, _ = O.synthetic_batch(NB, 3, H, W, seed=31)
+    full, model, _, _ = M.make_training_setup(W, H, dev(), channels=3, batch_size=NB, seed=7)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+    loss, _ = full.step(x.to(dev()))
+    gfull, pfull = full.flat.grad.cpu().numpy(), full.flat.data.cpu().numpy()
+    for rank, r, shared in res:
+        assert shared == [1.5, 1.5, 1.5]
+        for overlap in (True, False):
+            g, p, gl, nb, calls = r[overlap]
+            assert nb >= 4 and calls == nb
+            assert abs(gl - loss.item()) <= 1e-5 * abs(loss.item())
+            assert np.abs(0.5 * g - gfull).max() <= 2e-4 * np.abs(gfull).max()
+            assert np.abs(p - pfull).max() <= 2.5e-4          # (ADAM's first step is +-lr per element: sign flips of ~0 gradients)
+            assert (np.abs(p - pfull) < 1e-6).mean() > 0.98
+        assert np.array_equal(r[True][0], r[False][0])
