@@ -73,44 +73,61 @@ function rrule(::typeof(disparity_to_depth), disparity::CuF, min_depth, max_dept
 end
 
 # ---------------------------------------------------------------------------------------------
-# A2 Backproject / A3 Project (src/utils.jl:41-99): same callable structs as the reference
+# A2 Backproject / A3 Project (src/utils.jl:41-99): methods on the REFERENCE's callable structs.  The reference stores
+# no width / height: Backproject holds the (3, W*H) pixel grid, Project the (W-1, H-1) normaliser; both are read back
+# once per object (cached by identity), never per call.
 # ---------------------------------------------------------------------------------------------
-struct Backproject; width::Int; height::Int; end
-Backproject(::Type{T} = Float32; width, height) where T = Backproject(width, height)
+const SIZE_CACHE = IdDict{Any, Tuple{Int, Int}}()
+function image_size(b::Backproject)
+    get!(SIZE_CACHE, b.coordinates) do
+        last_px = Array(b.coordinates[:, end])                  # (W, H, 1): the grid is filled w = 1:W, h = 1:H (src/utils.jl:47-51)
+        (round(Int, last_px[1]), round(Int, last_px[2]))
+    end
+end
+function image_size(p::Project)
+    get!(SIZE_CACHE, p.normalizer) do
+        wh = vec(Array(p.normalizer))                           # (W - 1, H - 1), src/utils.jl:72
+        (round(Int, wh[1]) + 1, round(Int, wh[2]) + 1)
+    end
+end
+ChainRulesCore.@non_differentiable image_size(::Any)
+
 function (b::Backproject)(depth::CuF, invK::CuF)            # depth (1,P,N), invK (3,3) -> (3,P,N)
-    N = length(depth) ÷ (b.width * b.height)
-    pts = CUDA.zeros(Float32, 3, b.width * b.height, N)
+    W, H = image_size(b)
+    N = length(depth) ÷ (W * H)
+    pts = CUDA.zeros(Float32, 3, W * H, N)
     check(ccall((:md2_backproject_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
-                ctx(), depth, invK, pts, b.width, b.height, N, stream()))
+                ctx(), depth, invK, pts, W, H, N, stream()))
     pts
 end
 function rrule(b::Backproject, depth::CuF, invK::CuF)
     y = b(depth, invK)
+    W, H = image_size(b)
     function pb(Δ)
         g = similar(depth)
         check(ccall((:md2_backproject_bwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
-                    ctx(), CuF(unthunk(Δ)), invK, g, b.width, b.height, size(y, 3), stream()))
+                    ctx(), CuF(unthunk(Δ)), invK, g, W, H, size(y, 3), stream()))
         NoTangent(), g, NoTangent()
     end
     y, pb
 end
 
-struct Project; width::Int; height::Int; end
-Project(::Type{T} = Float32; width, height) where T = Project(width, height)
 function (p::Project)(points::CuF, K::CuF, R::CuF, t::CuF)  # (3,P,N),(3,3[,1]),(3,3,N),(3,1,N) -> (2,P,N)
+    W, H = image_size(p)
     N = size(points, 3)
     uv = CUDA.zeros(Float32, 2, size(points, 2), N)
     check(ccall((:md2_project_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
-                ctx(), points, K, R, t, uv, p.width, p.height, N, stream()))
+                ctx(), points, K, R, t, uv, W, H, N, stream()))
     uv
 end
 function rrule(p::Project, points::CuF, K::CuF, R::CuF, t::CuF)
     y = p(points, K, R, t)
+    W, H = image_size(p)
     function pb(Δ)
         gp, gR, gt = similar(points), similar(R), similar(t)
         check(ccall((:md2_project_bwd, LIB), Cint,
                     (Ptr{Cvoid}, P32, P32, P32, P32, P32, P32, P32, P32, Cint, Cint, Cint, Ptr{Cvoid}),
-                    ctx(), points, K, R, t, CuF(unthunk(Δ)), gp, gR, gt, p.width, p.height, size(points, 3), stream()))
+                    ctx(), points, K, R, t, CuF(unthunk(Δ)), gp, gR, gt, W, H, size(points, 3), stream()))
         NoTangent(), gp, NoTangent(), gR, gt
     end
     y, pb
@@ -170,9 +187,7 @@ end
 # ---------------------------------------------------------------------------------------------
 # A7 SSIM (src/utils.jl:13-39)
 # ---------------------------------------------------------------------------------------------
-struct SSIM; c1::Float64; c2::Float64; end
-SSIM() = SSIM(0.01^2, 0.03^2)
-function (ssim::SSIM)(x::CuF, y::CuF)
+function (ssim::SSIM)(x::CuF, y::CuF)                      # (more specific than the reference's (x::AbstractArray{T}, y::K))
     W, H, C, N = size(x); out = similar(x)
     check(ccall((:md2_ssim_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, P32, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
                 ctx(), x, y, out, W, H, C, N, stream()))
@@ -226,7 +241,7 @@ prediction_loss(ssim, predictions, target::CuF) =
               Int64(length(target) ÷ size(target, 4)), 0.85f0, size(target))[1]
 function rrule(::typeof(prediction_loss), ssim, predictions, target::CuF)
     out, pb = _photomin_rrule(collect(predictions), target, 0.85f0)
-    out, Δ -> ((gp, gt) = pb(Δ); (NoTangent(), NoTangent(), Tangent{typeof(predictions)}(gp...), gt))
+    out, Δ -> ((gp, gt) = pb(Δ); (NoTangent(), NoTangent(), predictions isa Tuple ? Tuple(gp) : gp, gt))   # plain Vector / Tuple cotangent
 end
 function automasking_loss(ssim, inputs::CuF, target::CuF; source_ids)      # inputs (W,H,C,L,N): frames passed as views
     W, H, C, L, N = size(inputs); fstride = W * H * C
@@ -234,24 +249,26 @@ function automasking_loss(ssim, inputs::CuF, target::CuF; source_ids)      # inp
     _photomin(preds, fill(Int64(fstride * L), length(source_ids)), target, Int64(W * H * C), 0.85f0, (W, H, C, N))[1]
 end
 ChainRulesCore.@non_differentiable automasking_loss(::Any...)              # a constant in train() (src/Monodepth.jl:159-164)
-_apply_mask(mask::CuF, warp_loss::CuF) = ifelse.(mask .<= warp_loss, mask, warp_loss)   # mask first: wins ties
+# _apply_mask (src/training.jl:17-19) keeps the reference's method: `minimum(cat(mask, warp_loss; dims=3); dims=3)` runs on
+# CuArrays as it is, and inside train_loss it is fused into the kernel anyway (mask first: it wins ties).
 
 # ---------------------------------------------------------------------------------------------
 # A8 smooth_loss (src/utils.jl:143-173)
 # ---------------------------------------------------------------------------------------------
-function smooth_loss(disparity::CuF, image::CuF; normalize::Bool = false)
+function _smooth(disparity::CuF, image::CuF, normalize::Bool)
     W, H, C, N = size(image); out = CUDA.zeros(Float32, 1)
     check(ccall((:md2_smooth_loss_fwd, LIB), Cint, (Ptr{Cvoid}, P32, P32, Int64, P32, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
                 ctx(), disparity, image, W * H * C, out, normalize, W, H, C, N, stream()))
     CUDA.@allowscalar out[1]
 end
-function rrule(::typeof(smooth_loss), disparity::CuF, image::CuF; normalize::Bool = false)
-    y = smooth_loss(disparity, image; normalize)
+smooth_loss(disparity::CuF, image::CuF) = _smooth(disparity, image, false)        # disparity (W,H,N), image (W,H,C,N)
+function rrule(::typeof(smooth_loss), disparity::CuF, image::CuF)
+    y = _smooth(disparity, image, false)
     function pb(Δ)
         W, H, C, N = size(image); gd, gi = similar(disparity), similar(image)
         check(ccall((:md2_smooth_loss_bwd, LIB), Cint,
                     (Ptr{Cvoid}, P32, P32, Int64, Cfloat, P32, P32, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}),
-                    ctx(), disparity, image, W * H * C, Float32(unthunk(Δ)), gd, gi, normalize, W, H, C, N, stream()))
+                    ctx(), disparity, image, W * H * C, Float32(unthunk(Δ)), gd, gi, false, W, H, C, N, stream()))
         NoTangent(), gd, gi
     end
     y, pb
@@ -277,6 +294,7 @@ struct VslDesc
     viz_warped::NTuple{MAX_S, P32}; viz_loss::P32
     saved::P32
     zero_grad_source::Int32
+    debug_choices::CuPtr{Int32}          # test hook of the C ABI; always NULL here
 end
 pad(v, n, z) = ntuple(i -> i <= length(v) ? v[i] : z, n)
 frameptr(x::CuF, id) = pointer(x, (id - 1) * size(x, 1) * size(x, 2) * size(x, 3) + 1)   # x (W,H,C,L,N), 1-based frame id
@@ -308,7 +326,7 @@ function vsl_fwdbwd(x::CuF, disparities, rvecs, tvecs, K::CuF, invK::CuF; target
         Float32(loss_scale === nothing ? 1 / L : loss_scale), Int32(normalize), ptr(loss),
         pad([ptr(g) for g in gd], MAX_L, P32(0)), pad([ptr(g) for g in gr], MAX_S, P32(0)),
         pad([ptr(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
-        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0), Int32(0)))
+        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0), Int32(0), CuPtr{Int32}(0)))
     GC.@preserve x disparities rvecs tvecs K invK auto_loss loss gd gr gt vw vl begin
         check(ccall((:md2_view_synthesis_loss_fwdbwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Ptr{Cvoid}),
                     ctx(), desc, 1f0, stream()))
@@ -343,7 +361,7 @@ function vsl_fwdbwd_host!(loss::Vector{Float32}, grads, x::Array{Float32,5}, dis
         Float32(1 / L), Int32(normalize), hp(loss),
         pad([hp(g) for g in gd], MAX_L, P32(0)), pad([hp(g) for g in gr], MAX_S, P32(0)),
         pad([hp(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
-        pad(P32[], MAX_S, P32(0)), P32(0), P32(0), Int32(1)))
+        pad(P32[], MAX_S, P32(0)), P32(0), P32(0), Int32(1), CuPtr{Int32}(0)))
     GC.@preserve x disparities rvecs tvecs K invK loss gd gr gt begin
         check(ccall((:md2_view_synthesis_loss_fwdbwd_host, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Cint),
                     ctx(), desc, 1f0, Cint(groups)))
@@ -360,18 +378,18 @@ function rrule(::typeof(view_synthesis_loss), x, disparities, rvecs, tvecs, K, i
     loss, (gd, gr, gt), _, _ = vsl_fwdbwd(x, disparities, rvecs, tvecs, K, invK; kw...)
     function pb(Δ)
         s = Float32(unthunk(Δ))
-        NoTangent(), NoTangent(), Tangent{typeof(disparities)}((s .* g for g in gd)...),
-        Tangent{typeof(rvecs)}((s .* g for g in gr)...), Tangent{typeof(tvecs)}((s .* g for g in gt)...),
-        NoTangent(), NoTangent()
+        # cotangents of Vector-of-array arguments are plain Vectors of arrays (what Zygote accumulates into)
+        NoTangent(), NoTangent(), [s .* g for g in gd], [s .* g for g in gr], [s .* g for g in gt], NoTangent(), NoTangent()
     end
     (CUDA.@allowscalar loss[1]), pb
 end
 
 """
-Drop-in for `train_loss` (src/training.jl:21-78): `model`, `cache::TrainCache`, `parameters::Params`
-are the reference's own objects; frame ids stay 1-based here.
+`train_loss` (src/training.jl:21-78) for a Float32 batch on the GPU: a METHOD of the reference's own generic (more
+specific in `x` than its `x::AbstractArray{T}`), taking the reference's `TrainCache` / `Params`; frame ids are 1-based.
+`model(...)` is differentiated by Zygote as before; everything after it is one rrule.
 """
-function train_loss(model, x::CuF, auto_loss, cache, parameters, do_visualization)
+function train_loss(model, x::CuArray{Float32, 5}, auto_loss, cache::TrainCache, parameters::Params, do_visualization)
     disparities, poses = model(x, cache.source_ids, cache.target_id)
     kw = (; target_id = cache.target_id, source_ids = cache.source_ids, scales = cache.scales,
           min_depth = parameters.min_depth, max_depth = parameters.max_depth,
@@ -408,7 +426,7 @@ function _warp_desc(disp, x, Ps, invKs, Ks, min_depth, max_depth, source_ids, gr
             pad([ptr(disp)], MAX_L, z), pad(Int32[W], MAX_L, Int32(0)), pad(Int32[H], MAX_L, Int32(0)), ptr(Ks), ptr(invKs),
             Int32(0), pad([ptr(P[1]) for P in Ps], MAX_S, z), pad([ptr(P[2]) for P in Ps], MAX_S, z), pad(Int32[], MAX_S, Int32(0)),
             z, Float32(min_depth), Float32(max_depth), pad(Float32[], MAX_L, 0f0), 1f0, Int32(0), z,
-            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z, Int32(0))
+            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z, Int32(0), CuPtr{Int32}(0))
 end
 function rrule(::typeof(warp), disp::CuF, x::CuF, Ps, backprojections, projections, invKs::CuF, Ks::CuF; min_depth, max_depth, source_ids)
     outs = warp(disp, x, Ps, backprojections, projections, invKs, Ks; min_depth, max_depth, source_ids)
@@ -419,13 +437,56 @@ function rrule(::typeof(warp), disp::CuF, x::CuF, Ps, backprojections, projectio
         GC.@preserve disp x Ps invKs Ks gouts gd gR gt begin
             check(ccall((:md2_warp_bwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Ptr{P32}, Ptr{Cvoid}), ctx(), desc, [ptr(g) for g in gouts], stream()))
         end
-        NoTangent(), gd, NoTangent(), Tangent{typeof(Ps)}((Tangent{typeof(P)}(r, t) for (P, r, t) in zip(Ps, gR, gt))...),
+        NoTangent(), gd, NoTangent(), [(r, t) for (r, t) in zip(gR, gt)],        # Ps is a Vector of (R, t) tuples
         NoTangent(), NoTangent(), NoTangent(), NoTangent()
     end
     outs, pb
 end
 
-export disparity_to_depth, Backproject, Project, so3_exp_map, hat, composeT, SSIM, photometric_loss, prediction_loss,
-       automasking_loss, _apply_mask, smooth_loss, warp, train_loss, view_synthesis_loss
+"""
+`slow_depth` (src/simple_depth.jl:1-62) for a Float32 triplet on the GPU: a METHOD of the reference's generic.  The 500
+ADAM(3e-4) iterations over (disparity, 2 poses) run as a device-resident loop (`md2_slow_depth`: four launches per
+iteration replayed from a CUDA graph); the host is involved only every `log_step` iterations, where the reference writes
+its PNG and prints the poses.
+"""
+function slow_depth(x::CuArray{Float32, 5}, ssim, backprojections, projections, invKs::CuF, Ks::CuF, transfer;
+                    target_id, source_ids, min_depth, max_depth, log_dir)
+    W, H, C, Lf, N = size(x); S = length(source_ids)
+    disp = CUDA.fill(0.5f0, W, H, 1, N)                                            # src/simple_depth.jl:8
+    rvecs = [CuArray(repeat(Float32[0, 0, 0.01], 1, N)) for _ in 1:S]              # :9-13
+    tvecs = [CUDA.zeros(Float32, 3, 1, N) for _ in 1:S]
+    loss = CUDA.zeros(Float32, 1); gd = similar(disp); gr = similar.(rvecs); gt = similar.(tvecs)
+    state = CUDA.zeros(Float32, 2 * (W * H * N + 6 * N * S)); clock = CUDA.zeros(Int64, 2)
+    iters, log_step = 500, 5
+    history = CUDA.zeros(Float32, iters)
+    fs = Int64(W * H * C * Lf); z = P32(0)
+    desc = Ref(VslDesc(W, H, N, C, S, 1, frameptr(x, target_id), fs,
+        pad([frameptr(x, i) for i in source_ids], MAX_S, z), pad(fill(fs, S), MAX_S, Int64(0)),
+        pad([ptr(disp)], MAX_L, z), pad(Int32[W], MAX_L, Int32(0)), pad(Int32[H], MAX_L, Int32(0)), ptr(Ks), ptr(invKs), Int32(1),
+        pad(ptr.(rvecs), MAX_S, z), pad(ptr.(tvecs), MAX_S, z), pad(Int32[i < target_id for i in source_ids], MAX_S, Int32(0)), z,
+        Float32(min_depth), Float32(max_depth), pad(Float32[1], MAX_L, 0f0), 1f0, Int32(0), ptr(loss),
+        pad([ptr(gd)], MAX_L, z), pad(ptr.(gr), MAX_S, z), pad(ptr.(gt), MAX_S, z), pad(P32[], MAX_S, z),
+        pad(P32[], MAX_S, z), z, z, Int32(0), CuPtr{Int32}(0)))
+    done = 0
+    GC.@preserve x disp rvecs tvecs loss gd gr gt state clock history Ks invKs begin
+        while done < iters
+            nxt = done == 0 ? 1 : min(iters, (done ÷ log_step + 1) * log_step)      # logs on iteration 1 and every 5th (:23)
+            check(ccall((:md2_slow_depth, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{VslDesc}, Cint, Cfloat, Cfloat, Cfloat, Cfloat, P32, CuPtr{Int64}, P32, Int64, Ptr{Cvoid}),
+                        ctx(), desc, nxt - done, 3f-4, 0.9f0, 0.999f0, 1f-8, state, clock, history, iters, stream()))
+            done = nxt
+            save_disparity(reshape(Array(disp), (W, H)), joinpath(log_dir, "d-$done.png"))   # :47-49
+            println(done, " ", mean(Array(disp)))
+            for s in 1:S
+                println("p$s.rvec, p$s.tvec = ", (Array(rvecs[s]), Array(tvecs[s])))
+            end
+        end
+    end
+    disp, [Pose(r, t) for (r, t) in zip(rvecs, tvecs)], Array(history)
+end
 
-end # module
+# `warp` is the only NEW name (the reference calls it and never defines it): `using .B200: warp` in Monodepth.jl.
+# view_synthesis_loss / vsl_fwdbwd / vsl_fwdbwd_host! are this binding's own additions.
+export warp, view_synthesis_loss, vsl_fwdbwd, vsl_fwdbwd_host!
+
+end # module B200

@@ -95,3 +95,32 @@ def test_package_synthetic_data_equals_test_side_generator():
             assert all(torch.equal(u, v) for u, v in zip(a[k], b[k]))
     for u, v in zip(SY.make_K(416, 128), O.make_K(416, 128)):
         assert torch.equal(u, v)
+
+
+def test_julia_binding_is_in_step_with_the_header():
+    """static checks of julia/Monodepth2B200.jl (no Julia in the image): its mirror of md2_vsl_desc lists the header's
+    fields in the header's order, every ccall names an exported symbol, and it extends the reference's generics instead
+    of defining its own (`import ..Monodepth: ...`)"""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "md2.h")).read()
+    body = hdr[hdr.index("typedef struct md2_vsl_desc {"):hdr.index("} md2_vsl_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for stmt in body.split("{", 1)[1].split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        first, *rest = stmt.split(",")
+        names = [first.split()[-1]] + [r.strip() for r in rest]
+        c_fields += [re.sub(r"\[.*\]", "", n).lstrip("*") for n in names]
+    jl = open(os.path.join(ROOT, "monodepth2.jl_b200", "julia", "Monodepth2B200.jl")).read()
+    jbody = jl[jl.index("struct VslDesc"):]
+    jbody = jbody[:jbody.index("\nend")]
+    j_fields = re.findall(r"(\w+)::", re.sub(r"#.*", "", jbody))
+    assert j_fields == c_fields
+    for sym in set(re.findall(r"ccall\(\(:(\w+), LIB\)", jl)):
+        assert sym in L.EXPORTS, sym
+    assert "import ..Monodepth:" in jl and "module B200" in jl
+    for name in ("train_loss", "slow_depth", "disparity_to_depth", "composeT", "smooth_loss", "prediction_loss", "automasking_loss"):
+        assert re.search(r"import \.\.Monodepth:[^#]*\b" + name + r"\b", jl, flags=re.S), name
+    assert not re.search(r"^struct (SSIM|Backproject|Project)\b", jl, flags=re.M)      # the reference's own structs are extended
