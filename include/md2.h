@@ -185,6 +185,14 @@ int md2_view_synthesis_loss_fwdbwd(md2_ctx*, const md2_vsl_desc*, float seed, md
  * three streams, and the pipeline is replayed as one CUDA graph while the descriptor stays the same.
  * Synchronous: returns when every output is in host memory.  saved / viz_* must be NULL. */
 int md2_view_synthesis_loss_fwdbwd_host(md2_ctx*, const md2_vsl_desc* host_desc, float seed, int32_t groups);
+/* Asynchronous form, for a caller that double-buffers its batches (a data loader one step ahead): `submit` enqueues the
+ * call on lane 0 or 1 and returns at once; `md2_host_wait(lane)` blocks until that call's outputs are in host memory.
+ * The two lanes own separate streams, staging buffers, scratch and cached graphs, so the device-to-host copies of step i
+ * overlap the host-to-device copies and kernels of step i+1 (submit(i+1, lane B) before wait(lane A)).  The host
+ * buffers of a submitted descriptor must stay valid and untouched until its wait returns; submitting on a lane with an
+ * uncollected call collects that call first.  md2_view_synthesis_loss_fwdbwd_host == submit + wait on lane 0. */
+int md2_view_synthesis_loss_fwdbwd_host_submit(md2_ctx*, const md2_vsl_desc* host_desc, float seed, int32_t groups, int32_t lane);
+int md2_host_wait(md2_ctx*, int32_t lane);
 
 /* warp: disparity (W,H,1,N) -> S warped images (W,H,C,N); uses the desc fields
  * W,H,N,C,S, source*, disparity[0], K, invK, pose_*, rot, trans, invert, min/max_depth;

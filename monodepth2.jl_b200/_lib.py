@@ -153,6 +153,8 @@ _SIGS = {
     "md2_view_synthesis_loss_bwd": [c_void, C.POINTER(VslDesc), _F, _P],
     "md2_view_synthesis_loss_fwdbwd": [c_void, C.POINTER(VslDesc), _F, _P],
     "md2_view_synthesis_loss_fwdbwd_host": [c_void, C.POINTER(VslDesc), _F, _I32],
+    "md2_view_synthesis_loss_fwdbwd_host_submit": [c_void, C.POINTER(VslDesc), _F, _I32, _I32],
+    "md2_host_wait": [c_void, _I32],
     "md2_warp_fwd": [c_void, C.POINTER(VslDesc), C.POINTER(_P), _P],
     "md2_warp_bwd": [c_void, C.POINTER(VslDesc), C.POINTER(_P), _P],
     "md2_adam_step": [c_void, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I64), _P, _P, _F, _F, _F, _F, _F, _P],

@@ -23,20 +23,25 @@ struct Workspace {
 
 enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, MD2_WS_GDISP,
        MD2_WS_MISC, MD2_WS_COUNT };
+// workspace banks: calls that may be in flight at the same time must not share scratch.  Bank 0 serves the
+// device-pointer entry points (one stream at a time, md2.h), banks 1.. the lanes of the host-buffer entry point.
+enum { MD2_HOST_LANES = 2, MD2_WS_BANKS = 1 + MD2_HOST_LANES };
 
 #include <vector>
 struct md2_ctx {
     int device;
     int64_t launches;
     int sm_count = 148;
-    int64_t ws_gen = 0;  // bumped whenever a workspace slot is (re)allocated: captured CUDA graphs hold the old pointers
-    md2::Workspace ws[MD2_WS_COUNT];
+    int bank = 0;                          // workspace bank the next run_vsl uses (set by the entry points)
+    int64_t ws_gen[MD2_WS_BANKS] = {};     // bumped whenever a slot of the bank is (re)allocated: captured CUDA graphs hold the old pointers
+    md2::Workspace ws[MD2_WS_BANKS][MD2_WS_COUNT];
     // optional device timing of the dominant (fused tile) kernel, see md2_profile_*
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
     size_t prof_used = 0;
-    void* host = nullptr;   // state of the host-buffer entry point (md2_host.cu), created on first use
+    void* host[MD2_HOST_LANES] = {};   // lanes of the host-buffer entry point (md2_host.cu), created on first use
     void* opt = nullptr;    // state of md2_slow_depth (md2_optim.cu), created on first use
+    void* replay = nullptr; // CUDA-graph cache of the device-pointer fused calls (md2_fused.cu), created on first use
 };
 
 namespace md2 {
@@ -85,6 +90,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Warp-aggregated scatter of one bilinear tap pair (left tap aL += vL, right tap aR += vR; nullptr = the tap does not exist).
+// Neighbouring lanes hold neighbouring output pixels, and under a smooth warp lane i's RIGHT tap is the very address of
+// lane i+1's LEFT tap: the pair is merged in registers (one shuffle each way) and issued as ONE red.global.add by the
+// receiving lane, so a pixel costs ~1 atomic per tap row and channel instead of 2 (the per-tap atomicAdd of a
+// thread-per-pixel sampler backward -- NNlib's -- serialises exactly those collisions in the L2).
+// Must be called by all 32 lanes of the warp (lanes without work pass nullptrs).
+__device__ __forceinline__ void red_pair_merged(float* aL, float* aR, float vL, float vR, int lane) {
+    const unsigned long long nbL = __shfl_down_sync(0xffffffffu, reinterpret_cast<unsigned long long>(aL), 1);
+    const bool give = aR != nullptr && lane < 31 && nbL == reinterpret_cast<unsigned long long>(aR);
+    const float recv = __shfl_up_sync(0xffffffffu, give ? vR : 0.f, 1);
+    if (aL) atomicAdd(aL, lane > 0 ? vL + recv : vL);
+    if (aR && !give) atomicAdd(aR, vR);
 }
 
 // Deterministic block-wide sum of NV values per thread; result valid in thread 0's out[].

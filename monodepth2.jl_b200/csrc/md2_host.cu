@@ -33,10 +33,15 @@ struct HostPath {
     float key_seed = 0.f;
     int64_t key_ws_gen = -1;       // ctx workspace generation the graph was captured with (the graph holds those pointers)
     bool have_key = false;
+    // a submitted call whose outputs have not been collected yet (md2_host_wait)
+    bool pending = false;
+    md2_vsl_desc pend_desc;
+    int pend_groups = 0;
+    size_t pend_small_in = 0;
 };
 
-static HostPath* host_path(md2_ctx* ctx) {
-    if (!ctx->host) {
+static HostPath* host_path(md2_ctx* ctx, int lane) {
+    if (!ctx->host[lane]) {
         HostPath* h = new HostPath();
         bool ok = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking) == cudaSuccess &&
@@ -52,13 +57,13 @@ static HostPath* host_path(md2_ctx* ctx) {
             delete h;
             return nullptr;
         }
-        ctx->host = h;
+        ctx->host[lane] = h;
     }
-    return static_cast<HostPath*>(ctx->host);
+    return static_cast<HostPath*>(ctx->host[lane]);
 }
 
-void host_path_destroy(md2_ctx* ctx) {
-    HostPath* h = static_cast<HostPath*>(ctx->host);
+static void host_lane_destroy(md2_ctx* ctx, int lane) {
+    HostPath* h = static_cast<HostPath*>(ctx->host[lane]);
     if (!h) return;
     if (h->exec) cudaGraphExecDestroy(h->exec);
     if (h->dbuf) cudaFree(h->dbuf);
@@ -68,7 +73,11 @@ void host_path_destroy(md2_ctx* ctx) {
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
     for (int k = 0; k < HOST_MAX_GROUPS; ++k) { cudaEventDestroy(h->ev_in[k]); cudaEventDestroy(h->ev_done[k]); }
     delete h;
-    ctx->host = nullptr;
+    ctx->host[lane] = nullptr;
+}
+
+void host_path_destroy(md2_ctx* ctx) {
+    for (int lane = 0; lane < MD2_HOST_LANES; ++lane) host_lane_destroy(ctx, lane);
 }
 
 // bump allocator over the staging buffer (256-byte aligned pieces)
@@ -269,11 +278,34 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
     return 0;
 }
 
-static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups) {
+// wait for the call in flight on a lane and move its small outputs (pose gradients, loss) into the caller's buffers
+static int collect(md2_ctx* ctx, int lane) {
+    HostPath* h = static_cast<HostPath*>(ctx->host[lane]);
+    if (!h || !h->pending) return 0;
+    MD2_CHECK(cudaStreamSynchronize(h->s_run));
+    h->pending = false;
+    const md2_vsl_desc* d = &h->pend_desc;
+    const int pr = d->pose_mode == 0 ? 9 : 3;
+    const float* q = h->hsmall + h->pend_small_in;
+    for (int s = 0; s < d->S; ++s) {
+        if (d->grad_rot[s]) memcpy(d->grad_rot[s], q, sizeof(float) * pr * d->N);
+        q += (size_t)pr * d->N;
+        if (d->grad_trans[s]) memcpy(d->grad_trans[s], q, sizeof(float) * 3 * d->N);
+        q += (size_t)3 * d->N;
+    }
+    double loss = 0.0;
+    for (int k = 0; k < h->pend_groups; ++k) loss += (double)q[k];
+    *d->loss = (float)loss;
+    return 0;
+}
+
+// enqueue one call on a lane (its own streams, staging buffers, workspace bank and cached graph); returns at once
+static int submit(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups, int lane) {
     MD2_REQUIRE(d != nullptr, "null descriptor");
     MD2_REQUIRE(d->N >= 1 && d->S >= 1 && d->S <= MAX_S && d->L >= 1 && d->L <= MAX_L, "bad N / S / L");
     MD2_REQUIRE(d->target && d->K && d->invK && d->loss, "null target / K / invK / loss");
     MD2_REQUIRE(!d->saved && !d->viz_loss && !d->viz_warped[0] && !d->viz_warped[1], "saved / viz outputs are not supported by the host entry point");
+    MD2_REQUIRE(!d->debug_choices, "debug_choices is not supported by the host entry point");
     for (int s = 0; s < d->S; ++s) MD2_REQUIRE(d->source[s] && d->rot[s] && d->trans[s], "null source / pose");
     for (int l = 0; l < d->L; ++l) MD2_REQUIRE(d->disparity[l] && d->grad_disparity[l], "null disparity / grad_disparity");
     if (groups < 1) groups = 1;
@@ -281,8 +313,11 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
     if (groups > d->N) groups = d->N;
     MD2_USE_DEVICE(ctx);
     MD2_REQUIRE(!ctx->prof_on, "kernel profiling (md2_profile_enable) is not available on the host entry point");
-    HostPath* h = host_path(ctx);
+    HostPath* h = host_path(ctx, lane);
     if (!h) return 1;
+    if (collect(ctx, lane)) return 1;          // a lane holds one call at a time: an uncollected one is finished first
+    struct BankGuard { md2_ctx* c; int prev; ~BankGuard() { c->bank = prev; } } bank_guard{ctx, ctx->bank};
+    ctx->bank = 1 + lane;
     Mirror m;
     const size_t need = carve(d, nullptr, m);
     if (need > h->dbytes) {
@@ -308,7 +343,7 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
             memcpy(q, d->trans[s], sizeof(float) * 3 * d->N); q += (size_t)3 * d->N;
         }
     }
-    const bool same = h->have_key && h->exec && h->key_groups == groups && h->key_seed == seed && h->key_ws_gen == ctx->ws_gen &&
+    const bool same = h->have_key && h->exec && h->key_groups == groups && h->key_seed == seed && h->key_ws_gen == ctx->ws_gen[ctx->bank] &&
                       memcmp(&h->key, d, sizeof(*d)) == 0;
     if (!same) {
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
@@ -316,11 +351,12 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
         // first call for this descriptor: run eagerly (sizes every workspace, validates the arguments) ...
         g_trace.on = getenv("MD2_HOST_TRACE") != nullptr;
         if (enqueue(ctx, h, d, m, seed, groups)) return 1;
-        MD2_CHECK(cudaStreamSynchronize(h->s_run));
-        g_trace.dump();
+        if (g_trace.on) { MD2_CHECK(cudaStreamSynchronize(h->s_run)); g_trace.dump(); }
         g_trace.on = false;
-        // ... then capture the same pipeline for the calls that follow
+        // ... then capture the same pipeline for the calls that follow.  (The capture is made now -- nothing executes
+        // while capturing, it only needs the workspaces to have their final sizes, which the eager call ensured.)
         if (!getenv("MD2_HOST_NO_GRAPH")) {
+            MD2_CHECK(cudaStreamSynchronize(h->s_run));
             cudaGraph_t graph = nullptr;
             const int64_t launches = ctx->launches;
             MD2_CHECK(cudaStreamBeginCapture(h->s_run, cudaStreamCaptureModeThreadLocal));
@@ -337,31 +373,40 @@ static int run_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups)
             cudaGraphDestroy(graph);
             if (ie != cudaSuccess) { h->exec = nullptr; return set_error("host path: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
             memcpy(&h->key, d, sizeof(*d)); h->key_groups = groups; h->key_seed = seed; h->have_key = true;   // (byte copy: the reuse test is a memcmp)
-            h->key_ws_gen = ctx->ws_gen;   // any later growth of a ctx workspace (a device call with a larger shape) invalidates the graph
+            h->key_ws_gen = ctx->ws_gen[ctx->bank];   // any later growth of the bank's workspaces invalidates the graph
         }
     } else {
         MD2_CHECK(cudaGraphLaunch(h->exec, h->s_run));
         ctx->launches += 3 * groups;
-        MD2_CHECK(cudaStreamSynchronize(h->s_run));
     }
-    {   // un-stage the small outputs: per source grad_rot, grad_trans, then the partial losses
-        const float* q = h->hsmall + m.small_in_floats;
-        for (int s = 0; s < d->S; ++s) {
-            if (d->grad_rot[s]) memcpy(d->grad_rot[s], q, sizeof(float) * pr * d->N);
-            q += (size_t)pr * d->N;
-            if (d->grad_trans[s]) memcpy(d->grad_trans[s], q, sizeof(float) * 3 * d->N);
-            q += (size_t)3 * d->N;
-        }
-        double loss = 0.0;
-        for (int k = 0; k < groups; ++k) loss += (double)q[k];
-        *d->loss = (float)loss;
-    }
+    h->pending = true;
+    memcpy(&h->pend_desc, d, sizeof(*d));
+    h->pend_groups = groups;
+    h->pend_small_in = m.small_in_floats;
     return 0;
 }
 
 }  // namespace md2
 
-extern "C" int md2_view_synthesis_loss_fwdbwd_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int32_t groups) {
+extern "C" {
+
+int md2_view_synthesis_loss_fwdbwd_host(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int32_t groups) {
     MD2_REQUIRE(ctx != nullptr, "null ctx");
-    return md2::run_host(ctx, d, seed, groups);
+    if (md2::submit(ctx, d, seed, groups, 0)) return 1;
+    return md2::collect(ctx, 0);
 }
+
+int md2_view_synthesis_loss_fwdbwd_host_submit(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int32_t groups, int32_t lane) {
+    MD2_REQUIRE(ctx != nullptr, "null ctx");
+    MD2_REQUIRE(lane >= 0 && lane < MD2_HOST_LANES, "lane must be 0 or 1");
+    return md2::submit(ctx, d, seed, groups, lane);
+}
+
+int md2_host_wait(md2_ctx* ctx, int32_t lane) {
+    MD2_REQUIRE(ctx != nullptr, "null ctx");
+    MD2_REQUIRE(lane >= 0 && lane < MD2_HOST_LANES, "lane must be 0 or 1");
+    MD2_USE_DEVICE(ctx);
+    return md2::collect(ctx, lane);
+}
+
+}  // extern "C"

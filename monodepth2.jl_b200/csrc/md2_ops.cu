@@ -234,12 +234,15 @@ __global__ void grid_sample_fwd_kernel(const float* __restrict__ in, const float
 __global__ void grid_sample_bwd_kernel(const float* __restrict__ in, const float* __restrict__ grid,
                                        const float* __restrict__ gout, float* __restrict__ gin,
                                        float* __restrict__ ggrid, int W, int H, int C, int N, int Wo, int Ho, int border) {
+    // (no early exit: every lane of a warp takes part in the shuffles of the merged scatter)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long Po = (long long)Wo * Ho;
-    if (i >= Po * N) return;
-    const int n = (int)(i / Po);
-    const long long po = i % Po;
-    const GsTaps t = gs_taps(grid[2 * i], grid[2 * i + 1], W, H, border);
+    const bool active = i < Po * N;
+    const long long ii = active ? i : 0;
+    const int lane = threadIdx.x & 31;
+    const int n = (int)(ii / Po);
+    const long long po = ii % Po;
+    const GsTaps t = gs_taps(grid[2 * ii], grid[2 * ii + 1], W, H, border);
     const float fx = t.ix - (float)t.x0, fy = t.iy - (float)t.y0;
     const bool xa = t.x0 >= 0 && t.x0 < W, xb = t.x0 + 1 >= 0 && t.x0 + 1 < W;
     const bool ya = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
@@ -247,22 +250,22 @@ __global__ void grid_sample_bwd_kernel(const float* __restrict__ in, const float
     for (int c = 0; c < C; ++c) {
         const long long pl = ((long long)n * C + c) * W * H;
         const float* b = in + pl;
-        const float g = gout[((long long)n * C + c) * Po + po];
+        const float g = active ? gout[((long long)n * C + c) * Po + po] : 0.f;
         const float v00 = (xa && ya) ? b[t.y0 * W + t.x0] : 0.f;
         const float v01 = (xb && ya) ? b[t.y0 * W + t.x0 + 1] : 0.f;
         const float v10 = (xa && yb) ? b[(t.y0 + 1) * W + t.x0] : 0.f;
         const float v11 = (xb && yb) ? b[(t.y0 + 1) * W + t.x0 + 1] : 0.f;
         gix += g * ((v01 - v00) * (1.f - fy) + (v11 - v10) * fy);
         giy += g * ((v10 - v00) * (1.f - fx) + (v11 - v01) * fx);
-        if (gin) {
-            float* gb = gin + pl;
-            if (xa && ya) atomicAdd(gb + t.y0 * W + t.x0, g * (1.f - fx) * (1.f - fy));
-            if (xb && ya) atomicAdd(gb + t.y0 * W + t.x0 + 1, g * fx * (1.f - fy));
-            if (xa && yb) atomicAdd(gb + (t.y0 + 1) * W + t.x0, g * (1.f - fx) * fy);
-            if (xb && yb) atomicAdd(gb + (t.y0 + 1) * W + t.x0 + 1, g * fx * fy);
+        if (gin) {   // (uniform: a kernel argument)
+            float* r0 = gin + pl + (long long)t.y0 * W + t.x0;
+            float* r1 = r0 + W;
+            const bool top = active && ya, bot = active && yb;
+            red_pair_merged((top && xa) ? r0 : nullptr, (top && xb) ? r0 + 1 : nullptr, g * (1.f - fx) * (1.f - fy), g * fx * (1.f - fy), lane);
+            red_pair_merged((bot && xa) ? r1 : nullptr, (bot && xb) ? r1 + 1 : nullptr, g * (1.f - fx) * fy, g * fx * fy, lane);
         }
     }
-    if (ggrid) {
+    if (ggrid && active) {
         ggrid[2 * i] = t.mx * gix;
         ggrid[2 * i + 1] = t.my * giy;
     }
@@ -278,21 +281,15 @@ struct WinXY {           // SSIM window statistics with the coefficients for bot
     float ay, by;        // dS/dy_j = ay + by y_j + g x_j
 };
 
-// x, y: one channel plane; (qx,qy) window centre (in image)
-__device__ __forceinline__ WinXY window_xy(const float* __restrict__ x, const float* __restrict__ y, int qx, int qy,
-                                           int W, int H) {
-    const float xc = x[qy * W + qx], yc = y[qy * W + qx];
+// statistics of one window from its nine samples of x and y (index 4 = the centre pixel)
+__device__ __forceinline__ WinXY window_core(const float (&xv)[9], const float (&yv)[9]) {
+    const float xc = xv[4], yc = yv[4];
     float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int ry = reflect1(qy + dy, H);
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int rx = reflect1(qx + dx, W);
-            const float a = x[ry * W + rx] - xc, b = y[ry * W + rx] - yc;
-            sx += a; sy += b;
-            sxx = fmaf(a, a, sxx); syy = fmaf(b, b, syy); sxy = fmaf(a, b, sxy);
-        }
+    for (int k = 0; k < 9; ++k) {
+        const float a = xv[k] - xc, b = yv[k] - yc;
+        sx += a; sy += b;
+        sxx = fmaf(a, a, sxx); syy = fmaf(b, b, syy); sxy = fmaf(a, b, sxy);
     }
     const float r9 = 1.0f / 9.0f;
     const float dx = sx * r9, dy = sy * r9;
@@ -314,44 +311,101 @@ __device__ __forceinline__ WinXY window_xy(const float* __restrict__ x, const fl
     return o;
 }
 
+// ---- shared-memory halo tiles (the SSIM window is a 3x3 stencil; its backward reaches two pixels out) ----------
+// A block owns a TW x TH tile of one image plane.  load_tile stages the tile plus a halo of HALO pixels of a plane into
+// shared memory, coalesced row by row; coordinates outside the image are folded back by the reflect-pad(1) of
+// src/utils.jl:26-27 (only -1 and n are ever used by an in-image window; anything further is clamped and never read).
+constexpr int TILE_W = 32, TILE_H = 8, TILE_THREADS = TILE_W * TILE_H;
+
+__device__ __forceinline__ int fold_coord(int g, int n) {
+    g = reflect1(g, n);
+    return g < 0 ? 0 : (g > n - 1 ? n - 1 : g);
+}
+template <int HALO>
+__device__ __forceinline__ void load_tile(float* __restrict__ sm, const float* __restrict__ plane, int x0, int y0, int W, int H) {
+    constexpr int SW = TILE_W + 2 * HALO, SH = TILE_H + 2 * HALO;
+    for (int k = threadIdx.x; k < SW * SH; k += TILE_THREADS) {
+        const int ty = k / SW, tx = k - ty * SW;
+        sm[k] = plane[(long long)fold_coord(y0 - HALO + ty, H) * W + fold_coord(x0 - HALO + tx, W)];
+    }
+}
+// the nine samples of the window centred on tile-local (cx, cy) of a staged tile with row pitch SW
+template <int SW>
+__device__ __forceinline__ void window_samples(const float* __restrict__ sm, int cx, int cy, float (&v)[9]) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) v[(dy + 1) * 3 + dx + 1] = sm[(cy + dy) * SW + cx + dx];
+}
+
 __device__ __forceinline__ float fold_w(int g, int d, int n) {   // adjoint of reflect-pad(1)
     return 1.0f + ((g == 1 && d == -1) ? 1.f : 0.f) + ((g == n - 2 && d == 1) ? 1.f : 0.f);
 }
 
-__global__ void ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
-                                int W, int H, long long planes) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long HW = (long long)W * H;
-    if (i >= HW * planes) return;
-    const long long pl = i / HW;
-    const int p = (int)(i % HW);
-    out[i] = window_xy(x + pl * HW, y + pl * HW, p % W, p / W, W, H).s;
+__global__ void __launch_bounds__(TILE_THREADS) ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                                                int W, int H) {
+    constexpr int SW = TILE_W + 2, SH = TILE_H + 2;
+    __shared__ float xs[SW * SH], ys[SW * SH];
+    const long long HW = (long long)W * H, pl = blockIdx.z;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    load_tile<1>(xs, x + pl * HW, x0, y0, W, H);
+    load_tile<1>(ys, y + pl * HW, x0, y0, W, H);
+    __syncthreads();
+    const int tx = threadIdx.x % TILE_W, ty = threadIdx.x / TILE_W;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) return;
+    float xv[9], yv[9];
+    window_samples<SW>(xs, tx + 1, ty + 1, xv);
+    window_samples<SW>(ys, tx + 1, ty + 1, yv);
+    out[pl * HW + (long long)gy * W + gx] = window_core(xv, yv).s;
 }
 
-__global__ void ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gout,
-                                float* __restrict__ gx, float* __restrict__ gy, int W, int H, long long planes) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long HW = (long long)W * H;
-    if (i >= HW * planes) return;
-    const long long pl = i / HW;
-    const int p = (int)(i % HW), jx = p % W, jy = p / W;
-    const float* xp = x + pl * HW; const float* yp = y + pl * HW; const float* gp = gout + pl * HW;
-    const float xj = xp[p], yj = yp[p];
-    float ax = 0.f, ay = 0.f;
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int qy = jy + dy;
-        if (qy < 0 || qy >= H) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int qx = jx + dx;
-            if (qx < 0 || qx >= W) continue;
-            const WinXY w = window_xy(xp, yp, qx, qy, W, H);
-            const float k = fold_w(jx, dx, W) * fold_w(jy, dy, H) * gp[qy * W + qx] * (-0.5f) * w.pass;
-            ax = fmaf(k, w.ax + w.bx * xj + w.g * yj, ax);
-            ay = fmaf(k, w.ay + w.by * yj + w.g * xj, ay);
+// Backward in two phases per tile: (1) the coefficients of every window that touches the tile (tile + halo 1), each
+// computed ONCE from the staged pixels (tile + halo 2) and scaled by its upstream cotangent; (2) every pixel gathers its
+// nine windows (gather form: deterministic, no atomics).  The naive form recomputes each window nine times from global memory.
+__global__ void __launch_bounds__(TILE_THREADS) ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gout,
+                                                                float* __restrict__ gx, float* __restrict__ gy, int W, int H) {
+    constexpr int SW = TILE_W + 4, SH = TILE_H + 4, CW = TILE_W + 2, CH = TILE_H + 2;
+    __shared__ float xs[SW * SH], ys[SW * SH];
+    __shared__ float cf[5][CW * CH];                 // k * (ax, bx, g, ay, by) of the windows around the tile
+    const long long HW = (long long)W * H, pl = blockIdx.z;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    load_tile<2>(xs, x + pl * HW, x0, y0, W, H);
+    load_tile<2>(ys, y + pl * HW, x0, y0, W, H);
+    __syncthreads();
+    for (int k = threadIdx.x; k < CW * CH; k += TILE_THREADS) {
+        const int wy = k / CW, wx = k - wy * CW;
+        const int qx = x0 - 1 + wx, qy = y0 - 1 + wy;     // window centre in the image
+        float c[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (qx >= 0 && qx < W && qy >= 0 && qy < H) {
+            float xv[9], yv[9];
+            window_samples<SW>(xs, wx + 1, wy + 1, xv);
+            window_samples<SW>(ys, wx + 1, wy + 1, yv);
+            const WinXY w = window_core(xv, yv);
+            const float kk = gout[pl * HW + (long long)qy * W + qx] * (-0.5f) * w.pass;
+            c[0] = kk * w.ax; c[1] = kk * w.bx; c[2] = kk * w.g; c[3] = kk * w.ay; c[4] = kk * w.by;
         }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) cf[j][k] = c[j];
     }
-    if (gx) gx[i] = ax;
-    if (gy) gy[i] = ay;
+    __syncthreads();
+    const int tx = threadIdx.x % TILE_W, ty = threadIdx.x / TILE_W;
+    const int jx = x0 + tx, jy = y0 + ty;
+    if (jx >= W || jy >= H) return;
+    const float xj = xs[(ty + 2) * SW + tx + 2], yj = ys[(ty + 2) * SW + tx + 2];
+    float ax = 0.f, ay = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int k = (ty + 1 + dy) * CW + tx + 1 + dx;      // (windows outside the image hold zeros)
+            const float f = fold_w(jx, dx, W) * fold_w(jy, dy, H);
+            ax = fmaf(f, cf[0][k] + cf[1][k] * xj + cf[2][k] * yj, ax);
+            ay = fmaf(f, cf[3][k] + cf[4][k] * yj + cf[2][k] * xj, ay);
+        }
+    const long long o = pl * HW + (long long)jy * W + jx;
+    if (gx) gx[o] = ax;
+    if (gy) gy[o] = ay;
 }
 
 struct PmArgs {
@@ -363,92 +417,136 @@ struct PmArgs {
     float* gpred[MAX_S];
 };
 
+// out = min([mask,] pe_0, ..., pe_{S-1}), pe_s = alpha mean_c SSIM(pred_s, target) + (1 - alpha) mean_c |target - pred_s|:
+// one block per tile and image; the target tile of a channel is staged once and shared by the S sources
 template <int C>
-__device__ __forceinline__ float photometric_at(const float* __restrict__ x, const float* __restrict__ y, int qx, int qy,
-                                                int W, int H, float alpha) {
-    const long long HW = (long long)W * H;
-    float ss = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        ss += window_xy(x + c * HW, y + c * HW, qx, qy, W, H).s;
-        l1 += fabsf(y[c * HW + qy * W + qx] - x[c * HW + qy * W + qx]);
-    }
-    return alpha * (ss * (1.0f / C)) + (1.0f - alpha) * (l1 * (1.0f / C));
-}
-
-template <int C>
-__global__ void photomin_fwd_kernel(PmArgs a, float* __restrict__ out, int* __restrict__ argmin) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_kernel(PmArgs a, float* __restrict__ out, int* __restrict__ argmin) {
+    constexpr int SW = TILE_W + 2, SH = TILE_H + 2;
+    __shared__ float ys[SW * SH], xs[SW * SH];
     const long long HW = (long long)a.W * a.H;
-    if (i >= HW * a.N) return;
-    const int n = (int)(i / HW), p = (int)(i % HW), qx = p % a.W, qy = p / a.W;
+    const int n = blockIdx.z, x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int tx = threadIdx.x % TILE_W, ty = threadIdx.x / TILE_W;
+    const int gx = x0 + tx, gy = y0 + ty;
+    const bool in = gx < a.W && gy < a.H;
     const float* y = a.target + n * a.target_ns;
+    float ss[MAX_S], l1[MAX_S];
+#pragma unroll
+    for (int s = 0; s < MAX_S; ++s) { ss[s] = 0.f; l1[s] = 0.f; }
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        __syncthreads();
+        load_tile<1>(ys, y + c * HW, x0, y0, a.W, a.H);
+#pragma unroll
+        for (int s = 0; s < MAX_S; ++s) {
+            if (s >= a.S) break;
+            __syncthreads();
+            load_tile<1>(xs, a.pred[s] + n * a.pred_ns[s] + c * HW, x0, y0, a.W, a.H);
+            __syncthreads();
+            float xv[9], yv[9];
+            window_samples<SW>(xs, tx + 1, ty + 1, xv);
+            window_samples<SW>(ys, tx + 1, ty + 1, yv);
+            ss[s] += window_core(xv, yv).s;
+            l1[s] += fabsf(yv[4] - xv[4]);
+        }
+    }
+    if (!in) return;
+    const long long i = (long long)n * HW + (long long)gy * a.W + gx;
     float best = 0.f; int bi = -1;
     if (a.mask) best = a.mask[i];
-    for (int s = 0; s < a.S; ++s) {
-        const float pe = photometric_at<C>(a.pred[s] + n * a.pred_ns[s], y, qx, qy, a.W, a.H, a.alpha);
+#pragma unroll
+    for (int s = 0; s < MAX_S; ++s) {
+        if (s >= a.S) break;
+        const float pe = a.alpha * (ss[s] * (1.0f / C)) + (1.0f - a.alpha) * (l1[s] * (1.0f / C));
         if ((s == 0 && !a.mask) || pe < best) { best = pe; bi = s; }
     }
     out[i] = best;
     if (argmin) argmin[i] = bi;
 }
 
+// Backward, two phases per tile and channel like ssim_bwd_kernel; a window's coefficients are those of ITS selected
+// source (argmin of the forward), so the tiles of all S sources are staged side by side.
 template <int C>
-__global__ void photomin_bwd_kernel(PmArgs a, const float* __restrict__ gout, const int* __restrict__ argmin,
-                                    float* __restrict__ gtarget, float* __restrict__ gmask) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(TILE_THREADS) photomin_bwd_kernel(PmArgs a, const float* __restrict__ gout, const int* __restrict__ argmin,
+                                                                    float* __restrict__ gtarget, float* __restrict__ gmask) {
+    constexpr int SW = TILE_W + 4, SH = TILE_H + 4, CW = TILE_W + 2, CH = TILE_H + 2;
+    __shared__ float ys[SW * SH], xs[MAX_S][SW * SH];
+    __shared__ float cf[5][CW * CH];
+    __shared__ int sel[CW * CH];
     const long long HW = (long long)a.W * a.H;
-    if (i >= HW * a.N) return;
-    const int n = (int)(i / HW), p = (int)(i % HW), jx = p % a.W, jy = p / a.W;
+    const int n = blockIdx.z, x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int tx = threadIdx.x % TILE_W, ty = threadIdx.x / TILE_W;
+    const int jx = x0 + tx, jy = y0 + ty;
+    const bool in = jx < a.W && jy < a.H;
     const float* y = a.target + n * a.target_ns;
     const int* am = argmin ? argmin + (long long)n * HW : nullptr;
-    float gp[MAX_S][C], gt[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) { gt[c] = 0.f; for (int s = 0; s < MAX_S; ++s) gp[s][c] = 0.f; }
     const float ks = a.alpha * (1.0f / C) * (-0.5f), kl = (1.0f - a.alpha) * (1.0f / C);
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int qy = jy + dy;
-        if (qy < 0 || qy >= a.H) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int qx = jx + dx;
-            if (qx < 0 || qx >= a.W) continue;
-            const int sq = am ? am[qy * a.W + qx] : 0;
-            if (sq < 0) continue;
-            const float k = fold_w(jx, dx, a.W) * fold_w(jy, dy, a.H) * gout[(long long)n * HW + qy * a.W + qx] * ks;
-            const float* x = a.pred[sq] + n * a.pred_ns[sq];
+    for (int k = threadIdx.x; k < CW * CH; k += TILE_THREADS) {      // selected source of every window around the tile (-1: mask / outside)
+        const int wy = k / CW, wx = k - wy * CW;
+        const int qx = x0 - 1 + wx, qy = y0 - 1 + wy;
+        sel[k] = (qx >= 0 && qx < a.W && qy >= 0 && qy < a.H) ? (am ? am[qy * a.W + qx] : 0) : -1;
+    }
+    const long long i = (long long)n * HW + (long long)(in ? jy : 0) * a.W + (in ? jx : 0);
+    const int sj = in ? (am ? am[(long long)jy * a.W + jx] : 0) : -1;
+    const float gj = in ? gout[i] : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        __syncthreads();
+        load_tile<2>(ys, y + c * HW, x0, y0, a.W, a.H);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const WinXY w = window_xy(x + c * HW, y + c * HW, qx, qy, a.W, a.H);
-                const float xj = x[c * HW + p], yj = y[c * HW + p];
-                const float kk = k * w.pass;
-                const float vx = kk * (w.ax + w.bx * xj + w.g * yj);
-#pragma unroll
-                for (int s = 0; s < MAX_S; ++s) if (s == sq) gp[s][c] += vx;
-                gt[c] = fmaf(kk, w.ay + w.by * yj + w.g * xj, gt[c]);
+        for (int s = 0; s < MAX_S; ++s)
+            if (s < a.S) load_tile<2>(xs[s], a.pred[s] + n * a.pred_ns[s] + c * HW, x0, y0, a.W, a.H);
+        __syncthreads();
+        for (int k = threadIdx.x; k < CW * CH; k += TILE_THREADS) {
+            const int wy = k / CW, wx = k - wy * CW;
+            const int sq = sel[k];
+            float cc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (sq >= 0) {
+                float xv[9], yv[9];
+                window_samples<SW>(xs[sq], wx + 1, wy + 1, xv);
+                window_samples<SW>(ys, wx + 1, wy + 1, yv);
+                const WinXY w = window_core(xv, yv);
+                const int qx = x0 - 1 + wx, qy = y0 - 1 + wy;
+                const float kk = gout[(long long)n * HW + (long long)qy * a.W + qx] * ks * w.pass;
+                cc[0] = kk * w.ax; cc[1] = kk * w.bx; cc[2] = kk * w.g; cc[3] = kk * w.ay; cc[4] = kk * w.by;
             }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) cf[j][k] = cc[j];
+        }
+        __syncthreads();
+        if (in) {
+            const float yj = ys[(ty + 2) * SW + tx + 2];
+            float gp[MAX_S], gt = 0.f;
+#pragma unroll
+            for (int s = 0; s < MAX_S; ++s) gp[s] = 0.f;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int k = (ty + 1 + dy) * CW + tx + 1 + dx;
+                    const int sq = sel[k];
+                    if (sq < 0) continue;
+                    const float f = fold_w(jx, dx, a.W) * fold_w(jy, dy, a.H);
+                    const float xj = xs[sq][(ty + 2) * SW + tx + 2];
+                    const float vx = f * (cf[0][k] + cf[1][k] * xj + cf[2][k] * yj);
+#pragma unroll
+                    for (int s = 0; s < MAX_S; ++s) if (s == sq) gp[s] += vx;
+                    gt = fmaf(f, cf[3][k] + cf[4][k] * yj + cf[2][k] * xj, gt);
+                }
+            if (sj >= 0) {
+                const float df = xs[sj][(ty + 2) * SW + tx + 2] - yj;
+                const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+#pragma unroll
+                for (int s = 0; s < MAX_S; ++s) if (s == sj) gp[s] += gj * kl * sg;
+                gt -= gj * kl * sg;
+            }
+            const long long o = ((long long)n * C + c) * HW + (long long)jy * a.W + jx;
+#pragma unroll
+            for (int s = 0; s < MAX_S; ++s)
+                if (s < a.S && a.gpred[s]) a.gpred[s][o] = gp[s];
+            if (gtarget) gtarget[o] = gt;
         }
     }
-    const int sj = am ? am[p] : 0;
-    const float gj = gout[i];
-    if (sj >= 0) {
-        const float* x = a.pred[sj] + n * a.pred_ns[sj];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const float df = x[c * HW + p] - y[c * HW + p];
-            const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-#pragma unroll
-            for (int s = 0; s < MAX_S; ++s) if (s == sj) gp[s][c] += gj * kl * sg;
-            gt[c] -= gj * kl * sg;
-        }
-    }
-    for (int s = 0; s < a.S; ++s)
-        if (a.gpred[s])
-#pragma unroll
-            for (int c = 0; c < C; ++c) a.gpred[s][((long long)n * C + c) * HW + p] = gp[s][c];
-    if (gtarget)
-#pragma unroll
-        for (int c = 0; c < C; ++c) gtarget[((long long)n * C + c) * HW + p] = gt[c];
-    if (gmask) gmask[i] = (sj < 0) ? gj : 0.f;
+    if (in && gmask) gmask[i] = (sj < 0) ? gj : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -677,7 +775,8 @@ int md2_ssim_fwd(md2_ctx* ctx, const float* x, const float* y, float* out, int32
     CTX_OK();
     MD2_REQUIRE(x && y && out && W >= 2 && H >= 2 && C > 0 && N > 0, "bad arguments (W,H >= 2)");
     const long long planes = (long long)C * N;
-    ssim_fwd_kernel<<<cdiv((long long)W * H * planes, 256), 256, 0, ST>>>(x, y, out, W, H, planes);
+    MD2_REQUIRE(planes <= 65535 && cdiv(H, TILE_H) <= 65535, "C * N and H / 8 must be <= 65535");
+    ssim_fwd_kernel<<<dim3(cdiv(W, TILE_W), cdiv(H, TILE_H), (unsigned)planes), TILE_THREADS, 0, ST>>>(x, y, out, W, H);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -686,7 +785,8 @@ int md2_ssim_bwd(md2_ctx* ctx, const float* x, const float* y, const float* gout
     CTX_OK();
     MD2_REQUIRE(x && y && gout && W >= 2 && H >= 2 && C > 0 && N > 0, "bad arguments (W,H >= 2)");
     const long long planes = (long long)C * N;
-    ssim_bwd_kernel<<<cdiv((long long)W * H * planes, 256), 256, 0, ST>>>(x, y, gout, gx, gy, W, H, planes);
+    MD2_REQUIRE(planes <= 65535 && cdiv(H, TILE_H) <= 65535, "C * N and H / 8 must be <= 65535");
+    ssim_bwd_kernel<<<dim3(cdiv(W, TILE_W), cdiv(H, TILE_H), (unsigned)planes), TILE_THREADS, 0, ST>>>(x, y, gout, gx, gy, W, H);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -714,9 +814,10 @@ int md2_photometric_min_fwd(md2_ctx* ctx, int32_t S, const float* const* pred, c
     PmArgs a;
     if (fill_pm(a, S, pred, pred_image_stride, target, target_image_stride, mask, alpha, W, H, C, N)) return 1;
     MD2_REQUIRE(out != nullptr, "null output");
-    const int g = cdiv((long long)W * H * N, 128);
-    if (C == 1) photomin_fwd_kernel<1><<<g, 128, 0, ST>>>(a, out, argmin);
-    else photomin_fwd_kernel<3><<<g, 128, 0, ST>>>(a, out, argmin);
+    MD2_REQUIRE(N <= 65535 && cdiv(H, TILE_H) <= 65535, "N and H / 8 must be <= 65535");
+    const dim3 g(cdiv(W, TILE_W), cdiv(H, TILE_H), N);
+    if (C == 1) photomin_fwd_kernel<1><<<g, TILE_THREADS, 0, ST>>>(a, out, argmin);
+    else photomin_fwd_kernel<3><<<g, TILE_THREADS, 0, ST>>>(a, out, argmin);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -731,9 +832,10 @@ int md2_photometric_min_bwd(md2_ctx* ctx, int32_t S, const float* const* pred, c
     MD2_REQUIRE(gout != nullptr, "null upstream gradient");
     MD2_REQUIRE(argmin != nullptr || (S == 1 && !mask), "argmin from the forward call is required when S > 1 or a mask is used");
     for (int s = 0; s < S; ++s) a.gpred[s] = gpred ? gpred[s] : nullptr;
-    const int g = cdiv((long long)W * H * N, 128);
-    if (C == 1) photomin_bwd_kernel<1><<<g, 128, 0, ST>>>(a, gout, argmin, gtarget, gmask);
-    else photomin_bwd_kernel<3><<<g, 128, 0, ST>>>(a, gout, argmin, gtarget, gmask);
+    MD2_REQUIRE(N <= 65535 && cdiv(H, TILE_H) <= 65535, "N and H / 8 must be <= 65535");
+    const dim3 g(cdiv(W, TILE_W), cdiv(H, TILE_H), N);
+    if (C == 1) photomin_bwd_kernel<1><<<g, TILE_THREADS, 0, ST>>>(a, gout, argmin, gtarget, gmask);
+    else photomin_bwd_kernel<3><<<g, TILE_THREADS, 0, ST>>>(a, gout, argmin, gtarget, gmask);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }

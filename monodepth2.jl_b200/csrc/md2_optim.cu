@@ -184,7 +184,7 @@ static int run_slow_depth(md2_ctx* ctx, const md2_vsl_desc* d, int iters, float 
     const float hp[4] = {lr, b1, b2, eps};
     const void* ptrs[4] = {state, clock, history, nullptr};
     int done = 0;
-    const bool same = o->have_key && o->exec && o->key_ws_gen == ctx->ws_gen && o->key_len == history_len &&
+    const bool same = o->have_key && o->exec && o->key_ws_gen == ctx->ws_gen[0] && o->key_len == history_len &&
                       memcmp(&o->key, d, sizeof(*d)) == 0 && memcmp(o->key_hp, hp, sizeof(hp)) == 0 && memcmp(o->key_ptrs, ptrs, sizeof(ptrs)) == 0;
     if (!same) {
         if (o->exec) { cudaGraphExecDestroy(o->exec); o->exec = nullptr; }
@@ -209,7 +209,7 @@ static int run_slow_depth(md2_ctx* ctx, const md2_vsl_desc* d, int iters, float 
             cudaGraphDestroy(graph);
             if (ie != cudaSuccess) { o->exec = nullptr; return set_error("slow_depth: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
             memcpy(&o->key, d, sizeof(*d)); memcpy(o->key_hp, hp, sizeof(hp)); memcpy(o->key_ptrs, ptrs, sizeof(ptrs));
-            o->key_len = history_len; o->key_ws_gen = ctx->ws_gen; o->have_key = true;
+            o->key_len = history_len; o->key_ws_gen = ctx->ws_gen[0]; o->have_key = true;
         }
     }
     for (; done < iters; ++done) {

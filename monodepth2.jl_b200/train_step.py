@@ -133,6 +133,8 @@ class StandInModel(nn.Module):
 
     def forward(self, x, source_ids, target_id):
         N, L, C, H, W = x.shape
+        if H % 32 or W % 32:
+            raise ValueError("the ResNet-18 encoder / U-Net decoder pair needs image sides that are multiples of 32")
         feats = [f.reshape(N, L, *f.shape[1:]) for f in self.encoder(x.reshape(N * L, C, H, W))]
         disparities = self.depth_decoder([f[:, target_id] for f in feats])
         last = feats[-1]

@@ -162,52 +162,84 @@ class HostViewSynthesisLoss:
     (`inputs`, `grads`); fill `inputs` in place (or pass tensors to `__call__`, which copies them in) and
     read `loss` / `grads` after the call.
 
+    Double-buffered form (a data loader one step ahead): `lane_inputs[k]` / `lane_grads[k]`, k = 0, 1, are two
+    independent buffer sets; `submit(k)` enqueues a step on lane k and returns at once, `wait(k)` blocks until its
+    outputs are in `lane_grads[k]` and returns the loss, so the device-to-host copies of one step overlap the
+    host-to-device copies and kernels of the next (md2_view_synthesis_loss_fwdbwd_host_submit / md2_host_wait).
+
     x (N,3,C,H,W); disparities (N,1,h_i,w_i) per scale; rvecs / tvecs (N,3) per source; K, invK (3,3)."""
+
+    LANES = 2
 
     def __init__(self, N, C_, H, W, disp_sizes, K, invK, *, device=None, target_id=1, source_ids=(0, 2),
                  scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3,
-                 automask=False, normalize_disparity=True, grad_x=False, groups=2):
+                 automask=False, normalize_disparity=True, grad_x=False, groups=2, lanes=1):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.ctx = Context.get(dev)
         self.groups, self.S, self.L = int(groups), len(source_ids), len(disp_sizes)
+        if not 1 <= lanes <= self.LANES:
+            raise ValueError("lanes must be 1 or 2")
         pin = lambda *shape: torch.zeros(*shape, dtype=_F32).pin_memory()
-        self.inputs = dict(x=pin(N, 3, C_, H, W), disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes],
-                           rvecs=[pin(N, 3) for _ in source_ids], tvecs=[pin(N, 3) for _ in source_ids],
-                           automask=pin(N, 1, H, W) if automask else None)
-        self.grads = dict(disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes], rvecs=[pin(N, 3) for _ in source_ids],
-                          tvecs=[pin(N, 3) for _ in source_ids], x=pin(N, 3, C_, H, W) if grad_x else None)
-        self._loss = pin(1)
         self._K = _cm(_f32c(K.reshape(3, 3).cpu())).pin_memory()
         self._invK = _cm(_f32c(invK.reshape(3, 3).cpu())).pin_memory()
-        x, gx = self.inputs["x"], self.grads["x"]
-        self.desc = L.make_vsl_desc(
-            target=x[:, target_id], target_stride=x.stride(0), sources=[x[:, i] for i in source_ids],
-            source_strides=[x.stride(0)] * self.S, disparities=self.inputs["disparities"], K_cm=self._K, invK_cm=self._invK,
-            rot=self.inputs["rvecs"], trans=self.inputs["tvecs"], pose_mode=1, invert=[i < target_id for i in source_ids],
-            automask=self.inputs["automask"], min_depth=min_depth, max_depth=max_depth,
-            smooth_weight=[disparity_smoothness * s for s in list(scales)[:self.L]], loss_scale=1.0 / self.L,
-            normalize_disparity=normalize_disparity, loss=self._loss, grad_disparity=self.grads["disparities"],
-            grad_rot=self.grads["rvecs"], grad_trans=self.grads["tvecs"],
-            grad_source=[gx[:, i] for i in source_ids] if grad_x else None, zero_grad_source=True, shape=(N, C_, H, W))
+        self.lane_inputs, self.lane_grads, self._lane_loss, self._descs = [], [], [], []
+        for _ in range(lanes):
+            inputs = dict(x=pin(N, 3, C_, H, W), disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes],
+                          rvecs=[pin(N, 3) for _ in source_ids], tvecs=[pin(N, 3) for _ in source_ids],
+                          automask=pin(N, 1, H, W) if automask else None)
+            grads = dict(disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes], rvecs=[pin(N, 3) for _ in source_ids],
+                         tvecs=[pin(N, 3) for _ in source_ids], x=pin(N, 3, C_, H, W) if grad_x else None)
+            loss = pin(1)
+            x, gx = inputs["x"], grads["x"]
+            desc = L.make_vsl_desc(
+                target=x[:, target_id], target_stride=x.stride(0), sources=[x[:, i] for i in source_ids],
+                source_strides=[x.stride(0)] * self.S, disparities=inputs["disparities"], K_cm=self._K, invK_cm=self._invK,
+                rot=inputs["rvecs"], trans=inputs["tvecs"], pose_mode=1, invert=[i < target_id for i in source_ids],
+                automask=inputs["automask"], min_depth=min_depth, max_depth=max_depth,
+                smooth_weight=[disparity_smoothness * s for s in list(scales)[:self.L]], loss_scale=1.0 / self.L,
+                normalize_disparity=normalize_disparity, loss=loss, grad_disparity=grads["disparities"],
+                grad_rot=grads["rvecs"], grad_trans=grads["tvecs"],
+                grad_source=[gx[:, i] for i in source_ids] if grad_x else None, zero_grad_source=True, shape=(N, C_, H, W))
+            self.lane_inputs.append(inputs); self.lane_grads.append(grads); self._lane_loss.append(loss); self._descs.append(desc)
+        self.inputs, self.grads, self._loss, self.desc = self.lane_inputs[0], self.lane_grads[0], self._lane_loss[0], self._descs[0]
+        x = self.inputs["x"]
         self.h2d_bytes = 4 * sum(t.numel() for t in [x] + self.inputs["disparities"] + self.inputs["rvecs"] + self.inputs["tvecs"]
                                  + ([self.inputs["automask"]] if automask else [])) + 72
         self.d2h_bytes = 4 + 4 * sum(t.numel() for t in self.grads["disparities"] + self.grads["rvecs"] + self.grads["tvecs"]) \
             + (8 * N * C_ * H * W if grad_x else 0)
 
-    def __call__(self, x=None, disparities=None, rvecs=None, tvecs=None, automask=None):
-        """copies any given (CPU) tensors into the pinned inputs, runs one step, returns the loss as a float"""
+    def fill(self, lane=0, x=None, disparities=None, rvecs=None, tvecs=None, automask=None):
+        """copies the given (CPU) tensors into the pinned inputs of a lane"""
+        inputs = self.lane_inputs[lane]
         if x is not None:
-            self.inputs["x"].copy_(x)
+            inputs["x"].copy_(x)
         for name, vals in (("disparities", disparities), ("rvecs", rvecs), ("tvecs", tvecs)):
             if vals is not None:
-                for dst, src in zip(self.inputs[name], vals):
+                for dst, src in zip(inputs[name], vals):
                     dst.copy_(src.reshape(dst.shape))
         if automask is not None:
-            self.inputs["automask"].copy_(automask.reshape(self.inputs["automask"].shape))
+            inputs["automask"].copy_(automask.reshape(inputs["automask"].shape))
+
+    def __call__(self, x=None, disparities=None, rvecs=None, tvecs=None, automask=None):
+        """copies any given (CPU) tensors into the pinned inputs, runs one step, returns the loss as a float"""
+        self.fill(0, x, disparities, rvecs, tvecs, automask)
         lib = self.ctx.lib
         if lib.md2_view_synthesis_loss_fwdbwd_host(self.ctx.handle, C.byref(self.desc), 1.0, self.groups):
             raise L.Md2Error(lib.md2_last_error().decode())
         return float(self._loss[0])
+
+    def submit(self, lane):
+        """enqueue one step on the lane's buffers; returns at once (the lane's inputs must stay untouched until wait)"""
+        lib = self.ctx.lib
+        if lib.md2_view_synthesis_loss_fwdbwd_host_submit(self.ctx.handle, C.byref(self._descs[lane]), 1.0, self.groups, lane):
+            raise L.Md2Error(lib.md2_last_error().decode())
+
+    def wait(self, lane):
+        """block until the lane's step is complete; its gradients are in lane_grads[lane]; returns the loss"""
+        lib = self.ctx.lib
+        if lib.md2_host_wait(self.ctx.handle, lane):
+            raise L.Md2Error(lib.md2_last_error().decode())
+        return float(self._lane_loss[lane][0])
 
     @property
     def loss(self):

@@ -248,3 +248,59 @@ def test_host_entry_point_matches_device_path(groups, automask, grad_x):
             assert torch.allclose(a, b, rtol=1e-4, atol=1e-8), rep
         if grad_x:
             assert torch.allclose(hv.grads["x"], rgx, rtol=1e-4, atol=1e-7), rep
+
+
+@pytest.mark.gpu
+def test_host_lanes_pipelined_steps_match_the_oracle():
+    """double-buffered host entry point: step i+1 is submitted on the other lane before step i is collected; every
+    step's host outputs match the float64 oracle (statistical bars; the device path is checked strictly elsewhere) and
+    equal the synchronous call bit for bit (all but the atomically accumulated source-image gradient)"""
+    N, Cc, H, W = 4, 1, 48, 96
+    K, invK = O.make_K(W, H)
+    dev = torch.device("cuda", 0)
+    batches = [O.synthetic_batch(N, Cc, H, W, seed=40 + k) for k in range(4)]
+    sizes = [(d.shape[-1], d.shape[-2]) for d in batches[0][1]]
+    hv = M.HostViewSynthesisLoss(N, Cc, H, W, sizes, K, invK, device=dev, groups=2, lanes=2)
+    sync = M.HostViewSynthesisLoss(N, Cc, H, W, sizes, K, invK, device=dev, groups=2)
+    results = {}
+
+    def collect(k):
+        lane = k % 2
+        loss = hv.wait(lane)
+        g = hv.lane_grads[lane]
+        results[k] = dict(loss=loss, gdisp=[t.clone() for t in g["disparities"]], grvec=[t.clone() for t in g["rvecs"]],
+                          gtvec=[t.clone() for t in g["tvecs"]])
+
+    for k, (x, disps, rv, tv) in enumerate(batches):
+        lane = k % 2
+        if k >= 2:
+            collect(k - 2)                       # the lane's previous step, before its buffers are refilled
+        hv.fill(lane, x, disps, rv, tv)
+        hv.submit(lane)
+    collect(2); collect(3)
+    for k, (x, disps, rv, tv) in enumerate(batches):
+        ref = oracle_vsl(x, disps, rv, tv, K, invK)
+        check_vsl_statistical(results[k], ref, tag=f"lane step {k}")
+        sl = sync(x, disps, rv, tv)
+        assert sl == results[k]["loss"]
+        for a, b in zip(sync.grads["disparities"] + sync.grads["rvecs"] + sync.grads["tvecs"],
+                        results[k]["gdisp"] + results[k]["grvec"] + results[k]["gtvec"]):
+            assert torch.equal(a, b), k
+
+
+@pytest.mark.gpu
+def test_host_entry_point_single_source_not_first_frame():
+    """S = 1 with source frame 2 and target frame 1: the lowest frame in use is not frame 0 of the per-image block
+    (the contiguous-frames copy must stop at the end of the last frame in use)"""
+    N, Cc, H, W = 3, 3, 32, 64
+    x, disps, rv, tv = O.synthetic_batch(N, Cc, H, W, seed=9)
+    K, invK = O.make_K(W, H)
+    dev = torch.device("cuda", 0)
+    hv = M.HostViewSynthesisLoss(N, Cc, H, W, [(d.shape[-1], d.shape[-2]) for d in disps], K, invK, device=dev, source_ids=(2,), groups=2)
+    loss = hv(x, disps, [rv[1]], [tv[1]])
+    dg = [d.to(dev).requires_grad_(True) for d in disps]
+    ref = M.view_synthesis_loss(x.to(dev), dg, [rv[1].to(dev)], [tv[1].to(dev)], K.to(dev), invK.to(dev), source_ids=(2,))
+    ref.backward()
+    assert abs(loss - ref.item()) <= 2e-6
+    for a, b in zip(hv.grads["disparities"], dg):
+        assert torch.allclose(a, b.grad.cpu(), rtol=1e-5, atol=1e-9)
