@@ -41,6 +41,7 @@ struct md2_ctx {
     size_t prof_used = 0;
     void* host[MD2_HOST_LANES] = {};   // lanes of the host-buffer entry point (md2_host.cu), created on first use
     void* opt = nullptr;    // state of md2_slow_depth (md2_optim.cu), created on first use
+    void* taps = nullptr;   // upsample tap tables per shape (md2_fused.cu), created on first use
     void* replay = nullptr; // CUDA-graph cache of the device-pointer fused calls (md2_fused.cu), created on first use
 };
 

@@ -14,6 +14,8 @@ namespace md2 {
 
 void host_path_destroy(md2_ctx* ctx);   // md2_host.cu
 void opt_path_destroy(md2_ctx* ctx);    // md2_optim.cu
+void replay_destroy(md2_ctx* ctx);
+void taps_destroy(md2_ctx* ctx);
 
 // ------------------------------------------------------------------------------------------
 // error / ctx plumbing
@@ -172,6 +174,15 @@ __device__ __forceinline__ float warp_reduce_32(float (&v)[32]) {
 constexpr int PREP_COLS = 31;
 constexpr int PREP_ROWS = 4;
 constexpr int PREP_WARPS = 8;
+#ifndef MD2_PREP_MINB
+#define MD2_PREP_MINB 4   // resident blocks per SM the lean prep kernel is compiled for (4: 64 registers, one wave at 416x128x8, some spills)
+#endif
+
+// one entry of a tap table (FusedParams::tap_x / tap_y): the two source indices and the weight of the second
+__device__ __forceinline__ void tap_load(const float* __restrict__ tab, int i, int& i0, int& i1, float& f) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(tab) + i);
+    i0 = __float_as_int(t.x); i1 = __float_as_int(t.y); f = t.z;
+}
 
 __device__ __forceinline__ float sel4(const float (&h)[4], int k) {   // k is warp-uniform
     return k == 0 ? h[0] : (k == 1 ? h[1] : (k == 2 ? h[2] : h[3]));
@@ -361,7 +372,7 @@ __device__ __forceinline__ float warp_reduce_16(float (&v)[16]) {
 // of its instructions on per-scale bookkeeping): scales 0 .. NLOW-1 are low-resolution, scale NLOW (the last) is at
 // full resolution, the call is the fused fwd+bwd one (statistics wanted), 3 (NLOW + 1) <= 16.
 template <int C, int NLOW>
-__global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __grid_constant__ FusedParams p, int strips, int chunks,
+__global__ void __launch_bounds__(32 * PREP_WARPS, MD2_PREP_MINB) prep_fast_kernel(const __grid_constant__ FusedParams p, int strips, int chunks,
                                                                     int nblk, float* __restrict__ pose_ab,
                                                                     float* __restrict__ part, int zero_blocks) {
     constexpr int NS = NLOW + 1;
@@ -370,6 +381,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
     pdl_trigger();
     if (blockIdx.x == 0 || (int)blockIdx.x > nblk) { prep_pose_or_zero<C>(p, nblk, pose_ab, zero_blocks); return; }
     __shared__ float red[PREP_WARPS][16];
+    __shared__ float hrow[PREP_WARPS][4][32];               // the four horizontally interpolated low-res rows of a patch, per lane
     const int W = p.W, H = p.H, HW = W * H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = (blockIdx.x - 1) * PREP_WARPS + warp;
@@ -403,8 +415,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
     for (int l = 0; l < NLOW; ++l) {
         const int dw = p.dw[l], dh = p.dh[l];
         int xa0, xa1, yb1; float fy0;
-        up_taps(gxc, dw, W, xa0, xa1, fxu[l]);
-        up_taps(min(Y0, H - 1), dh, H, yb[l], yb1, fy0);
+        tap_load(p.tap_x[l], gxc, xa0, xa1, fxu[l]);
+        tap_load(p.tap_y[l], min(Y0, H - 1), yb[l], yb1, fy0);
         const float* dp = p.disp[l] + (long long)n * dw * dh;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -439,16 +451,18 @@ __global__ void __launch_bounds__(32 * PREP_WARPS, 3) prep_fast_kernel(const __g
 #pragma unroll
             for (int r = 0; r <= PREP_ROWS; ++r) d[r] = dnat[r];
         } else {
-            const int dh = p.dh[l];
-            float h[4];                                      // low-res rows yb .. yb+3, interpolated horizontally
+            // low-res rows yb .. yb+3, interpolated horizontally, parked in this lane's column of shared memory: the rows a
+            // full-resolution row needs are picked by a warp-uniform index (no select chains, no barrier: lane-private)
+            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = fmaf(fxu[l], q[l][2 * k + 1] - q[l][2 * k], q[l][2 * k]);
+            for (int k = 0; k < 4; ++k) hrow[warp][k][lane] = fmaf(fxu[l], q[l][2 * k + 1] - q[l][2 * k], q[l][2 * k]);
+            __syncwarp();
             float* out = const_cast<float*>(p.dfull[l]) + ((long long)n * HW + gx);
 #pragma unroll
             for (int r = 0; r <= PREP_ROWS; ++r) {
                 int ya0, ya1; float fyu;
-                up_taps(min(Y0 + r, H - 1), dh, H, ya0, ya1, fyu);
-                const float top = sel4(h, ya0 - yb[l]), bot = sel4(h, ya1 - yb[l]);
+                tap_load(p.tap_y[l], min(Y0 + r, H - 1), ya0, ya1, fyu);
+                const float top = hrow[warp][(ya0 - yb[l]) & 3][lane], bot = hrow[warp][(ya1 - yb[l]) & 3][lane];
                 d[r] = fmaf(fyu, bot - top, top);
                 if (r < PREP_ROWS && Y0 + r < H && own_col) out[yo[r]] = d[r];
             }
@@ -725,11 +739,13 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
         yhi = min(H - 1, (int)ceilf((float)(yi + 1) / sy) + 1);
     }
     __shared__ float wys[FIN_MAXROWS];
+    const float* __restrict__ tyl = p.tap_y[l];
+    const float* __restrict__ txl = p.tap_x[l];
     // trim the conservative row range to the rows that really contribute (weight != 0)
     {
         int y0, y1; float fy;
-        while (ylo < yhi) { up_taps(ylo, h, H, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; ++ylo; }
-        while (yhi > ylo) { up_taps(yhi, h, H, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; --yhi; }
+        while (ylo < yhi) { tap_load(tyl, ylo, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; ++ylo; }
+        while (yhi > ylo) { tap_load(tyl, yhi, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; --yhi; }
     }
     const int ny = yhi - ylo + 1;
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
@@ -737,7 +753,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
         __syncthreads();
         if ((int)threadIdx.x < FIN_MAXROWS && base + (int)threadIdx.x < ny) {
             int y0, y1; float fy;
-            up_taps(ylo + base + threadIdx.x, h, H, y0, y1, fy);
+            tap_load(tyl, ylo + base + threadIdx.x, y0, y1, fy);
             wys[threadIdx.x] = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
         }
         __syncthreads();
@@ -776,7 +792,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
         float acc = 0.f;
         for (int x = xlo; x <= xhi; ++x) {
             int x0, x1; float fx;
-            up_taps(x, w, W, x0, x1, fx);
+            tap_load(txl, x, x0, x1, fx);
             const float wx = (x0 == xi ? 1.f - fx : 0.f) + (x1 == xi ? fx : 0.f);
             acc = fmaf(wx, vrow[x], acc);
         }
@@ -951,6 +967,82 @@ static int choose_march_rows_uncached(int W, int H, int LN, bool bwd, int sms, i
     return best_R;
 }
 
+// Tap tables of the align-corners upsample (A17) for the low-resolution scales of a shape: computed on the host with the
+// very function the kernels used to call per pixel (up_taps: exact integer arithmetic, one division per call), uploaded
+// once and kept per shape.  Read-only afterwards, so all streams / workspace banks share them.
+struct TapsEntry {
+    int W, H, L, dw[MAX_L], dh[MAX_L];
+    float* dev = nullptr;
+    uint64_t last_use = 0;
+};
+struct TapsCache {
+    static constexpr int CAP = 8;
+    TapsEntry e[CAP];
+    int used = 0;
+    uint64_t tick = 0;
+};
+void taps_destroy(md2_ctx* ctx) {
+    TapsCache* tc = static_cast<TapsCache*>(ctx->taps);
+    if (!tc) return;
+    for (int i = 0; i < tc->used; ++i)
+        if (tc->e[i].dev) cudaFree(tc->e[i].dev);
+    delete tc;
+    ctx->taps = nullptr;
+}
+// fills p.tap_x / p.tap_y; returns non-zero on error
+static int taps_get(md2_ctx* ctx, const md2_vsl_desc* d, FusedParams& p, cudaStream_t st) {
+    if (!ctx->taps) ctx->taps = new TapsCache();
+    TapsCache* tc = static_cast<TapsCache*>(ctx->taps);
+    ++tc->tick;
+    TapsEntry* hit = nullptr;
+    for (int i = 0; i < tc->used && !hit; ++i) {
+        TapsEntry& e = tc->e[i];
+        if (e.W == d->W && e.H == d->H && e.L == d->L && memcmp(e.dw, d->disp_w, sizeof(int) * d->L) == 0 && memcmp(e.dh, d->disp_h, sizeof(int) * d->L) == 0) hit = &e;
+    }
+    const int W = d->W, H = d->H;
+    if (!hit) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+            return set_error("internal: tap tables of a new shape requested under stream capture");
+        if (tc->used < TapsCache::CAP) hit = &tc->e[tc->used++];
+        else {
+            hit = &tc->e[0];
+            for (int i = 1; i < tc->used; ++i) if (tc->e[i].last_use < hit->last_use) hit = &tc->e[i];
+            MD2_CHECK(cudaDeviceSynchronize());              // a launch in flight may still read the evicted table
+            cudaFree(hit->dev); hit->dev = nullptr;
+            for (int b = 0; b < MD2_WS_BANKS; ++b) ctx->ws_gen[b]++;   // captured graphs hold its address
+        }
+        int n_low = 0;
+        for (int l = 0; l < d->L; ++l) n_low += (d->disp_w[l] != W || d->disp_h[l] != H) ? 1 : 0;
+        std::vector<float> h((size_t)4 * n_low * (W + H), 0.f);
+        size_t o = 0;
+        for (int l = 0; l < d->L; ++l) {
+            if (d->disp_w[l] == W && d->disp_h[l] == H) continue;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int n = pass ? H : W, m = pass ? d->disp_h[l] : d->disp_w[l];
+                for (int x = 0; x < n; ++x, o += 4) {
+                    int i0, i1; float f;
+                    up_taps(x, m, n, i0, i1, f);
+                    memcpy(&h[o], &i0, 4); memcpy(&h[o + 1], &i1, 4); h[o + 2] = f;
+                }
+            }
+        }
+        MD2_CHECK(cudaMalloc(&hit->dev, sizeof(float) * (h.size() + 4)));
+        MD2_CHECK(cudaMemcpy(hit->dev, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
+        hit->W = W; hit->H = H; hit->L = d->L;
+        memset(hit->dw, 0, sizeof(hit->dw)); memset(hit->dh, 0, sizeof(hit->dh));
+        memcpy(hit->dw, d->disp_w, sizeof(int) * d->L); memcpy(hit->dh, d->disp_h, sizeof(int) * d->L);
+    }
+    hit->last_use = tc->tick;
+    const float* q = hit->dev;
+    for (int l = 0; l < d->L; ++l) {
+        if (d->disp_w[l] == W && d->disp_h[l] == H) { p.tap_x[l] = p.tap_y[l] = nullptr; continue; }
+        p.tap_x[l] = q; q += (size_t)4 * W;
+        p.tap_y[l] = q; q += (size_t)4 * H;
+    }
+    return 0;
+}
+
 static int check_desc(const md2_vsl_desc* d, bool need_loss_inputs) {
     MD2_REQUIRE(d != nullptr, "null descriptor");
     MD2_REQUIRE(d->W >= 2 && d->H >= 2 && d->W <= 65535 && d->H <= 32767, "W, H must be in 2..65535 / 2..32767");
@@ -1028,6 +1120,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
             low_rows += d->disp_h[l];
         }
     }
+    if (n_low && taps_get(ctx, d, p, st)) return 1;
     {   // full-resolution views of every scale: the caller's buffers for native-size scales, L2-resident
         // scratch (upsampled disparity; full-resolution gradient before its adjoint down-sampling) otherwise
         const size_t img = (size_t)N * W * H;
@@ -1444,6 +1537,7 @@ int md2_destroy(md2_ctx* ctx) {
     md2::host_path_destroy(ctx);
     md2::opt_path_destroy(ctx);
     md2::replay_destroy(ctx);
+    md2::taps_destroy(ctx);
     delete ctx;
     return 0;
 }

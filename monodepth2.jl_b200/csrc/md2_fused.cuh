@@ -59,6 +59,9 @@ struct FusedParams {
     const float* prep_part;
     int prep_nblk;
     float usx[MAX_L], usy[MAX_L];       // up_scale(dw, W), up_scale(dh, H) of every scale (host-computed: no device divisions)
+    // align-corners upsample taps of the low-resolution scales, tabulated once per shape on the host (up_taps is exact
+    // integer arithmetic with a division per call): entry x of tap_x[l] / y of tap_y[l] = { i0, i1 (int bits), f, 0 }
+    const float* tap_x[MAX_L]; const float* tap_y[MAX_L];
     int* dbg;                           // optional test hook: the discrete decisions per pixel and scale (md2.h: debug_choices)
 };
 
