@@ -731,31 +731,19 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
     if (l < 0 || n >= p.N) return;
     const int w = p.dw[l], h = p.dh[l];
     const int W = p.W, H = p.H;
-    const float sx = p.usx[l], sy = p.usy[l];
     const float* g = p.gfull[l] + (long long)n * W * H;
-    int ylo = 0, yhi = H - 1;
-    if (sy > 0.f) {
-        ylo = max(0, (int)floorf((float)(yi - 1) / sy) - 1);
-        yhi = min(H - 1, (int)ceilf((float)(yi + 1) / sy) + 1);
-    }
     __shared__ float wys[FIN_MAXROWS];
-    const float* __restrict__ tyl = p.tap_y[l];
-    const float* __restrict__ txl = p.tap_x[l];
-    // trim the conservative row range to the rows that really contribute (weight != 0)
+    const float* __restrict__ wts = p.inv_w[l];
+    // the full-resolution rows that reach low-res row yi and their weights (adjoint tap table: no search, no divisions)
+    int ylo, ny, ystart;
     {
-        int y0, y1; float fy;
-        while (ylo < yhi) { tap_load(tyl, ylo, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; ++ylo; }
-        while (yhi > ylo) { tap_load(tyl, yhi, y0, y1, fy); if (((y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f)) != 0.f) break; --yhi; }
+        const float4 e = __ldg(reinterpret_cast<const float4*>(p.inv_y[l]) + yi);
+        ylo = __float_as_int(e.x); ny = __float_as_int(e.y); ystart = __float_as_int(e.z);
     }
-    const int ny = yhi - ylo + 1;
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
     for (int base = 0; base < ny; base += FIN_MAXROWS) {
         __syncthreads();
-        if ((int)threadIdx.x < FIN_MAXROWS && base + (int)threadIdx.x < ny) {
-            int y0, y1; float fy;
-            tap_load(tyl, ylo + base + threadIdx.x, y0, y1, fy);
-            wys[threadIdx.x] = (y0 == yi ? 1.f - fy : 0.f) + (y1 == yi ? fy : 0.f);
-        }
+        if ((int)threadIdx.x < FIN_MAXROWS && base + (int)threadIdx.x < ny) wys[threadIdx.x] = __ldg(wts + ystart + base + threadIdx.x);
         __syncthreads();
         const int cnt = min(FIN_MAXROWS, ny - base);
         if (vec) {
@@ -782,20 +770,13 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
         }
     }
     __syncthreads();
-    const float rsx = sx > 0.f ? 1.0f / sx : 0.f;
     for (int xi = threadIdx.x; xi < w; xi += FIN_THREADS) {
-        int xlo = 0, xhi = W - 1;
-        if (sx > 0.f) {
-            xlo = max(0, (int)floorf((float)(xi - 1) * rsx) - 1);
-            xhi = min(W - 1, (int)ceilf((float)(xi + 1) * rsx) + 1);
-        }
+        const float4 e = __ldg(reinterpret_cast<const float4*>(p.inv_x[l]) + xi);
+        const int xlo = __float_as_int(e.x), nx = __float_as_int(e.y);
+        const float* __restrict__ wx = wts + __float_as_int(e.z);
         float acc = 0.f;
-        for (int x = xlo; x <= xhi; ++x) {
-            int x0, x1; float fx;
-            tap_load(txl, x, x0, x1, fx);
-            const float wx = (x0 == xi ? 1.f - fx : 0.f) + (x1 == xi ? fx : 0.f);
-            acc = fmaf(wx, vrow[x], acc);
-        }
+#pragma unroll 4
+        for (int k = 0; k < nx; ++k) acc = fmaf(__ldg(wx + k), vrow[xlo + k], acc);
         p.gdisp[l][((long long)n * h + yi) * w + xi] = acc;
     }
 }
@@ -972,6 +953,7 @@ static int choose_march_rows_uncached(int W, int H, int LN, bool bwd, int sms, i
 // once and kept per shape.  Read-only afterwards, so all streams / workspace banks share them.
 struct TapsEntry {
     int W, H, L, dw[MAX_L], dh[MAX_L];
+    int wcount[MAX_L] = {};   // floats of the inverse weight list of every low-res scale
     float* dev = nullptr;
     uint64_t last_use = 0;
 };
@@ -1012,20 +994,40 @@ static int taps_get(md2_ctx* ctx, const md2_vsl_desc* d, FusedParams& p, cudaStr
             cudaFree(hit->dev); hit->dev = nullptr;
             for (int b = 0; b < MD2_WS_BANKS; ++b) ctx->ws_gen[b]++;   // captured graphs hold its address
         }
-        int n_low = 0;
-        for (int l = 0; l < d->L; ++l) n_low += (d->disp_w[l] != W || d->disp_h[l] != H) ? 1 : 0;
-        std::vector<float> h((size_t)4 * n_low * (W + H), 0.f);
-        size_t o = 0;
+        // layout per low-res scale: tap_x (4W) | tap_y (4H) | inv_x (4w) | inv_y (4h) | inv_w (weights of x, then of y)
+        std::vector<float> h;
         for (int l = 0; l < d->L; ++l) {
             if (d->disp_w[l] == W && d->disp_h[l] == H) continue;
+            std::vector<int> i0s[2], i1s[2];
+            std::vector<float> fs[2];
             for (int pass = 0; pass < 2; ++pass) {
                 const int n = pass ? H : W, m = pass ? d->disp_h[l] : d->disp_w[l];
-                for (int x = 0; x < n; ++x, o += 4) {
-                    int i0, i1; float f;
-                    up_taps(x, m, n, i0, i1, f);
-                    memcpy(&h[o], &i0, 4); memcpy(&h[o + 1], &i1, 4); h[o + 2] = f;
+                i0s[pass].resize(n); i1s[pass].resize(n); fs[pass].resize(n);
+                for (int x = 0; x < n; ++x) {
+                    up_taps(x, m, n, i0s[pass][x], i1s[pass][x], fs[pass][x]);
+                    float e[4] = {0.f, 0.f, fs[pass][x], 0.f};
+                    memcpy(&e[0], &i0s[pass][x], 4); memcpy(&e[1], &i1s[pass][x], 4);
+                    h.insert(h.end(), e, e + 4);
                 }
             }
+            std::vector<float> wts;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int n = pass ? H : W, m = pass ? d->disp_h[l] : d->disp_w[l];
+                for (int i = 0; i < m; ++i) {
+                    auto wgt = [&](int x) { return (i0s[pass][x] == i ? 1.f - fs[pass][x] : 0.f) + (i1s[pass][x] == i ? fs[pass][x] : 0.f); };
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi && wgt(lo) == 0.f) ++lo;
+                    while (hi > lo && wgt(hi) == 0.f) --hi;
+                    const int cnt = hi - lo + 1, start = (int)wts.size();
+                    for (int x = lo; x <= hi; ++x) wts.push_back(wgt(x));
+                    float e[4] = {0.f, 0.f, 0.f, 0.f};
+                    memcpy(&e[0], &lo, 4); memcpy(&e[1], &cnt, 4); memcpy(&e[2], &start, 4);
+                    h.insert(h.end(), e, e + 4);
+                }
+            }
+            while (wts.size() & 3) wts.push_back(0.f);       // keep the next scale's tables 16-byte aligned
+            h.insert(h.end(), wts.begin(), wts.end());
+            hit->wcount[l] = (int)wts.size();
         }
         MD2_CHECK(cudaMalloc(&hit->dev, sizeof(float) * (h.size() + 4)));
         MD2_CHECK(cudaMemcpy(hit->dev, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
@@ -1036,9 +1038,12 @@ static int taps_get(md2_ctx* ctx, const md2_vsl_desc* d, FusedParams& p, cudaStr
     hit->last_use = tc->tick;
     const float* q = hit->dev;
     for (int l = 0; l < d->L; ++l) {
-        if (d->disp_w[l] == W && d->disp_h[l] == H) { p.tap_x[l] = p.tap_y[l] = nullptr; continue; }
+        if (d->disp_w[l] == W && d->disp_h[l] == H) { p.tap_x[l] = p.tap_y[l] = p.inv_x[l] = p.inv_y[l] = p.inv_w[l] = nullptr; continue; }
         p.tap_x[l] = q; q += (size_t)4 * W;
         p.tap_y[l] = q; q += (size_t)4 * H;
+        p.inv_x[l] = q; q += (size_t)4 * d->disp_w[l];
+        p.inv_y[l] = q; q += (size_t)4 * d->disp_h[l];
+        p.inv_w[l] = q; q += (size_t)hit->wcount[l];
     }
     return 0;
 }

@@ -62,6 +62,9 @@ struct FusedParams {
     // align-corners upsample taps of the low-resolution scales, tabulated once per shape on the host (up_taps is exact
     // integer arithmetic with a division per call): entry x of tap_x[l] / y of tap_y[l] = { i0, i1 (int bits), f, 0 }
     const float* tap_x[MAX_L]; const float* tap_y[MAX_L];
+    // ... and their adjoint (gather form of the upsample's pullback): entry i of inv_x[l] / inv_y[l] = { lo, count, start
+    // (int bits), 0 }: low-res index i receives full-res indices lo .. lo+count-1 with the weights inv_w[l][start ..]
+    const float* inv_x[MAX_L]; const float* inv_y[MAX_L]; const float* inv_w[MAX_L];
     int* dbg;                           // optional test hook: the discrete decisions per pixel and scale (md2.h: debug_choices)
 };
 

@@ -176,4 +176,4 @@ def test_two_rank_nccl_step_equals_the_full_batch_step():
             assert np.abs(0.5 * g - gfull).max() <= 2e-4 * np.abs(gfull).max()
             assert np.abs(p - pfull).max() <= 2.5e-4          # (ADAM's first step is +-lr per element: sign flips of ~0 gradients)
             assert (np.abs(p - pfull) < 1e-6).mean() > 0.98
-        assert np.array_equal(r[True][0], r[False][0])
+        assert np.allclose(r[True][0], r[False][0], rtol=1e-4, atol=1e-7 * np.abs(gfull).max())    # overlapped == blocking all-reduce
