@@ -128,7 +128,7 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 #define MD2_M2_MAXREG_C1 128
 #endif
 #ifndef MD2_M2_MAXREG_C3
-#define MD2_M2_MAXREG_C3 192
+#define MD2_M2_MAXREG_C3 255   // (129 .. 255 registers all give two warps per scheduler: take the room, no spills)
 #endif
 
 // AM: the call has an automask map (src/training.jl:60-62); DBG: test hook, also exports the discrete decisions of every
@@ -160,7 +160,9 @@ struct March2 {
     static constexpr int TOTAL4 = NSLOT * NP4 + NHIST * NH4;   // Vec4 per lane
     static constexpr int SMEM_FLOATS = TOTAL4 * 32 * 4;
     static constexpr int THREADS = 32;
-    static constexpr int MAXREG = C == 1 ? MD2_M2_MAXREG_C1 : MD2_M2_MAXREG_C3;
+    // (registers are allocated per scheduler: <= 128 -> 4 warps, <= 168 -> 3, <= 255 -> 2.  C = 3 with two sources does not fit 168
+    // without spilling, so it takes the whole 2-warp budget; C = 3 with one source fits 168)
+    static constexpr int MAXREG = C == 1 ? MD2_M2_MAXREG_C1 : (S == 1 ? 168 : MD2_M2_MAXREG_C3);
     static_assert(P_U + S <= NE4 * 4 && P_V + S <= NE4 * 4 && P_OFF + S <= NE4 * 4, "u, v, off must fit the early words");
 
     // image row read for march row i (reflect-pad(1) above and below the image, clamped beyond)
