@@ -319,26 +319,25 @@ def run_ours(args):
         barrier()
         return NB * world * e_steps / (e_ms * 1e-3), e_ms, pct, hv.h2d_bytes, hv.d2h_bytes
 
-    def pcie_probe(h2d_bytes, d2h_bytes, iters=40):
-        """the floor of the end-to-end step on THIS box at THIS N: every rank moves the step's input bytes to its GPU and the
-        step's output bytes back, both directions at once, back to back, nothing else (pinned buffers, two streams)"""
-        hin, hout = torch.empty(h2d_bytes // 4).pin_memory(), torch.empty(d2h_bytes // 4).pin_memory()
-        din, dout = torch.empty(h2d_bytes // 4, device=dev), torch.zeros(d2h_bytes // 4, device=dev)
-        sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        def burst(n):
-            for _ in range(n):
-                with torch.cuda.stream(sa):
-                    din.copy_(hin, non_blocking=True)
-                with torch.cuda.stream(sb):
-                    hout.copy_(dout, non_blocking=True)
-            sa.synchronize(); sb.synchronize()
-        burst(5)
-        barrier()
-        t0 = time.perf_counter()
-        burst(iters)
-        ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev) / iters
-        barrier()
-        return ms
+    def pcie_probe(h2d_bytes, d2h_bytes):
+        """the floor of the end-to-end step on THIS box at THIS N: the step's bytes at the large-transfer bandwidth of the
+        host link, measured here with all ranks copying at once (64 MB pinned buffers, back to back, each direction)"""
+        n = (64 << 20) // 4
+        hbuf, dbuf = torch.empty(n).pin_memory(), torch.empty(n, device=dev)
+        rates = {}
+        for direction in ("h2d", "d2h"):
+            def burst(k):
+                for _ in range(k):
+                    (dbuf.copy_(hbuf, non_blocking=True) if direction == "h2d" else hbuf.copy_(dbuf, non_blocking=True))
+                torch.cuda.synchronize(dev)
+            burst(3)
+            barrier()
+            t0 = time.perf_counter()
+            burst(8)
+            ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev) / 8
+            rates[direction] = 4 * n / (ms * 1e-3) / 1e9
+            barrier()
+        return max(h2d_bytes / rates["h2d"], d2h_bytes / rates["d2h"]) / 1e6, rates
 
     e_steps = min(args.steps, 500)
     # what a training step needs on the host: the loss and the gradients of the network outputs (disparities, poses).
@@ -347,7 +346,7 @@ def run_ours(args):
     e2e_sync, es_ms, es_pct, h2d, d2h = time_host(False, e_steps, lanes=1)
     e2e_value, e_ms, e2e_pct, _, _ = time_host(False, e_steps, lanes=2)
     e2e_g1, _, _, h2d_g1, d2h_g1 = time_host(True, max(50, e_steps // 2), lanes=2)
-    floor_ms = pcie_probe(h2d, d2h)
+    floor_ms, link = pcie_probe(h2d, d2h)
 
     # the same through the autograd mirror of the reference API (torch tensors, many small copies): secondary figure
     pin = lambda t: t.contiguous().pin_memory()
@@ -408,8 +407,9 @@ def run_ours(args):
                        "monodepth2_jl_b200.HostViewSynthesisLoss(lanes=2), pinned host buffers, every step's loss and gradients collected on the host",
                 "value_synchronous": round(e2e_sync, 1), "ms_per_step_synchronous": round(es_ms / e_steps, 5), "ms_per_call_synchronous_p5_p50_p95": es_pct,
                 "pcie_floor_ms": round(floor_ms, 5), "pcie_floor_frames_per_s": round(NB * world / (floor_ms * 1e-3), 1),
-                "pcie_floor_note": f"measured in this run: all {world} rank(s) at once copy the step's {h2d} B host->device and {d2h} B device->host "
-                                   "(pinned, both directions concurrently, back to back, no kernels): the ceiling of any end-to-end step on this host",
+                "host_link_GBps_per_gpu": {k: round(v, 1) for k, v in link.items()},
+                "pcie_floor_note": f"the step's {h2d} B host->device and {d2h} B device->host at the large-transfer rate of the host link measured in this run "
+                                   f"(64 MB pinned copies, all {world} rank(s) at once): max of the two directions",
                 "autograd_api_value": round(e2e_autograd, 1), "cpus_bound_to_gpu_numa_node": bound},
         "roofline": {"bound": "hbm", "kernel": f"march2_kernel<C={CH},S=2,AM={int(AM)}> (fused fwd+bwd single-warp marching kernel, all scales in one launch)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
