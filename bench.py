@@ -291,14 +291,16 @@ def run_ours(args):
             run = lambda: hv()
             hv()                                # first call sizes the workspaces and captures the graph
         else:
-            hv.submit(0); hv.submit(1); hv.wait(0)          # (captures both lanes' graphs; lane 1 stays in flight)
+            for lane in range(lanes):           # (captures every lane's graph)
+                hv.submit(lane)
+            hv.wait(0)
             state = {"k": 0}
 
-            def run():                          # one step: submit on the free lane, collect the other lane's (previous) step
-                lane = state["k"] & 1
+            def run():                          # one step: submit on the free lane, collect the OLDEST step in flight
+                lane = state["k"] % lanes
                 hv.submit(lane)
                 state["k"] += 1
-                return hv.wait(lane ^ 1)
+                return hv.wait((lane + 1) % lanes)
         for _ in range(6):
             run()
         barrier()
@@ -310,8 +312,9 @@ def run_ours(args):
             t1 = time.perf_counter()
             run()
             per_call.append(time.perf_counter() - t1)
-        if lanes == 2:
-            hv.wait((state["k"] - 1) & 1)       # the last step in flight
+        if lanes > 1:
+            for j in range(1, lanes):           # the steps still in flight
+                hv.wait((state["k"] - j) % lanes)
         e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev)
         gc.enable()
         per_call.sort()
@@ -320,23 +323,25 @@ def run_ours(args):
         return NB * world * e_steps / (e_ms * 1e-3), e_ms, pct, hv.h2d_bytes, hv.d2h_bytes
 
     def pcie_probe(h2d_bytes, d2h_bytes):
-        """the floor of the end-to-end step on THIS box at THIS N: the step's bytes at the large-transfer bandwidth of the
-        host link, measured here with all ranks copying at once (64 MB pinned buffers, back to back, each direction)"""
-        n = (64 << 20) // 4
-        hbuf, dbuf = torch.empty(n).pin_memory(), torch.empty(n, device=dev)
-        rates = {}
-        for direction in ("h2d", "d2h"):
-            def burst(k):
-                for _ in range(k):
-                    (dbuf.copy_(hbuf, non_blocking=True) if direction == "h2d" else hbuf.copy_(dbuf, non_blocking=True))
-                torch.cuda.synchronize(dev)
-            burst(3)
-            barrier()
-            t0 = time.perf_counter()
-            burst(8)
-            ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev) / 8
-            rates[direction] = 4 * n / (ms * 1e-3) / 1e9
-            barrier()
+        """the floor of the end-to-end step on THIS box at THIS N: the step's bytes at the best rate the host link shows
+        in this run with all ranks copying at once (pinned buffers of 64 MB, 16 MB and of the step's own size, back to
+        back, each direction; the host->device rate of these boxes varies with the transfer size, so the best is taken)"""
+        rates = {"h2d": 0.0, "d2h": 0.0}
+        for nbytes in (64 << 20, 16 << 20, h2d_bytes):
+            n = nbytes // 4
+            hbuf, dbuf = torch.empty(n).pin_memory(), torch.empty(n, device=dev)
+            for direction in ("h2d", "d2h"):
+                def burst(k):
+                    for _ in range(k):
+                        (dbuf.copy_(hbuf, non_blocking=True) if direction == "h2d" else hbuf.copy_(dbuf, non_blocking=True))
+                    torch.cuda.synchronize(dev)
+                burst(3)
+                barrier()
+                t0 = time.perf_counter()
+                burst(8)
+                ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev) / 8
+                rates[direction] = max(rates[direction], 4 * n / (ms * 1e-3) / 1e9)
+                barrier()
         return max(h2d_bytes / rates["h2d"], d2h_bytes / rates["d2h"]) / 1e6, rates
 
     e_steps = min(args.steps, 500)
@@ -344,8 +349,8 @@ def run_ours(args):
     # The gradient of the source IMAGES (g = 1 of the device-resident figure) is computed by Zygote in the reference and
     # thrown away -- it is not an output a trainer reads back; the same call with it copied back too is `value_g1`.
     e2e_sync, es_ms, es_pct, h2d, d2h = time_host(False, e_steps, lanes=1)
-    e2e_value, e_ms, e2e_pct, _, _ = time_host(False, e_steps, lanes=2)
-    e2e_g1, _, _, h2d_g1, d2h_g1 = time_host(True, max(50, e_steps // 2), lanes=2)
+    e2e_value, e_ms, e2e_pct, _, _ = time_host(False, e_steps, lanes=args.e2e_lanes)
+    e2e_g1, _, _, h2d_g1, d2h_g1 = time_host(True, max(50, e_steps // 2), lanes=args.e2e_lanes)
     floor_ms, link = pcie_probe(h2d, d2h)
 
     # the same through the autograd mirror of the reference API (torch tensors, many small copies): secondary figure
@@ -403,13 +408,13 @@ def run_ours(args):
                         "discards, is neither formed nor copied back); value_g1 = the same call with the source-image gradients formed and copied back too",
                 "value_g1": round(e2e_g1, 1), "d2h_bytes_per_step_g1": d2h_g1,
                 "api": "md2_view_synthesis_loss_fwdbwd_host_submit / md2_host_wait (C ABI, host pointers; copies and kernels of a call on "
-                       "copy/compute streams, replayed as a CUDA graph; two lanes: step i+1 is submitted before step i is collected) via "
-                       "monodepth2_jl_b200.HostViewSynthesisLoss(lanes=2), pinned host buffers, every step's loss and gradients collected on the host",
+                       "copy/compute streams, replayed as a CUDA graph; " + f"{args.e2e_lanes} lanes: a step is submitted before the oldest one in flight is collected; the pinned inputs / gradients of a lane are one "
+                       "allocation each and travel as one copy each way) via monodepth2_jl_b200.HostViewSynthesisLoss, every step's loss and gradients collected on the host",
                 "value_synchronous": round(e2e_sync, 1), "ms_per_step_synchronous": round(es_ms / e_steps, 5), "ms_per_call_synchronous_p5_p50_p95": es_pct,
                 "pcie_floor_ms": round(floor_ms, 5), "pcie_floor_frames_per_s": round(NB * world / (floor_ms * 1e-3), 1),
                 "host_link_GBps_per_gpu": {k: round(v, 1) for k, v in link.items()},
-                "pcie_floor_note": f"the step's {h2d} B host->device and {d2h} B device->host at the large-transfer rate of the host link measured in this run "
-                                   f"(64 MB pinned copies, all {world} rank(s) at once): max of the two directions",
+                "pcie_floor_note": f"the step's {h2d} B host->device and {d2h} B device->host at the best rate the host link showed in this run "
+                                   f"(pinned copies of 64 MB / 16 MB / the step's size, all {world} rank(s) at once): max of the two directions",
                 "autograd_api_value": round(e2e_autograd, 1), "cpus_bound_to_gpu_numa_node": bound},
         "roofline": {"bound": "hbm", "kernel": f"march2_kernel<C={CH},S=2,AM={int(AM)}> (fused fwd+bwd single-warp marching kernel, all scales in one launch)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -636,6 +641,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=2)
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="steps in flight in the multi-buffered end-to-end measurement (2 or 3)")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the GPU-local CPUs")
     ap.add_argument("--config", type=int, default=2, choices=[1] + sorted(CONFIGS),
                     help="BASELINE.json configuration (1-based): 2 (default, the metric's), 3, 4; 1 = the slow_depth triplet optimiser")

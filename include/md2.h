@@ -34,6 +34,7 @@ extern "C" {
 #define MD2_MAX_SOURCES 2
 #define MD2_MAX_SCALES 8
 #define MD2_ADAM_MAX_TENSORS 16
+#define MD2_HOST_LANES 3
 
 typedef struct md2_ctx md2_ctx;
 typedef void* md2_stream;
@@ -185,10 +186,12 @@ int md2_view_synthesis_loss_fwdbwd(md2_ctx*, const md2_vsl_desc*, float seed, md
  * three streams, and the pipeline is replayed as one CUDA graph while the descriptor stays the same.
  * Synchronous: returns when every output is in host memory.  saved / viz_* must be NULL. */
 int md2_view_synthesis_loss_fwdbwd_host(md2_ctx*, const md2_vsl_desc* host_desc, float seed, int32_t groups);
-/* Asynchronous form, for a caller that double-buffers its batches (a data loader one step ahead): `submit` enqueues the
- * call on lane 0 or 1 and returns at once; `md2_host_wait(lane)` blocks until that call's outputs are in host memory.
- * The two lanes own separate streams, staging buffers, scratch and cached graphs, so the device-to-host copies of step i
- * overlap the host-to-device copies and kernels of step i+1 (submit(i+1, lane B) before wait(lane A)).  The host
+/* Asynchronous form, for a caller that multi-buffers its batches (a data loader a step or two ahead): `submit` enqueues
+ * the call on lane 0 .. MD2_HOST_LANES-1 and returns at once; `md2_host_wait(lane)` blocks until that call's outputs are in
+ * host memory.  The lanes own separate streams, staging buffers, scratch and cached graphs, so the device-to-host copies
+ * of step i overlap the host-to-device copies and kernels of step i+1 (submit(i+1, lane B) before wait(lane A)).
+ * With one image group (groups = 1), inputs that lie in ONE stretch of host memory (frames, every disparity, automask
+ * carved out of one pinned allocation) travel as a single copy, and so do the disparity gradients on the way back.  The host
  * buffers of a submitted descriptor must stay valid and untouched until its wait returns; submitting on a lane with an
  * uncollected call collects that call first.  md2_view_synthesis_loss_fwdbwd_host == submit + wait on lane 0. */
 int md2_view_synthesis_loss_fwdbwd_host_submit(md2_ctx*, const md2_vsl_desc* host_desc, float seed, int32_t groups, int32_t lane);

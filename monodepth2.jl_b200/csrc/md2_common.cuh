@@ -25,7 +25,7 @@ enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, 
        MD2_WS_MISC, MD2_WS_COUNT };
 // workspace banks: calls that may be in flight at the same time must not share scratch.  Bank 0 serves the
 // device-pointer entry points (one stream at a time, md2.h), banks 1.. the lanes of the host-buffer entry point.
-enum { MD2_HOST_LANES = 2, MD2_WS_BANKS = 1 + MD2_HOST_LANES };
+enum { MD2_WS_BANKS = 1 + MD2_HOST_LANES };
 
 #include <vector>
 struct md2_ctx {

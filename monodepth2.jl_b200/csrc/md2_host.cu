@@ -102,9 +102,31 @@ struct Mirror {
     bool xcontig;                  // frames travel as whole images of `xstride` floats starting at host pointer xbase
     const float* xbase; float* xall; int64_t xstride;
     int64_t xspan;                 // floats from xbase to the end of the last frame in use of one image
+    // slab mode (one image group): every large input / every disparity gradient lies in ONE stretch of host memory
+    // (a caller that carves its pinned buffers out of one allocation): the device mirror keeps the host layout and the
+    // stretch travels as a single copy at the large-transfer rate of the link
+    bool in_slab, out_slab;
+    const float* in_lo; float* in_dev; size_t in_floats;
+    float* out_lo; float* out_dev; size_t out_floats;
 };
 
-static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
+// do the host ranges [p_k, p_k + n_k) tile one stretch of memory (gaps of at most `pad` floats)?  -> lowest address, span
+static bool one_stretch(const float* const* p, const size_t* n, int cnt, size_t pad, const float** lo, size_t* span) {
+    if (cnt < 2) return false;
+    int order[2 + MAX_L];
+    for (int i = 0; i < cnt; ++i) order[i] = i;
+    for (int i = 1; i < cnt; ++i)
+        for (int j = i; j > 0 && p[order[j]] < p[order[j - 1]]; --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    for (int i = 0; i + 1 < cnt; ++i) {
+        const float* end = p[order[i]] + n[order[i]];
+        if (p[order[i + 1]] < end || (size_t)(p[order[i + 1]] - end) > pad) return false;
+    }
+    *lo = p[order[0]];
+    *span = (size_t)(p[order[cnt - 1]] + n[order[cnt - 1]] - p[order[0]]);
+    return true;
+}
+
+static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m, int groups) {
     Carver c{base};
     const size_t img = (size_t)d->C * d->W * d->H, N = d->N;
     const int pr = d->pose_mode == 0 ? 9 : 3;
@@ -122,7 +144,29 @@ static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
         m.xcontig = same && st >= (int64_t)img && (hi - lo) + (int64_t)img <= st && st <= 4 * (int64_t)img * (d->S + 1);
         m.xbase = lo; m.xstride = st; m.xspan = (hi - lo) + (int64_t)img;
     }
-    if (m.xcontig) {
+    m.in_slab = m.out_slab = false;
+    if (groups == 1 && m.xcontig) {
+        const float* p[2 + MAX_L]; size_t n[2 + MAX_L]; int cnt = 0;
+        p[cnt] = m.xbase; n[cnt++] = (size_t)(N - 1) * m.xstride + (size_t)m.xspan;
+        for (int l = 0; l < d->L; ++l) { p[cnt] = d->disparity[l]; n[cnt++] = N * (size_t)d->disp_w[l] * d->disp_h[l]; }
+        if (d->automask) { p[cnt] = d->automask; n[cnt++] = N * (size_t)d->W * d->H; }
+        m.in_slab = one_stretch(p, n, cnt, 1024, &m.in_lo, &m.in_floats);
+    }
+    if (groups == 1 && d->L >= 2) {
+        const float* p[MAX_L]; size_t n[MAX_L];
+        bool all = true;
+        for (int l = 0; l < d->L; ++l) { p[l] = d->grad_disparity[l]; n[l] = N * (size_t)d->disp_w[l] * d->disp_h[l]; all = all && p[l]; }
+        const float* lo = nullptr;
+        m.out_slab = all && one_stretch(p, n, d->L, 1024, &lo, &m.out_floats);
+        m.out_lo = const_cast<float*>(lo);
+    }
+    m.in_dev = m.in_slab ? c.take(m.in_floats) : nullptr;
+    m.out_dev = m.out_slab ? c.take(m.out_floats) : nullptr;
+    if (m.in_slab) {
+        m.xall = m.in_dev ? m.in_dev + (m.xbase - m.in_lo) : nullptr;
+        m.tgt = m.xall ? m.xall + (d->target - m.xbase) : nullptr;
+        for (int s = 0; s < MAX_S; ++s) m.src[s] = (s < d->S && m.xall) ? m.xall + (d->source[s] - m.xbase) : nullptr;
+    } else if (m.xcontig) {
         m.xall = c.take(N * (size_t)m.xstride);
         m.tgt = m.xall ? m.xall + (d->target - m.xbase) : nullptr;
         for (int s = 0; s < MAX_S; ++s) m.src[s] = (s < d->S && m.xall) ? m.xall + (d->source[s] - m.xbase) : nullptr;
@@ -144,10 +188,13 @@ static size_t carve(const md2_vsl_desc* d, char* base, Mirror& m) {
     for (int l = 0; l < MAX_L; ++l) {
         const bool on = l < d->L;
         const size_t px = on ? (size_t)d->disp_w[l] * d->disp_h[l] : 0;
-        m.disp[l] = on ? c.take(N * px) : nullptr;
-        m.gdisp[l] = on ? c.take(N * px) : nullptr;
+        if (on && m.in_slab) m.disp[l] = m.in_dev ? m.in_dev + (d->disparity[l] - m.in_lo) : nullptr;
+        else m.disp[l] = on ? c.take(N * px) : nullptr;
+        if (on && m.out_slab) m.gdisp[l] = m.out_dev ? m.out_dev + (d->grad_disparity[l] - m.out_lo) : nullptr;
+        else m.gdisp[l] = on ? c.take(N * px) : nullptr;
     }
-    m.automask = d->automask ? c.take(N * (size_t)d->W * d->H) : nullptr;
+    if (d->automask && m.in_slab) m.automask = m.in_dev ? m.in_dev + (d->automask - m.in_lo) : nullptr;
+    else m.automask = d->automask ? c.take(N * (size_t)d->W * d->H) : nullptr;
     // small inputs: K, invK, then per source rot, trans
     m.small_in_floats = 18 + (size_t)d->S * (pr + 3) * N;
     m.small_in = c.take(m.small_in_floats);
@@ -199,7 +246,8 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
     MD2_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_fork, 0));
     // once per call: intrinsics and poses (one block, staged by run_host), the low-resolution disparities (small)
     MD2_H2D(m.small_in, h->hsmall, sizeof(float) * m.small_in_floats);
-    for (int l = 0; l < L; ++l)
+    if (m.in_slab) MD2_H2D(m.in_dev, m.in_lo, sizeof(float) * m.in_floats);     // frames, every disparity, automask: one copy
+    for (int l = 0; l < L && !m.in_slab; ++l)
         if (d->disp_w[l] != W || d->disp_h[l] != H)
             MD2_H2D(m.disp[l], d->disparity[l], sizeof(float) * (size_t)N * d->disp_w[l] * d->disp_h[l]);
     g_trace.mark(h->s_in, "in-small", 0);
@@ -208,7 +256,9 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
     for (int k = 0; k < groups; ++k) {
         const int n0 = (int)((long long)N * k / groups), n1 = (int)((long long)N * (k + 1) / groups), nk = n1 - n0;
         // ---- inputs of group k: frames (strided host views -> dense), full-resolution disparities, automask
-        if (m.xcontig) {
+        if (m.in_slab) {
+            // (everything travelled with the slab)
+        } else if (m.xcontig) {
             // (not nk * xstride: xbase need not be the first frame of the per-image block, and the host buffer ends with
             // the last frame of the last image)
             MD2_H2D(m.xall + (size_t)n0 * m.xstride, m.xbase + (size_t)n0 * m.xstride,
@@ -220,10 +270,10 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
                 MD2_CHECK(cudaMemcpy2DAsync(m.src[s] + n0 * img, imgb, d->source[s] + (size_t)n0 * d->source_image_stride[s],
                                             sizeof(float) * d->source_image_stride[s], imgb, nk, cudaMemcpyHostToDevice, h->s_in));
         }
-        for (int l = 0; l < L; ++l)
+        for (int l = 0; l < L && !m.in_slab; ++l)
             if (d->disp_w[l] == W && d->disp_h[l] == H)
                 MD2_H2D(m.disp[l] + (size_t)n0 * W * H, d->disparity[l] + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
-        if (d->automask) MD2_H2D(m.automask + (size_t)n0 * W * H, d->automask + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
+        if (d->automask && !m.in_slab) MD2_H2D(m.automask + (size_t)n0 * W * H, d->automask + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
         g_trace.mark(h->s_in, "in", k);
         MD2_CHECK(cudaEventRecord(h->ev_in[k], h->s_in));
         // ---- kernels of group k: the device descriptor of its images; loss_scale carries the group's share
@@ -254,7 +304,8 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
         MD2_CHECK(cudaEventRecord(h->ev_done[k], h->s_run));
         // ---- outputs of group k
         MD2_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[k], 0));
-        for (int l = 0; l < L; ++l)
+        if (m.out_slab) MD2_D2H(m.out_lo, m.out_dev, sizeof(float) * m.out_floats);    // every disparity gradient: one copy
+        for (int l = 0; l < L && !m.out_slab; ++l)
             if (d->disp_w[l] == W && d->disp_h[l] == H)
                 MD2_D2H(d->grad_disparity[l] + (size_t)n0 * W * H, m.gdisp[l] + (size_t)n0 * W * H, sizeof(float) * (size_t)nk * W * H);
         for (int s = 0; s < S; ++s)
@@ -265,7 +316,7 @@ static int enqueue(md2_ctx* ctx, HostPath* h, const md2_vsl_desc* d, const Mirro
         g_trace.mark(h->s_out, "out", k);
     }
     // once per call: the small outputs of all groups
-    for (int l = 0; l < L; ++l)
+    for (int l = 0; l < L && !m.out_slab; ++l)
         if (d->disp_w[l] != W || d->disp_h[l] != H)
             MD2_D2H(d->grad_disparity[l], m.gdisp[l], sizeof(float) * (size_t)N * d->disp_w[l] * d->disp_h[l]);
     MD2_D2H(h->hsmall + m.small_in_floats, m.small_out, sizeof(float) * m.small_out_floats);   // pose gradients + partial losses
@@ -319,14 +370,14 @@ static int submit(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int groups, i
     struct BankGuard { md2_ctx* c; int prev; ~BankGuard() { c->bank = prev; } } bank_guard{ctx, ctx->bank};
     ctx->bank = 1 + lane;
     Mirror m;
-    const size_t need = carve(d, nullptr, m);
+    const size_t need = carve(d, nullptr, m, groups);
     if (need > h->dbytes) {
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; h->have_key = false; }
         if (h->dbuf) { MD2_CHECK(cudaDeviceSynchronize()); cudaFree(h->dbuf); h->dbuf = nullptr; h->dbytes = 0; }
         MD2_CHECK(cudaMalloc(&h->dbuf, need + need / 4));
         h->dbytes = need + need / 4;
     }
-    carve(d, h->dbuf, m);
+    carve(d, h->dbuf, m, groups);
     const int pr = d->pose_mode == 0 ? 9 : 3;
     if (m.small_in_floats + m.small_out_floats > h->hsmall_floats) {
         if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; h->have_key = false; }
@@ -398,13 +449,13 @@ int md2_view_synthesis_loss_fwdbwd_host(md2_ctx* ctx, const md2_vsl_desc* d, flo
 
 int md2_view_synthesis_loss_fwdbwd_host_submit(md2_ctx* ctx, const md2_vsl_desc* d, float seed, int32_t groups, int32_t lane) {
     MD2_REQUIRE(ctx != nullptr, "null ctx");
-    MD2_REQUIRE(lane >= 0 && lane < MD2_HOST_LANES, "lane must be 0 or 1");
+    MD2_REQUIRE(lane >= 0 && lane < MD2_HOST_LANES, "lane must be in 0 .. MD2_HOST_LANES-1");
     return md2::submit(ctx, d, seed, groups, lane);
 }
 
 int md2_host_wait(md2_ctx* ctx, int32_t lane) {
     MD2_REQUIRE(ctx != nullptr, "null ctx");
-    MD2_REQUIRE(lane >= 0 && lane < MD2_HOST_LANES, "lane must be 0 or 1");
+    MD2_REQUIRE(lane >= 0 && lane < MD2_HOST_LANES, "lane must be in 0 .. MD2_HOST_LANES-1");
     MD2_USE_DEVICE(ctx);
     return md2::collect(ctx, lane);
 }

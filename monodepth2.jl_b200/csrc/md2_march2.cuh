@@ -124,6 +124,9 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 #ifndef MD2_M2_RC
 #define MD2_M2_RC 0
 #endif
+#ifndef MD2_M2_MERGE
+#define MD2_M2_MERGE 0
+#endif
 #ifndef MD2_M2_MAXREG_C1
 #define MD2_M2_MAXREG_C1 128
 #endif
@@ -613,17 +616,41 @@ struct March2 {
 #pragma unroll
                     for (int s = 0; s < S; ++s) act[s] = act[s] || (ibar[ch].v[s] != 0.f);
                 }
-                // (merging a pixel's right taps into the right-hand lane's left taps by shuffle -- two atomics per pixel and
-                // source instead of four -- was measured slower here, as in the two-warp kernel: 62.2 vs 59.5 us at 416x128x8)
+                // Merging a pixel's right taps into the right-hand lane's left taps by shuffle (two reductions per pixel and
+                // source instead of four, where neighbouring lanes sample neighbouring cells) trades 2 REDs for 2 SHFLs per
+                // channel and tap row.  C = 1: measured slower (62.2 vs 59.5 us at 416x128x8: the kernel is short of issue
+                // slots and LSU wavefronts, both cost the same).  C = 3: the warp has slots to spare and waits on its own
+                // reductions instead -- MD2_M2_MERGE selects (0: never, 1: C = 3 only, 2: always)
+                if (MD2_M2_MERGE == 2 || (MD2_M2_MERGE == 1 && C == 3)) {
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    if (act[s]) {   // (ptxas turns predicated atomics into one branch each: one region per source instead)
+                    for (int s = 0; s < S; ++s) {
+                        const int offa = act[s] ? off[s] : (-0x40000000 - lane);       // an idle lane neither gives nor receives
+                        const int nb = w_dn(offa, lane);                                // left-tap offset of the right-hand lane
+                        const bool give = act[s] && lane < 31 && nb == off[s] + 1;
                         float* o = c.gb[s] + off[s];
                         float* o1 = c.gb[s] + (off[s] + c.W);
 #pragma unroll
                         for (int ch = 0; ch < C; ++ch) {
-                            g_red(o + ch * c.HW, t0[ch].v[s]); g_red1(o + ch * c.HW, t1[ch].v[s]);
-                            g_red(o1 + ch * c.HW, b0[ch].v[s]); g_red1(o1 + ch * c.HW, b1[ch].v[s]);
+                            float rt = w_up(give ? t1[ch].v[s] : 0.f, lane), rb = w_up(give ? b1[ch].v[s] : 0.f, lane);
+                            if (lane == 0) { rt = 0.f; rb = 0.f; }                     // (shfl.up hands lane 0 its own value back)
+                            if (act[s]) {
+                                g_red(o + ch * c.HW, t0[ch].v[s] + rt);
+                                g_red(o1 + ch * c.HW, b0[ch].v[s] + rb);
+                                if (!give) { g_red1(o + ch * c.HW, t1[ch].v[s]); g_red1(o1 + ch * c.HW, b1[ch].v[s]); }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (act[s]) {   // (ptxas turns predicated atomics into one branch each: one region per source instead)
+                            float* o = c.gb[s] + off[s];
+                            float* o1 = c.gb[s] + (off[s] + c.W);
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) {
+                                g_red(o + ch * c.HW, t0[ch].v[s]); g_red1(o + ch * c.HW, t1[ch].v[s]);
+                                g_red(o1 + ch * c.HW, b0[ch].v[s]); g_red1(o1 + ch * c.HW, b1[ch].v[s]);
+                            }
                         }
                     }
                 }

@@ -169,7 +169,7 @@ class HostViewSynthesisLoss:
 
     x (N,3,C,H,W); disparities (N,1,h_i,w_i) per scale; rvecs / tvecs (N,3) per source; K, invK (3,3)."""
 
-    LANES = 2
+    LANES = 3
 
     def __init__(self, N, C_, H, W, disp_sizes, K, invK, *, device=None, target_id=1, source_ids=(0, 2),
                  scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3,
@@ -178,17 +178,29 @@ class HostViewSynthesisLoss:
         self.ctx = Context.get(dev)
         self.groups, self.S, self.L = int(groups), len(source_ids), len(disp_sizes)
         if not 1 <= lanes <= self.LANES:
-            raise ValueError("lanes must be 1 or 2")
+            raise ValueError(f"lanes must be in 1 .. {self.LANES}")
         pin = lambda *shape: torch.zeros(*shape, dtype=_F32).pin_memory()
+
+        def slab(shapes):
+            """tensors of the given shapes carved out of ONE pinned allocation (64-float alignment): the host entry point
+            recognises the stretch and moves it with a single copy at the large-transfer rate of the link"""
+            sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+            offs, tot = [], 0
+            for n in sizes:
+                offs.append(tot); tot += (n + 63) & ~63
+            buf = torch.zeros(tot, dtype=_F32).pin_memory()
+            return [buf[o:o + n].view(*sh) for o, n, sh in zip(offs, sizes, shapes)], buf
         self._K = _cm(_f32c(K.reshape(3, 3).cpu())).pin_memory()
         self._invK = _cm(_f32c(invK.reshape(3, 3).cpu())).pin_memory()
         self.lane_inputs, self.lane_grads, self._lane_loss, self._descs = [], [], [], []
         for _ in range(lanes):
-            inputs = dict(x=pin(N, 3, C_, H, W), disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes],
-                          rvecs=[pin(N, 3) for _ in source_ids], tvecs=[pin(N, 3) for _ in source_ids],
-                          automask=pin(N, 1, H, W) if automask else None)
-            grads = dict(disparities=[pin(N, 1, h, w) for (w, h) in disp_sizes], rvecs=[pin(N, 3) for _ in source_ids],
-                         tvecs=[pin(N, 3) for _ in source_ids], x=pin(N, 3, C_, H, W) if grad_x else None)
+            big, in_buf = slab([(N, 3, C_, H, W)] + [(N, 1, h, w) for (w, h) in disp_sizes] + ([(N, 1, H, W)] if automask else []))
+            gbig, out_buf = slab([(N, 1, h, w) for (w, h) in disp_sizes])
+            nd = len(disp_sizes)
+            inputs = dict(x=big[0], disparities=big[1:1 + nd], rvecs=[pin(N, 3) for _ in source_ids], tvecs=[pin(N, 3) for _ in source_ids],
+                          automask=big[1 + nd] if automask else None, _slab=in_buf)
+            grads = dict(disparities=gbig, rvecs=[pin(N, 3) for _ in source_ids],
+                         tvecs=[pin(N, 3) for _ in source_ids], x=pin(N, 3, C_, H, W) if grad_x else None, _slab=out_buf)
             loss = pin(1)
             x, gx = inputs["x"], grads["x"]
             desc = L.make_vsl_desc(

@@ -251,7 +251,8 @@ def test_host_entry_point_matches_device_path(groups, automask, grad_x):
 
 
 @pytest.mark.gpu
-def test_host_lanes_pipelined_steps_match_the_oracle():
+@pytest.mark.parametrize("groups", [1, 2])       # 1: the pinned slabs travel as one copy each way; 2: image groups pipelined inside a call
+def test_host_lanes_pipelined_steps_match_the_oracle(groups):
     """double-buffered host entry point: step i+1 is submitted on the other lane before step i is collected; every
     step's host outputs match the float64 oracle (statistical bars; the device path is checked strictly elsewhere) and
     equal the synchronous call bit for bit (all but the atomically accumulated source-image gradient)"""
@@ -260,8 +261,8 @@ def test_host_lanes_pipelined_steps_match_the_oracle():
     dev = torch.device("cuda", 0)
     batches = [O.synthetic_batch(N, Cc, H, W, seed=40 + k) for k in range(4)]
     sizes = [(d.shape[-1], d.shape[-2]) for d in batches[0][1]]
-    hv = M.HostViewSynthesisLoss(N, Cc, H, W, sizes, K, invK, device=dev, groups=2, lanes=2)
-    sync = M.HostViewSynthesisLoss(N, Cc, H, W, sizes, K, invK, device=dev, groups=2)
+    hv = M.HostViewSynthesisLoss(N, Cc, H, W, sizes, K, invK, device=dev, groups=groups, lanes=2)
+    sync = M.HostViewSynthesisLoss(N, Cc, H, W, sizes, K, invK, device=dev, groups=groups)
     results = {}
 
     def collect(k):
