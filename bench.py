@@ -640,7 +640,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=2)
+    ap.add_argument("--e2e-groups", type=int, default=1, help="image groups inside one synchronous host call (1: the pinned slabs travel as one copy each way)")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="steps in flight in the multi-buffered end-to-end measurement (2 or 3)")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the GPU-local CPUs")
     ap.add_argument("--config", type=int, default=2, choices=[1] + sorted(CONFIGS),
