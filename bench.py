@@ -342,7 +342,7 @@ def run_ours(args):
                 ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev) / 8
                 rates[direction] = max(rates[direction], 4 * n / (ms * 1e-3) / 1e9)
                 barrier()
-        return max(h2d_bytes / rates["h2d"], d2h_bytes / rates["d2h"]) / 1e6, rates
+        return max(h2d_bytes / rates["h2d"], d2h_bytes / rates["d2h"]) / 1e6, rates, (h2d_bytes / rates["h2d"] + d2h_bytes / rates["d2h"]) / 1e6
 
     e_steps = min(args.steps, 500)
     # what a training step needs on the host: the loss and the gradients of the network outputs (disparities, poses).
@@ -351,7 +351,7 @@ def run_ours(args):
     e2e_sync, es_ms, es_pct, h2d, d2h = time_host(False, e_steps, lanes=1)
     e2e_value, e_ms, e2e_pct, _, _ = time_host(False, e_steps, lanes=args.e2e_lanes)
     e2e_g1, _, _, h2d_g1, d2h_g1 = time_host(True, max(50, e_steps // 2), lanes=args.e2e_lanes)
-    floor_ms, link = pcie_probe(h2d, d2h)
+    floor_ms, link, floor_shared_ms = pcie_probe(h2d, d2h)
 
     # the same through the autograd mirror of the reference API (torch tensors, many small copies): secondary figure
     pin = lambda t: t.contiguous().pin_memory()
@@ -412,9 +412,11 @@ def run_ours(args):
                        "allocation each and travel as one copy each way) via monodepth2_jl_b200.HostViewSynthesisLoss, every step's loss and gradients collected on the host",
                 "value_synchronous": round(e2e_sync, 1), "ms_per_step_synchronous": round(es_ms / e_steps, 5), "ms_per_call_synchronous_p5_p50_p95": es_pct,
                 "pcie_floor_ms": round(floor_ms, 5), "pcie_floor_frames_per_s": round(NB * world / (floor_ms * 1e-3), 1),
+                "pcie_floor_ms_if_directions_share_the_host_path": round(floor_shared_ms, 5),
                 "host_link_GBps_per_gpu": {k: round(v, 1) for k, v in link.items()},
                 "pcie_floor_note": f"the step's {h2d} B host->device and {d2h} B device->host at the best rate the host link showed in this run "
-                                   f"(pinned copies of 64 MB / 16 MB / the step's size, all {world} rank(s) at once): max of the two directions",
+                                   f"(pinned copies of 64 MB / 16 MB / the step's size, all {world} rank(s) at once, one direction at a time): max of the two directions "
+                                   "(full duplex: what one GPU sees); their sum is the floor when the ranks saturate a shared host path (what eight GPUs see)",
                 "autograd_api_value": round(e2e_autograd, 1), "cpus_bound_to_gpu_numa_node": bound},
         "roofline": {"bound": "hbm", "kernel": f"march2_kernel<C={CH},S=2,AM={int(AM)}> (fused fwd+bwd single-warp marching kernel, all scales in one launch)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
