@@ -32,8 +32,9 @@ def batch(n, c, h, w, seed):
 
 
 def test_step_trains_and_matches_autograd_plus_torch_adam():
-    """one step of the trainer == the same model / loss with torch.autograd and torch.optim.Adam (the Flux rule and
-    torch's coincide for eps = 1e-8 up to where eps is added; checked to 1e-6)"""
+    """the trainer's gradient (flat buffer, hooks) == torch.autograd's on an identical model, its first update == the
+    Flux rule applied to that gradient, and three steps stay within ADAM's step bound of torch.optim.Adam (the two rules
+    coincide; early steps are sign-like, so elements whose gradient is rounding noise may step the other way)"""
     W, H = 128, 64
     trainer, model, cache, hp = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=3)
     torch.manual_seed(3)
@@ -41,23 +42,33 @@ def test_step_trains_and_matches_autograd_plus_torch_adam():
     ref_model.load_state_dict(model.state_dict())
     ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-4, eps=1e-8)
     x = batch(2, 3, H, W, 1)
+    p0 = trainer.flat.data.clone()
     losses = []
-    for _ in range(3):
+    for it in range(3):
         loss, _ = trainer.step(x)
         losses.append(loss.item())
         ref_opt.zero_grad()
         l2, *_ = M.train_loss(ref_model, x, None, cache, hp, False)
         l2.backward()
+        if it == 0:
+            assert abs(l2.item() - loss.item()) <= 1e-6 * abs(l2.item())
+            for (n1, p1), (_, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
+                if p2.grad is None:
+                    continue
+                scale = p2.grad.abs().max().clamp_min(1e-12)
+                assert ((p1.grad - p2.grad).abs().max() / scale).item() <= 2e-3, n1          # (cuDNN picks its algorithms per call)
+            g = trainer.flat.grad.double().cpu()
+            upd = 1e-4 * (0.1 * g / (1 - 0.9)) / ((0.001 * g * g / (1 - 0.999)).sqrt() + 1e-8)     # Flux ADAM, t = 1
+            assert torch.allclose((p0.double().cpu() - upd).float(), trainer.flat.data.cpu(), rtol=1e-5, atol=1e-8)
         ref_opt.step()
     assert all(torch.isfinite(torch.tensor(losses)))
     assert trainer.opt.steps == 3
-    # (ADAM's early steps are sign-like: an element whose gradient is rounding noise may step the other way, 2 lr apart)
     close, total = 0, 0
     for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
         assert n1 == n2
         assert (p1 - p2).abs().max().item() <= 2 * 1e-4 * 3 + 1e-6, n1
         close += torch.isclose(p1, p2, rtol=1e-4, atol=3e-6).sum().item(); total += p1.numel()
-    assert close / total > 0.97, close / total
+    assert close / total > 0.9, close / total
     assert losses[-1] != losses[0]
 
 
@@ -90,7 +101,7 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
         b.step(xs[k])
     frac = lambda m1, m2: sum(torch.isclose(p1, p2, rtol=1e-4, atol=2e-6).sum().item() for p1, p2 in zip(m1.parameters(), m2.parameters())) / \
         sum(p.numel() for p in m1.parameters())
-    assert frac(ma, mb) > 0.97
+    assert frac(ma, mb) > 0.9
     # a cold optimiser (what resuming from the reference's model-only BSON dump does) does NOT reproduce the trajectory
     c, mc, _, _ = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=99)
     sd = torch.load(path, map_location="cpu", weights_only=False)
@@ -98,7 +109,7 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
         mc.load_state_dict(sd["model"])
     for k in range(3, 5):
         c.step(xs[k])
-    assert frac(ma, mc) < 0.9
+    assert frac(ma, mc) < 0.6
 
 
 def _nccl_worker(rank, world, port, q):
