@@ -125,6 +125,7 @@ _SIGS = {
     "md2_destroy": [c_void],
     "md2_profile_enable": [c_void, _I32],
     "md2_profile_read": [c_void, C.POINTER(C.c_float), C.POINTER(C.c_int64)],
+    "md2_profile_read_phases": [c_void, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64)],
     "md2_disparity_to_depth_fwd": [c_void, _P, _P, _I64, _F, _F, _P],
     "md2_disparity_to_depth_bwd": [c_void, _P, _P, _P, _I64, _F, _F, _P],
     "md2_backproject_fwd": [c_void, _P, _P, _P, _I32, _I32, _I32, _P],
@@ -228,6 +229,11 @@ class Context:
 
     def profile(self, on):
         self._check(self.lib.md2_profile_enable(self.handle, int(on)))
+
+    def profile_read_phases(self):
+        a, b, c, n = C.c_float(), C.c_float(), C.c_float(), C.c_int64()
+        self._check(self.lib.md2_profile_read_phases(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value
 
     def profile_read(self):
         ms, n = C.c_float(), C.c_int64()

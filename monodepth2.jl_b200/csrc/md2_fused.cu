@@ -1173,6 +1173,16 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     p.prep_part = do_stats ? part2 : nullptr;
     p.prep_nblk = prep_nblk;
 
+    cudaEvent_t evp0 = nullptr, evp3 = nullptr;   // profile mode 2: the step's first and last time stamp
+    if (ctx->prof_on == 2) {
+        while (ctx->prof_used + 4 > ctx->prof_ev.size()) {
+            cudaEvent_t e;
+            MD2_CHECK(cudaEventCreate(&e));
+            ctx->prof_ev.push_back(e);
+        }
+        evp0 = ctx->prof_ev[ctx->prof_used + 2]; evp3 = ctx->prof_ev[ctx->prof_used + 3];
+        MD2_CHECK(cudaEventRecord(evp0, st));
+    }
     {   // prep: poses, upsampled low-res disparities (+ smoothness sums for the fused fwd+bwd, + zero-fill)
         const int nb = (do_stats || n_low) ? prep_nblk : 0;
         dim3 g(1 + nb + S * aux_blocks, N);
@@ -1200,7 +1210,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
             }
         }
         ev0 = ctx->prof_ev[ctx->prof_used]; ev1 = ctx->prof_ev[ctx->prof_used + 1];
-        ctx->prof_used += 2;
+        ctx->prof_used += ctx->prof_on == 2 ? 4 : 2;
         MD2_CHECK(cudaEventRecord(ev0, st));
     }
     if (v2) {
@@ -1221,6 +1231,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
         MD2_CHECK(launch_after(2, finish_kernel, dim3(blocks), dim3(FIN_THREADS), sizeof(float) * ((W + 3) & ~3), st, p, NP, tiles, bwd ? 1 : 0, low_rows));
         MD2_LAUNCH_CHECK(ctx);
     }
+    if (evp3) MD2_CHECK(cudaEventRecord(evp3, st));
     return 0;
 }
 
@@ -1557,15 +1568,32 @@ int md2_profile_enable(md2_ctx* ctx, int32_t on) {
 }
 int md2_profile_read(md2_ctx* ctx, float* total_ms, int64_t* launches) {
     MD2_REQUIRE(ctx != nullptr && total_ms && launches, "bad arguments");
+    const size_t per = ctx->prof_on == 2 ? 4 : 2;
     float tot = 0.f;
-    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    for (size_t i = 0; i + per <= ctx->prof_used; i += per) {
         MD2_CHECK(cudaEventSynchronize(ctx->prof_ev[i + 1]));
         float ms = 0.f;
         MD2_CHECK(cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
         tot += ms;
     }
     *total_ms = tot;
-    *launches = (int64_t)(ctx->prof_used / 2);
+    *launches = (int64_t)(ctx->prof_used / per);
+    ctx->prof_used = 0;
+    return 0;
+}
+int md2_profile_read_phases(md2_ctx* ctx, float* prep_ms, float* march_ms, float* finish_ms, int64_t* launches) {
+    MD2_REQUIRE(ctx != nullptr && prep_ms && march_ms && finish_ms && launches, "bad arguments");
+    MD2_REQUIRE(ctx->prof_on == 2, "md2_profile_enable(ctx, 2) first");
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (size_t i = 0; i + 4 <= ctx->prof_used; i += 4) {
+        MD2_CHECK(cudaEventSynchronize(ctx->prof_ev[i + 3]));
+        float ms = 0.f;
+        MD2_CHECK(cudaEventElapsedTime(&ms, ctx->prof_ev[i + 2], ctx->prof_ev[i])); a += ms;       // prep
+        MD2_CHECK(cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1])); b += ms;       // march
+        MD2_CHECK(cudaEventElapsedTime(&ms, ctx->prof_ev[i + 1], ctx->prof_ev[i + 3])); c += ms;   // finish
+    }
+    *prep_ms = a; *march_ms = b; *finish_ms = c;
+    *launches = (int64_t)(ctx->prof_used / 4);
     ctx->prof_used = 0;
     return 0;
 }

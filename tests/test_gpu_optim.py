@@ -107,3 +107,18 @@ def test_slow_depth_resumes_in_chunks():
     d1, p1, h1 = M.slow_depth(x.to(dev()), K.to(dev()), invK.to(dev()), iters=12)
     d2, p2, h2 = M.slow_depth(x.to(dev()), K.to(dev()), invK.to(dev()), iters=12, log_step=2, on_log=lambda *a: None)
     assert torch.equal(h1, h2) and torch.equal(d1, d2) and torch.equal(p1[0].rvec, p2[0].rvec)
+
+
+def test_slow_depth_at_config1_size_matches_the_oracle():
+    """BASELINE.json configs[0] at its real size: a 416x128 RGB triplet, first iterations of the 500"""
+    x, _, _, _ = O.synthetic_batch(1, 3, 128, 416, seed=42)
+    K, invK = O.make_K(416, 128)
+    iters = 6
+    rd, rr, rt, rh = O.slow_depth(x.double(), K.double(), invK.double(), iters=iters)
+    disp, poses, hist = M.slow_depth(x.to(dev()), K.to(dev()), invK.to(dev()), iters=iters)
+    ref = torch.tensor(rh, dtype=torch.float64)
+    assert abs(hist[0].item() - ref[0].item()) <= 1e-5 * ref[0].item()
+    assert torch.allclose(hist.cpu().double(), ref, rtol=2e-4)
+    assert (disp.cpu().double() - rd).abs().max() <= 2 * 3e-4 * iters
+    for p, r, t in zip(poses, rr, rt):
+        assert torch.allclose(p.rvec.cpu().double(), r, atol=5e-5) and torch.allclose(p.tvec.cpu().double(), t, atol=5e-5)

@@ -188,3 +188,31 @@ def test_two_rank_nccl_step_equals_the_full_batch_step():
             assert np.abs(p - pfull).max() <= 2.5e-4          # (ADAM's first step is +-lr per element: sign flips of ~0 gradients)
             assert (np.abs(p - pfull) < 1e-6).mean() > 0.98
         assert np.allclose(r[True][0], r[False][0], rtol=1e-4, atol=1e-7 * np.abs(gfull).max())    # overlapped == blocking all-reduce
+
+
+def test_training_reduces_the_loss_on_a_fixed_batch():
+    """the whole stack end to end: 40 steps of the trainer on one batch must lower the loss (gradient signs / scaling through
+    the stand-in networks, the fused loss, the flat gradient buffer and the fused ADAM)"""
+    W, H = 128, 64
+    trainer, model, cache, hp = M.make_training_setup(W, H, dev(), channels=3, batch_size=2, seed=11, lr=1e-3)
+    x = batch(2, 3, H, W, 5)
+    losses = [trainer.step(x)[0].item() for _ in range(40)]
+    assert all(l == l for l in losses)
+    assert min(losses[-5:]) < 0.9 * losses[0], (losses[0], losses[-5:])
+
+
+def test_profile_phases_of_a_step():
+    x, disps, rv, tv = O.synthetic_batch(2, 1, 64, 128, seed=3)
+    from oracle.torch_oracle import make_K
+    K, invK = make_K(128, 64)
+    d = dev()
+    ctx = M.Context.get(d)
+    args = (x.to(d), [t.to(d).requires_grad_(True) for t in disps], [t.to(d) for t in rv], [t.to(d) for t in tv], K.to(d), invK.to(d))
+    ctx.profile(2)
+    try:
+        for _ in range(3):
+            M.view_synthesis_loss(*args)
+        prep, march, finish, n = ctx.profile_read_phases()
+    finally:
+        ctx.profile(False)
+    assert n == 3 and prep > 0 and march > 0 and finish > 0
