@@ -620,9 +620,16 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 constexpr int FIN_MAXROWS = 64;   // contributing full-resolution rows handled per pass of phase A
-constexpr int FIN_THREADS = 128;  // small blocks: the whole grid is resident at once (one latency chain, no waves)
+constexpr int FIN_THREADS = 128;
+#ifndef MD2_FIN_MINB
+#define MD2_FIN_MINB 7
+#endif
+#ifndef MD2_FIN_UNROLL
+#define MD2_FIN_UNROLL 16
+#endif
+constexpr int FIN_UNROLL = MD2_FIN_UNROLL;  // small blocks: the whole grid is resident at once (one latency chain, no waves)
 
-__global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd, int low_rows) {
+__global__ void __launch_bounds__(FIN_THREADS, MD2_FIN_MINB) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd, int low_rows) {
     extern __shared__ __align__(16) float vrow[];   // [W rounded up to 4] (adjoint blocks)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_wait();
@@ -750,7 +757,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 8) finish_kernel(const __grid_con
             for (int x = 4 * threadIdx.x; x < W; x += 4 * FIN_THREADS) {
                 float4 acc = base ? *reinterpret_cast<const float4*>(vrow + x) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* gp = g + (long long)(ylo + base) * W + x;
-#pragma unroll 8
+#pragma unroll FIN_UNROLL
                 for (int k = 0; k < cnt; ++k) {
                     const float4 q = __ldcg(reinterpret_cast<const float4*>(gp + (long long)k * W));
                     const float wk = wys[k];
