@@ -247,6 +247,27 @@ def run_ours(args):
     frames = NB * world * args.steps
     value = frames / (ms * 1e-3)
 
+    # ---- the same call warm (one input set back to back: L2-resident) and forward-only (cold ring), SURVEY 8(d) ----
+    def timed(fn, n):
+        for i in range(5):
+            fn(i)
+        barrier()
+        e0.record(stream)
+        for i in range(n):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        return D.max_over_ranks(e0.elapsed_time(e1), device=dev) / n
+    fwd_only = lib.md2_view_synthesis_loss_fwd
+
+    def step_fwd(i):
+        if fwd_only(handle, C.byref(descs[i % n_sets]), sptr):
+            raise RuntimeError(lib.md2_last_error().decode())
+    n_var = min(args.steps, 500)
+    variants = {"fwdbwd_warm_l2_ms": round(timed(lambda i: step(0), n_var), 5), "fwd_only_cold_ms": round(timed(step_fwd, n_var), 5),
+                "fwd_only_warm_l2_ms": round(timed(lambda i: step_fwd(0), n_var), 5),
+                "note": "same workload; warm = one input set back to back (L2-resident), cold = the ring; fwd_only = md2_view_synthesis_loss_fwd (loss value only)"}
+
     # ---- roofline of the dominant kernel: second pass with per-launch CUDA events ----
     ctx.profile(True)
     for i in range(args.steps):
@@ -406,6 +427,7 @@ def run_ours(args):
                    "l2_policy": f"inputs larger than L2: ring of {n_sets} input/gradient sets ({n_sets * set_bytes / 1e6:.0f} MB) rotated per step",
                    "api": "md2_view_synthesis_loss_fwdbwd (C ABI), one call per step", "sharding": "batch, no data-path collective"},
         "images_per_s": round(3 * value, 1),
+        "variants": variants,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -571,11 +571,11 @@ march_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int 
 // the single-warp marching kernel (md2_march2.cuh): value + gradient.  Persistent one-warp blocks, as many as are
 // resident on the whole GPU; block b walks the work items b, b + grid, ... (same items / partial-sum rows as above)
 // ------------------------------------------------------------------------------------------
-template <int C, int S, bool AM, bool DBG>
-__global__ void __maxnreg__((March2<C, S, AM, DBG>::MAXREG))
+template <int C, int S, bool AM, bool DBG, bool GRAD>
+__global__ void __maxnreg__((March2<C, S, AM, DBG, GRAD>::MAXREG))
 march2_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int q_full, int lgroups) {
     extern __shared__ __align__(16) float wsm[];
-    using M = March2<C, S, AM, DBG>;
+    using M = March2<C, S, AM, DBG, GRAD>;
     constexpr int NP = M::NPART;
     const int lane = threadIdx.x;
     pdl_trigger();
@@ -593,7 +593,8 @@ march2_kernel(const __grid_constant__ FusedParams p, int strips, int chunks, int
             float v[32];
             M::run(p, sx, cy, z, lane, wsm, v);
             const float tot = warp_reduce_32(v);
-            if (lane == 0 || (lane >= NSTAT && lane < NP))
+            // value + gradient: the loss sum and the pose sums (the smoothness sums come from the prep kernel); forward-only: the four statistics
+            if (GRAD ? (lane == 0 || (lane >= NSTAT && lane < NP)) : lane < NSTAT)
                 p.partial[((long long)z * ipg + cy * strips + sx) * NP + lane] = tot;
         }
     }
@@ -822,38 +823,45 @@ static int launch_march(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <int C, int S, bool AM, bool DBG = false>
+template <int C, int S, bool AM, bool DBG = false, bool GRAD = true>
 static int march2_resident() {
-    using M = March2<C, S, AM, DBG>;
+    using M = March2<C, S, AM, DBG, GRAD>;
     static int resident = 0;
     if (!resident) {
         const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
         int occ = 0;
-        if (cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
-        cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2_kernel<C, S, AM, DBG>, M::THREADS, smem) != cudaSuccess) occ = 0;
+        if (cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
+        cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG, GRAD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2_kernel<C, S, AM, DBG, GRAD>, M::THREADS, smem) != cudaSuccess) occ = 0;
         resident = occ > 0 ? occ : 8;
         if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] march2_kernel<%d,%d>: %d resident warps/SM, %zu B smem/warp\n", C, S, resident, smem);
     }
     return resident;
 }
 
-template <int C, int S, bool AM, bool DBG = false>
+template <int C, int S, bool AM, bool DBG = false, bool GRAD = true>
 static int launch_march2(md2_ctx* ctx, const FusedParams& p, cudaStream_t st) {
-    using M = March2<C, S, AM, DBG>;
+    using M = March2<C, S, AM, DBG, GRAD>;
     const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
     const int strips = cdiv(p.W, M::OW), chunks = cdiv(p.H, p.m_R), q_full = p.H / p.m_R;
     const int lgroups = p.m_group > 0 ? (p.m_group < strips ? p.m_group : strips) : 1;
     const long long items = ((long long)strips * q_full + (chunks > q_full ? lgroups : 0)) * p.L * p.N;
-    const long long cap = (long long)ctx->sm_count * march2_resident<C, S, AM, DBG>();
+    const long long cap = (long long)ctx->sm_count * march2_resident<C, S, AM, DBG, GRAD>();
     const int blocks = (int)(items < cap ? items : cap);
-    MD2_CHECK(launch_after(1, march2_kernel<C, S, AM, DBG>, dim3(blocks), dim3(M::THREADS), smem, st, p, strips, chunks, q_full, lgroups));
+    MD2_CHECK(launch_after(1, march2_kernel<C, S, AM, DBG, GRAD>, dim3(blocks), dim3(M::THREADS), smem, st, p, strips, chunks, q_full, lgroups));
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
 
-static int dispatch_march2(md2_ctx* ctx, int C, int S, const FusedParams& p, cudaStream_t st) {
+static int dispatch_march2(md2_ctx* ctx, int C, int S, const FusedParams& p, cudaStream_t st, bool grad = true) {
     const bool am = p.automask != nullptr;
+    if (!grad) {   // forward-only instantiations
+        if (C == 1 && S == 1) return am ? launch_march2<1, 1, true, false, false>(ctx, p, st) : launch_march2<1, 1, false, false, false>(ctx, p, st);
+        if (C == 1 && S == 2) return am ? launch_march2<1, 2, true, false, false>(ctx, p, st) : launch_march2<1, 2, false, false, false>(ctx, p, st);
+        if (C == 3 && S == 1) return am ? launch_march2<3, 1, true, false, false>(ctx, p, st) : launch_march2<3, 1, false, false, false>(ctx, p, st);
+        if (C == 3 && S == 2) return am ? launch_march2<3, 2, true, false, false>(ctx, p, st) : launch_march2<3, 2, false, false, false>(ctx, p, st);
+        return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
+    }
     if (p.dbg) {   // test hook (md2.h: debug_choices): the instantiations that also export the decisions
         if (S != 2) return set_error("view_synthesis_loss: debug_choices needs S = 2");
         if (C == 1) return am ? launch_march2<1, 2, true, true>(ctx, p, st) : launch_march2<1, 2, false, true>(ctx, p, st);
@@ -866,7 +874,15 @@ static int dispatch_march2(md2_ctx* ctx, int C, int S, const FusedParams& p, cud
     return set_error("view_synthesis_loss: unsupported C=%d S=%d (C in {1,3}, S in {1,2})", C, S);
 }
 
-static int march2_resident_of(int C, int S, bool am) {
+static int march2_resident_of(int C, int S, bool am, bool grad = true) {
+    if (!grad) {
+        if (am) {
+            if (C == 1) return S == 1 ? march2_resident<1, 1, true, false, false>() : march2_resident<1, 2, true, false, false>();
+            return S == 1 ? march2_resident<3, 1, true, false, false>() : march2_resident<3, 2, true, false, false>();
+        }
+        if (C == 1) return S == 1 ? march2_resident<1, 1, false, false, false>() : march2_resident<1, 2, false, false, false>();
+        return S == 1 ? march2_resident<3, 1, false, false, false>() : march2_resident<3, 2, false, false, false>();
+    }
     if (am) {
         if (C == 1) return S == 1 ? march2_resident<1, 1, true>() : march2_resident<1, 2, true>();
         return S == 1 ? march2_resident<3, 1, true>() : march2_resident<3, 2, true>();
@@ -1153,11 +1169,11 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     p.mode = mode;
     fill_pose_io(d, p.pose);
 
-    const bool v2 = bwd && !use_march_v1();
-    p.m_R = choose_march_rows(W, H, L * N, bwd, ctx->sm_count, v2 ? march2_resident_of(C, S, d->automask != nullptr) : march_resident_of(C, S, bwd), p.m_group);
+    const bool v2 = !use_march_v1();   // the single-warp kernels (md2_march2.cuh) serve every mode; MD2_MARCH_V1=1: the round-1 warp-pair kernels
+    p.m_R = choose_march_rows(W, H, L * N, v2 || bwd, ctx->sm_count, v2 ? march2_resident_of(C, S, d->automask != nullptr, bwd) : march_resident_of(C, S, bwd), p.m_group);
     static const bool dbg_env = getenv("MD2_DEBUG") != nullptr, generic_env = getenv("MD2_PREP_GENERIC") != nullptr;
     if (dbg_env) fprintf(stderr, "[md2] chunk height %d, %d groups of short last chunks per (scale, image)\n", p.m_R, p.m_group);
-    const int tiles = cdiv(W, bwd ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
+    const int tiles = cdiv(W, (v2 || bwd) ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)
     const int NP = NSTAT + 12 * S;
     p.pose_slot = 0;
     // prep kernel partition: 31-column x 4-row patches, one warp each, eight warps per block
@@ -1194,7 +1210,8 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
         const int nb = (do_stats || n_low) ? prep_nblk : 0;
         dim3 g(1 + nb + S * aux_blocks, N);
         // usual decoder layout (low-res scales first, one full-resolution scale last, fused fwd+bwd): the lean kernel
-        bool usual = do_stats && nb > 0 && L >= 1 && L <= 4 && n_low == L - 1 && d->disp_w[L - 1] == W && d->disp_h[L - 1] == H;
+        // (the lean kernel always forms the smoothness sums; calls that do not want them -- forward-only, separate backward -- ignore its partials)
+        bool usual = nb > 0 && L >= 1 && L <= 4 && n_low == L - 1 && d->disp_w[L - 1] == W && d->disp_h[L - 1] == H;
         if (generic_env) usual = false;
 #define MD2_PREPF(CC, NL) prep_fast_kernel<CC, NL><<<g, 32 * PREP_WARPS, 0, st>>>(p, prep_strips, prep_chunks, nb, pose_ab, part2, zero_blocks)
 #define MD2_PREP(CC, LL) prep_kernel<CC, LL><<<g, 32 * PREP_WARPS, 0, st>>>(p, prep_strips, prep_chunks, nb, do_stats, pose_ab, part2, zero_blocks)
@@ -1223,12 +1240,9 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     if (v2) {
         // the optional visualisation outputs of train_loss (src/training.jl:34-37,71-74; every 50th step of the reference's
         // loop) are written by the forward-only kernel; the value + gradient kernel does not carry them
-        if (d->viz_loss || d->viz_warped[0] || (S > 1 && d->viz_warped[S - 1])) {
-            FusedParams pf = p;
-            pf.m_R = choose_march_rows(W, H, L * N, false, ctx->sm_count, march_resident_of(C, S, false), pf.m_group);
-            if (dispatch_march<false>(ctx, C, S, pf, st)) return 1;
-        }
-        if (dispatch_march2(ctx, C, S, p, st)) return 1;
+        const bool viz = d->viz_loss || d->viz_warped[0] || (S > 1 && d->viz_warped[S - 1]);
+        if (!bwd || viz) { if (dispatch_march2(ctx, C, S, p, st, false)) return 1; }
+        if (bwd) { if (dispatch_march2(ctx, C, S, p, st, true)) return 1; }
     }
     else if (bwd) { if (dispatch_march<true>(ctx, C, S, p, st)) return 1; }
     else     { if (dispatch_march<false>(ctx, C, S, p, st)) return 1; }

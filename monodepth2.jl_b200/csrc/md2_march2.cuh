@@ -136,7 +136,9 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 
 // AM: the call has an automask map (src/training.jl:60-62); DBG: test hook, also exports the discrete decisions of every
 // pixel (FusedParams::dbg, md2.h: debug_choices) -- a separate instantiation, the production kernels carry none of it
-template <int C, int S, bool AM, bool DBG = false>
+// GRAD = false: the forward-only call (md2_view_synthesis_loss_fwd, and the writer of the visualisation outputs): stages C, A and
+// W alone -- no pixel packets, no adjoint stages; the loss, smoothness and mean-disparity sums of every item instead
+template <int C, int S, bool AM, bool DBG = false, bool GRAD = true>
 struct March2 {
     using V = SV<S>;
     static constexpr int HALO = 2;
@@ -159,13 +161,13 @@ struct March2 {
     static constexpr int NH4 = (NHF + 3) / 4;
     static constexpr int NSLOT = 4;                      // pixel packets of rows i-2 .. i+1 are in flight
     static constexpr int NHIST = 2;                      // window sums of rows i-2, i-1 (row i takes the slot of row i-2 once that has been read)
-    static constexpr int HIST0 = NSLOT * NP4 * 32;       // Vec4 index of the history region
-    static constexpr int TOTAL4 = NSLOT * NP4 + NHIST * NH4;   // Vec4 per lane
+    static constexpr int HIST0 = GRAD ? NSLOT * NP4 * 32 : 0;  // Vec4 index of the history region (forward-only: no pixel packets)
+    static constexpr int TOTAL4 = (GRAD ? NSLOT * NP4 : 0) + NHIST * NH4;   // Vec4 per lane
     static constexpr int SMEM_FLOATS = TOTAL4 * 32 * 4;
     static constexpr int THREADS = 32;
     // (registers are allocated per scheduler: <= 128 -> 4 warps, <= 168 -> 3, <= 255 -> 2.  C = 3 with two sources does not fit 168
     // without spilling, so it takes the whole 2-warp budget; C = 3 with one source fits 168)
-    static constexpr int MAXREG = C == 1 ? MD2_M2_MAXREG_C1 : (S == 1 ? 168 : MD2_M2_MAXREG_C3);
+    static constexpr int MAXREG = !GRAD ? (C == 1 ? 96 : 168) : (C == 1 ? MD2_M2_MAXREG_C1 : (S == 1 ? 168 : MD2_M2_MAXREG_C3));
     static_assert(P_U + S <= NE4 * 4 && P_V + S <= NE4 * 4 && P_OFF + S <= NE4 * 4, "u, v, off must fit the early words");
 
     // image row read for march row i (reflect-pad(1) above and below the image, clamped beyond)
@@ -200,6 +202,9 @@ struct March2 {
         float sA, sB, nega; // smoothness gradient A ghat - B (appendix A.6), -depth_a
         ring_ref rr;        // this lane's Vec4 column of the warp's ring
         int* dbg;           // DBG: decisions of this (scale, image) + this lane's column
+        int do_viz;         // forward-only: this item writes the visualisation outputs (last scale, src/training.jl:71-74)
+        float* vz_loss;     // ... warp-loss map of this image + this lane's column
+        float* vz_warp[S];  // ... warped sources
     };
 
     struct Carry {          // loop-carried state
@@ -216,6 +221,7 @@ struct March2 {
         V B[3 * C], Cq[3 * C];   // vertical adjoint accumulators of pixel rows i-1 and i
         V P0[3], P1[3], Ph[3];   // pose accumulators
         float warp_sum;
+        float ssx, ssy, dsum;    // forward-only: smoothness / mean-disparity sums (src/utils.jl:159-173, src/training.jl:64)
     };
 
     static MD2_DEV int slot_vec(int row) { return (row & (NSLOT - 1)) * (NP4 * 32); }           // Vec4 index of the first word of a row's pixel packet
@@ -290,7 +296,7 @@ struct March2 {
                                                             (k.qb.v[s] != 0.0f || (q.v[s] == 0.0f && dv.v[s] > ylo && dv.v[s] < yhi) ? (1 << 30) : 0);
             }
         }
-        if (NE4 > 0) {   // early words of the pixel packet (the rest is carried in registers until stage C stores it)
+        if (GRAD && NE4 > 0) {   // early words of the pixel packet (the rest is carried in registers until stage C stores it)
             float pk[NE4 > 0 ? NE4 * 4 : 4];
 #pragma unroll
             for (int j = 0; j < NE4 * 4; ++j) pk[j] = 0.f;
@@ -357,10 +363,12 @@ struct March2 {
             for (int s = 0; s < S; ++s) { pk[P_FX + s] = k.fx.v[s]; pk[P_FY + s] = k.fy.v[s]; }
             pk[P_Z] = k.zc;
             const int base = slot_vec(it);
+            if (GRAD) {
 #pragma unroll
-            for (int w4 = NE4; w4 < NP4; ++w4) {   // (the early words were written by A one iteration ago)
-                Vec4 q4; q4.x = pk[4 * w4]; q4.y = pk[4 * w4 + 1]; q4.z = pk[4 * w4 + 2]; q4.w = pk[4 * w4 + 3];
-                s_st4(c.rr, base + w4 * 32, q4);
+                for (int w4 = NE4; w4 < NP4; ++w4) {   // (the early words were written by A one iteration ago)
+                    Vec4 q4; q4.x = pk[4 * w4]; q4.y = pk[4 * w4 + 1]; q4.z = pk[4 * w4 + 2]; q4.w = pk[4 * w4 + 3];
+                    s_st4(c.rr, base + w4 * 32, q4);
+                }
             }
         }
         // horizontal 3-sums (window column centred on this lane)
@@ -393,7 +401,7 @@ struct March2 {
         }
         // pixel packet of row i-2 (for P)
         float pk[NP4 * 4];
-        {
+        if (GRAD) {
             const int base = slot_vec(it - 2);
 #pragma unroll
             for (int w4 = 0; w4 < NP4; ++w4) {
@@ -466,6 +474,7 @@ struct March2 {
                     dbgw |= (df.v[s] > 0.f ? 1 : (df.v[s] < 0.f ? 2 : 0)) << (8 + 2 * (s * C + ch));
                 }
             }
+            if (!GRAD) continue;
             // dS/dx_j = alpha + beta x'_j + gamma y'_j for CENTRED member values x' = x - rc; all three carry a factor 1/2
             const V rDn = sv_mul(inv, Cc), rC = sv_mul(inv, Dn);
             V beta = sv_mul(sv_mul(Sv, sv_bc<S>(9.0f)), rDn);
@@ -492,6 +501,34 @@ struct March2 {
             if (am_q <= wlv) { wlv = am_q; sel = -1; }
         }
         k.warp_sum += row_own ? wlv * c.mp : 0.f;
+        if (!GRAD) {
+            // ---- forward-only: visualisation outputs of the last scale, smoothness / mean-disparity sums of pixel row q ----
+            const bool own = row_own && c.mp != 0.f;
+            if (c.do_viz) {   // (warp-uniform: a property of the item)
+                if (c.vz_loss) g_st_if(c.vz_loss + q * c.W, wlv, own);
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (c.vz_warp[s]) {
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) g_st_if(c.vz_warp[s] + (ch * c.HW + q * c.W), k.xmp[ch].v[s] + c.rc[ch], own);
+                    }
+            }
+            const float Dr = w_dn(k.Dp, lane);
+            float gxs = 0.f, gys = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                gxs += fabsf(k.ymp[ch] - w_dn(k.ymp[ch], lane));
+                gys += fabsf(k.ymp[ch] - curT[ch]);
+            }
+            const float wx = f_ex2(gxs * (-1.4426950408889634f / C)), wy = f_ex2(gys * (-1.4426950408889634f / C));
+            k.ssx += (own && c.cxr != 0.f) ? fabsf(k.Dp - Dr) * wx : 0.f;                       // (cxr != 0: the pixel has a right neighbour)
+            k.ssy += (own && (unsigned)q < (unsigned)(c.H - 1)) ? fabsf(k.Dp - curD) * wy : 0.f;
+            k.dsum += own ? k.Dp : 0.f;
+            k.Dp = curD;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) { k.xmp[ch] = X[ch]; k.ymp[ch] = curT[ch]; }
+            return;
+        }
         // coefficients of the selected source, scaled by the upstream cotangent of this window
         float wp[3 * C];
         {
@@ -745,7 +782,7 @@ struct March2 {
         {
             const float up_s = p.gloss * p.loss_scale * p.smooth_w[scale];
             c.sA = up_s; c.sB = 0.f;
-            if (p.normalize_disp) {
+            if (GRAD && p.normalize_disp) {
                 float ssx, ssy, dsum;
                 prep_stats(p, scale, n, lane, ssx, ssy, dsum);
                 const float m = dsum / (float)c.HW + 1e-7f;
@@ -755,6 +792,18 @@ struct March2 {
         }
         c.rr = ring_ref_of(wsm, lane);
         c.dbg = DBG ? p.dbg + ((long long)(scale * p.N + n) * c.HW + gxm) * (1 + S) : nullptr;
+        c.do_viz = 0; c.vz_loss = nullptr;
+#pragma unroll
+        for (int s = 0; s < S; ++s) c.vz_warp[s] = nullptr;
+        if (!GRAD && scale == p.L - 1) {
+            c.vz_loss = p.viz_loss ? p.viz_loss + (long long)n * c.HW + gxm : nullptr;
+            c.do_viz = c.vz_loss != nullptr;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                c.vz_warp[s] = p.viz_warped[s] ? p.viz_warped[s] + (long long)n * C * c.HW + gxm : nullptr;
+                if (c.vz_warp[s]) c.do_viz = 1;
+            }
+        }
         // pin the per-lane invariants in registers (otherwise they are re-derived from launch parameters / special
         // registers inside the row loop, with a scoreboard wait each)
         keep(c.lane); keep(c.W); keep(c.H); keep(c.rr); keep(c.mp); keep(c.kq); keep(c.da); keep(c.db);
@@ -777,7 +826,8 @@ struct March2 {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) { k.xmp[ch] = sv_bc<S>(0.f); k.ymp[ch] = 0.f; }
         k.Dp = 0.f; k.selp = -1; k.ghp = 0.f; k.ey_prev = 0.f; k.warp_sum = 0.f; k.zc = 0.f; k.amn = 0.f;
-        const int i0 = c.Y0 - HALO, iend = c.Y1 + HALO;
+        k.ssx = 0.f; k.ssy = 0.f; k.dsum = 0.f;
+        const int i0 = c.Y0 - (GRAD ? HALO : 1), iend = c.Y1 + (GRAD ? HALO : 1);   // (forward-only: windows reach one row out)
         {   // prime the pipeline: raw loads of row i0, then A(i0)
             k.gy = image_row(i0, c.H);
             const int toff = k.gy * c.W;
@@ -794,6 +844,7 @@ struct March2 {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
         v[0] = k.warp_sum;
+        if (!GRAD) { v[1] = k.ssx; v[2] = k.ssy; v[3] = k.dsum; return; }
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll

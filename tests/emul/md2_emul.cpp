@@ -63,9 +63,9 @@ static void run_march(const FusedParams& p, std::vector<double>& sums) {
 }
 
 // single-warp marching kernel (md2_march2.cuh): one warp of lockstep fibers walks all work items of a (scale, image)
-template <int C, int S, bool AM, bool DBG = false>
+template <int C, int S, bool AM, bool DBG = false, bool GRAD = true>
 static void run_march2(const FusedParams& p, std::vector<double>& sums) {
-    using M = March2<C, S, AM, DBG>;
+    using M = March2<C, S, AM, DBG, GRAD>;
     const int NP = M::NPART;
     const int strips = (p.W + M::OW - 1) / M::OW, chunks = (p.H + p.m_R - 1) / p.m_R;
     sums.assign((size_t)p.L * p.N * NP, 0.0);
@@ -103,6 +103,14 @@ static int dispatch(int C, int S, const FusedParams& p, std::vector<double>& sum
         if (C == 1 && S == 2) { run_march<1, 2, BWD>(p, sums); return 0; }
         if (C == 3 && S == 1) { run_march<3, 1, BWD>(p, sums); return 0; }
         if (C == 3 && S == 2) { run_march<3, 2, BWD>(p, sums); return 0; }
+        return 1;
+    }
+    if (variant == 2 && !BWD) {   // forward-only instantiations of the single-warp kernel
+        const bool am = p.automask != nullptr;
+        if (C == 1 && S == 1) { if (am) run_march2<1, 1, true, false, false>(p, sums); else run_march2<1, 1, false, false, false>(p, sums); return 0; }
+        if (C == 1 && S == 2) { if (am) run_march2<1, 2, true, false, false>(p, sums); else run_march2<1, 2, false, false, false>(p, sums); return 0; }
+        if (C == 3 && S == 1) { if (am) run_march2<3, 1, true, false, false>(p, sums); else run_march2<3, 1, false, false, false>(p, sums); return 0; }
+        if (C == 3 && S == 2) { if (am) run_march2<3, 2, true, false, false>(p, sums); else run_march2<3, 2, false, false, false>(p, sums); return 0; }
         return 1;
     }
     if (variant == 2 && BWD) {
@@ -195,7 +203,7 @@ static int emul_vsl(const md2_vsl_desc* d, int mode, float gloss, int variant, i
     if (bwd && variant == 2 && (p.viz_loss || p.viz_warped[0] || p.viz_warped[1])) {
         // as run_vsl on the device: the visualisation outputs come from the forward-only kernel
         std::vector<double> tmp;
-        if (dispatch<false>(C, S, p, tmp, 1)) return 1;
+        if (dispatch<false>(C, S, p, tmp, 2)) return 1;
     }
     if (bwd ? dispatch<true>(C, S, p, sums, variant) : dispatch<false>(C, S, p, sums, variant)) return 1;
     if (bwd)   // adjoint of the upsample for the low-res scales (down_adjoint_kernel on the device)

@@ -64,9 +64,9 @@ def emul_vsl(x, disps, rvecs, tvecs, K, invK, *, mode=2, gloss=1.0, target_id=1,
         grad_source=[out["gx"][:, i] for i in source_ids] if grad_source else None,
         viz_warped=out.get("viz_warped"), viz_loss=out.get("viz_loss"), saved=out["saved"], debug_choices=out.get("choices"),
         shape=(N, Cc, H, W))
-    if variant == "march2" and mode != 0:
+    if variant == "march2":
         rc = lib.md2_emul_march2(C.byref(desc), mode, gloss, R)
-    elif variant in ("march", "march2"):
+    elif variant == "march":
         rc = lib.md2_emul_march(C.byref(desc), mode, gloss, R)
     else:
         rc = lib.md2_emul_vsl(C.byref(desc), mode, gloss)
