@@ -175,6 +175,11 @@ typedef struct md2_vsl_desc {
      *   word 1+s: x0 | y0 << 14 | mask_x << 29 | mask_y << 30 of source s (0-based gather cell, clip-gradient masks)
      * A parity test evaluates the float64 oracle with exactly these decisions forced (tests/test_gpu_forced.py). */
     int32_t* debug_choices;
+    /* != 0 and automask == NULL: the call forms the automask map itself from the un-warped source frames
+     * (automasking_loss(ssim, x, target; source_ids), src/Monodepth.jl:159-164 / src/training.jl:9-11) as part of its launch
+     * sequence -- the reference's separate pre-pass folded into the call.  The map is a constant of the loss, as in the
+     * reference (it is computed outside `gradient`). */
+    int32_t compute_automask;
 } md2_vsl_desc;
 
 int md2_view_synthesis_loss_fwd(md2_ctx*, const md2_vsl_desc*, md2_stream);

@@ -40,6 +40,7 @@ class VslDesc(C.Structure):
         ("saved", c_void),
         ("zero_grad_source", C.c_int32),
         ("debug_choices", c_void),
+        ("compute_automask", C.c_int32),
     ]
 
 
@@ -65,7 +66,8 @@ def frame_view(x, idx):
 def make_vsl_desc(*, target, target_stride, sources, source_strides, disparities, K_cm, invK_cm, rot, trans,
                   pose_mode, invert, automask=None, min_depth=0.1, max_depth=100.0, smooth_weight, loss_scale,
                   normalize_disparity=True, loss=None, grad_disparity=None, grad_rot=None, grad_trans=None,
-                  grad_source=None, viz_warped=None, viz_loss=None, saved=None, zero_grad_source=False, debug_choices=None, shape):
+                  grad_source=None, viz_warped=None, viz_loss=None, saved=None, zero_grad_source=False, debug_choices=None,
+                  compute_automask=False, shape):
     """shape = (N, C, H, W).  `target`/`sources` are tensors whose data_ptr() is element
     (n=0,c=0,y=0,x=0) of an (N,C,H,W) view with per-image stride *_stride and dense C,H,W."""
     N, Cc, H, W = shape
@@ -110,6 +112,7 @@ def make_vsl_desc(*, target, target_stride, sources, source_strides, disparities
     d.viz_loss = _ptr(viz_loss)
     d.saved = _ptr(saved)
     d.zero_grad_source = int(bool(zero_grad_source))
+    d.compute_automask = int(bool(compute_automask))
     if debug_choices is not None:
         if debug_choices.dtype != torch.int32 or not debug_choices.is_contiguous():
             raise TypeError("debug_choices: expected a contiguous int32 tensor")

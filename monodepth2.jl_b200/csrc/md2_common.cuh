@@ -22,7 +22,7 @@ struct Workspace {
 }  // namespace md2
 
 enum { MD2_WS_PARTIAL = 0, MD2_WS_SUMS, MD2_WS_POSE, MD2_WS_STATS, MD2_WS_DISP, MD2_WS_GDISP,
-       MD2_WS_MISC, MD2_WS_COUNT };
+       MD2_WS_MISC, MD2_WS_AUTOMASK, MD2_WS_COUNT };
 // workspace banks: calls that may be in flight at the same time must not share scratch.  Bank 0 serves the
 // device-pointer entry points (one stream at a time, md2.h), banks 1.. the lanes of the host-buffer entry point.
 enum { MD2_WS_BANKS = 1 + MD2_HOST_LANES };
@@ -49,6 +49,9 @@ namespace md2 {
 
 // returns nullptr (and sets the error) on failure
 void* ws_get(md2_ctx* ctx, int slot, size_t bytes);
+// md2_ops.cu: out (N,1,H,W) = min over the S frames of photometric_loss(frame_s, target) (automasking_loss on frame views)
+int launch_automask(md2_ctx* ctx, int S, const float* const* frames, const int64_t* frame_ns, const float* target, int64_t target_ns,
+                    float* out, int W, int H, int C, int N, cudaStream_t st);
 
 // the C entry points make the ctx's device current for the duration of the call and restore the caller's device
 struct DeviceGuard {

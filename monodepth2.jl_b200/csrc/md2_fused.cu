@@ -1130,6 +1130,15 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     }
     p.viz_loss = d->viz_loss;
     p.automask = d->automask;
+    if (!d->automask && d->compute_automask) {
+        // the automask pre-pass of the training loop (src/Monodepth.jl:159-164) as the first launch of this call
+        float* am = (float*)ws_get(ctx, MD2_WS_AUTOMASK, sizeof(float) * (size_t)N * W * H);
+        if (!am) return 1;
+        int64_t ns[MAX_S];
+        for (int s = 0; s < S; ++s) ns[s] = d->source_image_stride[s];
+        if (launch_automask(ctx, S, d->source, ns, d->target, d->target_image_stride, am, W, H, C, N, st)) return 1;
+        p.automask = am;
+    }
     p.dbg = (bwd && !use_march_v1()) ? d->debug_choices : nullptr;
     if (d->debug_choices) MD2_REQUIRE(p.dbg != nullptr, "debug_choices is served by the value + gradient calls only");
     {   // the reference rounds min_disp and max_disp to T first (src/utils.jl:176-178)
@@ -1170,7 +1179,7 @@ int run_vsl(md2_ctx* ctx, const md2_vsl_desc* d, int mode, float gloss, cudaStre
     fill_pose_io(d, p.pose);
 
     const bool v2 = !use_march_v1();   // the single-warp kernels (md2_march2.cuh) serve every mode; MD2_MARCH_V1=1: the round-1 warp-pair kernels
-    p.m_R = choose_march_rows(W, H, L * N, v2 || bwd, ctx->sm_count, v2 ? march2_resident_of(C, S, d->automask != nullptr, bwd) : march_resident_of(C, S, bwd), p.m_group);
+    p.m_R = choose_march_rows(W, H, L * N, v2 || bwd, ctx->sm_count, v2 ? march2_resident_of(C, S, p.automask != nullptr, bwd) : march_resident_of(C, S, bwd), p.m_group);
     static const bool dbg_env = getenv("MD2_DEBUG") != nullptr, generic_env = getenv("MD2_PREP_GENERIC") != nullptr;
     if (dbg_env) fprintf(stderr, "[md2] chunk height %d, %d groups of short last chunks per (scale, image)\n", p.m_R, p.m_group);
     const int tiles = cdiv(W, (v2 || bwd) ? 28 : 30) * cdiv(H, p.m_R);   // work items per (scale, image)

@@ -1,6 +1,8 @@
 // Stand-alone operators of the path (one reference function each, forward + backward) so that
 // every entry point of src/utils.jl and src/training.jl:1-19 has a drop-in.  These are the simple
 // thread-per-element versions; the speed path is the fused kernel in md2_fused.cu.
+#include <string.h>
+
 #include "md2_common.cuh"
 #include "md2_fused.cuh"
 
@@ -547,6 +549,21 @@ __global__ void __launch_bounds__(TILE_THREADS) photomin_bwd_kernel(PmArgs a, co
         }
     }
     if (in && gmask) gmask[i] = (sj < 0) ? gj : 0.f;
+}
+
+int launch_automask(md2_ctx* ctx, int S, const float* const* frames, const int64_t* frame_ns, const float* target, int64_t target_ns,
+                    float* out, int W, int H, int C, int N, cudaStream_t st) {
+    PmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = S; a.W = W; a.H = H; a.C = C; a.N = N;
+    for (int s = 0; s < S; ++s) { a.pred[s] = frames[s]; a.pred_ns[s] = frame_ns[s]; }
+    a.target = target; a.target_ns = target_ns; a.mask = nullptr; a.alpha = PHOTO_ALPHA;
+    MD2_REQUIRE(N <= 65535 && cdiv(H, TILE_H) <= 65535, "N and H / 8 must be <= 65535");
+    const dim3 g(cdiv(W, TILE_W), cdiv(H, TILE_H), N);
+    if (C == 1) photomin_fwd_kernel<1><<<g, TILE_THREADS, 0, st>>>(a, out, nullptr);
+    else photomin_fwd_kernel<3><<<g, TILE_THREADS, 0, st>>>(a, out, nullptr);
+    MD2_LAUNCH_CHECK(ctx);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

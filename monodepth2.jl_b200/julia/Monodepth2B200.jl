@@ -295,6 +295,7 @@ struct VslDesc
     saved::P32
     zero_grad_source::Int32
     debug_choices::CuPtr{Int32}          # test hook of the C ABI; always NULL here
+    compute_automask::Int32              # != 0 with automask == NULL: the call forms the automask map itself
 end
 pad(v, n, z) = ntuple(i -> i <= length(v) ? v[i] : z, n)
 frameptr(x::CuF, id) = pointer(x, (id - 1) * size(x, 1) * size(x, 2) * size(x, 3) + 1)   # x (W,H,C,L,N), 1-based frame id
@@ -308,7 +309,7 @@ gradients for a unit cotangent (the pullback scales them).
 """
 function vsl_fwdbwd(x::CuF, disparities, rvecs, tvecs, K::CuF, invK::CuF; target_id, source_ids, scales,
                     min_depth, max_depth, disparity_smoothness, auto_loss = nothing, normalize = true,
-                    smooth_weight = nothing, loss_scale = nothing, viz = false)
+                    smooth_weight = nothing, loss_scale = nothing, viz = false, compute_automask = false)
     W, H, C, Lf, N = size(x); S = length(source_ids); L = length(disparities)
     loss = CUDA.zeros(Float32, 1)
     gd = [similar(d) for d in disparities]; gr = [similar(r) for r in rvecs]; gt = [similar(t) for t in tvecs]
@@ -326,7 +327,7 @@ function vsl_fwdbwd(x::CuF, disparities, rvecs, tvecs, K::CuF, invK::CuF; target
         Float32(loss_scale === nothing ? 1 / L : loss_scale), Int32(normalize), ptr(loss),
         pad([ptr(g) for g in gd], MAX_L, P32(0)), pad([ptr(g) for g in gr], MAX_S, P32(0)),
         pad([ptr(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
-        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0), Int32(0), CuPtr{Int32}(0)))
+        pad([ptr(v) for v in vw], MAX_S, P32(0)), ptr(vl), P32(0), Int32(0), CuPtr{Int32}(0), Int32(compute_automask && auto_loss === nothing)))
     GC.@preserve x disparities rvecs tvecs K invK auto_loss loss gd gr gt vw vl begin
         check(ccall((:md2_view_synthesis_loss_fwdbwd, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Ptr{Cvoid}),
                     ctx(), desc, 1f0, stream()))
@@ -361,7 +362,7 @@ function vsl_fwdbwd_host!(loss::Vector{Float32}, grads, x::Array{Float32,5}, dis
         Float32(1 / L), Int32(normalize), hp(loss),
         pad([hp(g) for g in gd], MAX_L, P32(0)), pad([hp(g) for g in gr], MAX_S, P32(0)),
         pad([hp(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
-        pad(P32[], MAX_S, P32(0)), P32(0), P32(0), Int32(1), CuPtr{Int32}(0)))
+        pad(P32[], MAX_S, P32(0)), P32(0), P32(0), Int32(1), CuPtr{Int32}(0), Int32(0)))
     GC.@preserve x disparities rvecs tvecs K invK loss gd gr gt begin
         check(ccall((:md2_view_synthesis_loss_fwdbwd_host, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Cint),
                     ctx(), desc, 1f0, Cint(groups)))
@@ -394,7 +395,8 @@ function train_loss(model, x::CuArray{Float32, 5}, auto_loss, cache::TrainCache,
     kw = (; target_id = cache.target_id, source_ids = cache.source_ids, scales = cache.scales,
           min_depth = parameters.min_depth, max_depth = parameters.max_depth,
           disparity_smoothness = parameters.disparity_smoothness,
-          auto_loss = parameters.automasking ? auto_loss : nothing)
+          auto_loss = parameters.automasking ? auto_loss : nothing,
+          compute_automask = parameters.automasking && auto_loss === nothing)   # no map handed in: the call forms it itself
     rvecs = [p.rvec for p in poses]; tvecs = [p.tvec for p in poses]
     loss = view_synthesis_loss(x, collect(disparities), rvecs, tvecs, cache.K, cache.invK; kw...)
     if do_visualization     # forward-only second pass for the logging outputs (every 50 iterations)
@@ -426,7 +428,7 @@ function _warp_desc(disp, x, Ps, invKs, Ks, min_depth, max_depth, source_ids, gr
             pad([ptr(disp)], MAX_L, z), pad(Int32[W], MAX_L, Int32(0)), pad(Int32[H], MAX_L, Int32(0)), ptr(Ks), ptr(invKs),
             Int32(0), pad([ptr(P[1]) for P in Ps], MAX_S, z), pad([ptr(P[2]) for P in Ps], MAX_S, z), pad(Int32[], MAX_S, Int32(0)),
             z, Float32(min_depth), Float32(max_depth), pad(Float32[], MAX_L, 0f0), 1f0, Int32(0), z,
-            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z, Int32(0), CuPtr{Int32}(0))
+            pad([gd], MAX_L, z), pad(gR, MAX_S, z), pad(gt, MAX_S, z), pad(P32[], MAX_S, z), pad(P32[], MAX_S, z), z, z, Int32(0), CuPtr{Int32}(0), Int32(0))
 end
 function rrule(::typeof(warp), disp::CuF, x::CuF, Ps, backprojections, projections, invKs::CuF, Ks::CuF; min_depth, max_depth, source_ids)
     outs = warp(disp, x, Ps, backprojections, projections, invKs, Ks; min_depth, max_depth, source_ids)
@@ -466,7 +468,7 @@ function slow_depth(x::CuArray{Float32, 5}, ssim, backprojections, projections, 
         pad(ptr.(rvecs), MAX_S, z), pad(ptr.(tvecs), MAX_S, z), pad(Int32[i < target_id for i in source_ids], MAX_S, Int32(0)), z,
         Float32(min_depth), Float32(max_depth), pad(Float32[1], MAX_L, 0f0), 1f0, Int32(0), ptr(loss),
         pad([ptr(gd)], MAX_L, z), pad(ptr.(gr), MAX_S, z), pad(ptr.(gt), MAX_S, z), pad(P32[], MAX_S, z),
-        pad(P32[], MAX_S, z), z, z, Int32(0), CuPtr{Int32}(0)))
+        pad(P32[], MAX_S, z), z, z, Int32(0), CuPtr{Int32}(0), Int32(0)))
     done = 0
     GC.@preserve x disp rvecs tvecs loss gd gr gt state clock history Ks invKs begin
         while done < iters

@@ -18,7 +18,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import SSIM, Backproject, Project, automasking_loss
+from .ops import SSIM, Backproject, Project
 from .training import Adam, AsyncViz, Params, Pose, TrainCache, train_loss
 
 _F32 = torch.float32
@@ -259,9 +259,9 @@ class DataParallelTrainer:
         AsyncViz ticket whose .get() gives train_loss's (vis_disparity, vis_warped, vis_loss) host copies -- the copy
         runs on a side stream and is normally collected one step later, when the log is written."""
         c, hp = self.cache, self.hp
-        auto = automasking_loss(c.ssim, x, x[:, c.target_id], c.source_ids) if hp.automasking else None   # src/Monodepth.jl:159-164
         self.flat.arm()
-        loss, vd, vw, vl = train_loss(self.model, x, auto, c, hp, do_visualization, viz=self.viz if do_visualization else None)
+        # (auto_loss = None with parameters.automasking: the fused call forms the automask map itself, src/Monodepth.jl:159-164)
+        loss, vd, vw, vl = train_loss(self.model, x, None, c, hp, do_visualization, viz=self.viz if do_visualization else None)
         loss.backward()
         scale = self.flat.finish()
         self.opt.step([self.flat.grad], grad_scale=scale)

@@ -95,7 +95,8 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             loss_scale=cfg["loss_scale"], normalize_disparity=cfg["normalize"], loss=loss,
             grad_disparity=gd, grad_rot=gr, grad_trans=gt,
             grad_source=[gx[:, i] for i in sid] if need_x else None,
-            viz_warped=viz_w, viz_loss=viz_l, debug_choices=cfg.get("debug_choices") if any_grad else None, shape=(N, Cc, H, W))
+            viz_warped=viz_w, viz_loss=viz_l, debug_choices=cfg.get("debug_choices") if any_grad else None,
+            compute_automask=cfg.get("compute_automask", False), shape=(N, Cc, H, W))
         if any_grad:
             c.call("md2_view_synthesis_loss_fwdbwd", C.byref(desc), 1.0)
             ctx.grads = (gd, gr, gt, gx)
@@ -120,7 +121,7 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
                         scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0,
                         disparity_smoothness=1e-3, auto_loss=None, normalize_disparity=True,
                         smooth_weight=None, loss_scale=None, poses_are_rvec=True, invert=None,
-                        return_viz=False, K_cm=None, invK_cm=None, debug_choices=None):
+                        return_viz=False, K_cm=None, invK_cm=None, debug_choices=None, compute_automask=False):
     """Everything of train_loss after `model(...)` (src/training.jl:29-77) in fused kernels.
 
     x (N,L,C,H,W); disparities: list of (N,1,h_i,w_i) at the decoder's native sizes (smaller ones
@@ -129,6 +130,8 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
     or R (N,3,3)/t (N,3) as returned by composeT.  auto_loss (N,1,H,W) enables automasking.
     Returns the scalar loss (and, if return_viz, the last scale's warp-loss map and warped
     images, which the reference copies out for logging).
+    compute_automask=True (with auto_loss=None): the automask map is formed inside the call from the un-warped source
+    frames (the pre-pass of src/Monodepth.jl:159-164 folded in; a constant of the loss, as in the reference).
     debug_choices: optional int32 (L,N,H,W,1+S) test hook that receives the kernel's discrete decisions
     (include/md2.h: md2_vsl_desc.debug_choices)."""
     S, Lc = len(source_ids), len(disparities)
@@ -145,7 +148,8 @@ def view_synthesis_loss(x, disparities, rot, trans, K, invK, *, target_id=1, sou
                smooth_weight=smooth_weight if smooth_weight is not None else
                [disparity_smoothness * s for s in list(scales)[:Lc]],
                loss_scale=loss_scale if loss_scale is not None else 1.0 / Lc,
-               normalize=normalize_disparity, viz=return_viz, debug_choices=debug_choices)
+               normalize=normalize_disparity, viz=return_viz, debug_choices=debug_choices,
+               compute_automask=bool(compute_automask) and auto_loss is None)
     trans = [t.reshape(-1, 3) for t in trans]
     out = _ViewSynthesisLoss.apply(cfg, x, *disparities, *rot, *trans)
     if return_viz:
@@ -194,11 +198,12 @@ class HostViewSynthesisLoss:
         self._invK = _cm(_f32c(invK.reshape(3, 3).cpu())).pin_memory()
         self.lane_inputs, self.lane_grads, self._lane_loss, self._descs = [], [], [], []
         for _ in range(lanes):
-            big, in_buf = slab([(N, 3, C_, H, W)] + [(N, 1, h, w) for (w, h) in disp_sizes] + ([(N, 1, H, W)] if automask else []))
+            am_in = bool(automask) and automask != "inside"          # a map handed in by the caller ("inside": formed by the call)
+            big, in_buf = slab([(N, 3, C_, H, W)] + [(N, 1, h, w) for (w, h) in disp_sizes] + ([(N, 1, H, W)] if am_in else []))
             gbig, out_buf = slab([(N, 1, h, w) for (w, h) in disp_sizes])
             nd = len(disp_sizes)
             inputs = dict(x=big[0], disparities=big[1:1 + nd], rvecs=[pin(N, 3) for _ in source_ids], tvecs=[pin(N, 3) for _ in source_ids],
-                          automask=big[1 + nd] if automask else None, _slab=in_buf)
+                          automask=big[1 + nd] if am_in else None, _slab=in_buf)
             grads = dict(disparities=gbig, rvecs=[pin(N, 3) for _ in source_ids],
                          tvecs=[pin(N, 3) for _ in source_ids], x=pin(N, 3, C_, H, W) if grad_x else None, _slab=out_buf)
             loss = pin(1)
@@ -207,7 +212,7 @@ class HostViewSynthesisLoss:
                 target=x[:, target_id], target_stride=x.stride(0), sources=[x[:, i] for i in source_ids],
                 source_strides=[x.stride(0)] * self.S, disparities=inputs["disparities"], K_cm=self._K, invK_cm=self._invK,
                 rot=inputs["rvecs"], trans=inputs["tvecs"], pose_mode=1, invert=[i < target_id for i in source_ids],
-                automask=inputs["automask"], min_depth=min_depth, max_depth=max_depth,
+                automask=inputs["automask"], compute_automask=(automask == "inside"), min_depth=min_depth, max_depth=max_depth,
                 smooth_weight=[disparity_smoothness * s for s in list(scales)[:self.L]], loss_scale=1.0 / self.L,
                 normalize_disparity=normalize_disparity, loss=loss, grad_disparity=grads["disparities"],
                 grad_rot=grads["rvecs"], grad_trans=grads["tvecs"],
@@ -216,7 +221,7 @@ class HostViewSynthesisLoss:
         self.inputs, self.grads, self._loss, self.desc = self.lane_inputs[0], self.lane_grads[0], self._lane_loss[0], self._descs[0]
         x = self.inputs["x"]
         self.h2d_bytes = 4 * sum(t.numel() for t in [x] + self.inputs["disparities"] + self.inputs["rvecs"] + self.inputs["tvecs"]
-                                 + ([self.inputs["automask"]] if automask else [])) + 72
+                                 + ([self.inputs["automask"]] if self.inputs["automask"] is not None else [])) + 72
         self.d2h_bytes = 4 + 4 * sum(t.numel() for t in self.grads["disparities"] + self.grads["rvecs"] + self.grads["tvecs"]) \
             + (8 * N * C_ * H * W if grad_x else 0)
 
@@ -376,6 +381,7 @@ def train_loss(model, x, auto_loss, cache: TrainCache, parameters: Params, do_vi
         min_depth=parameters.min_depth, max_depth=parameters.max_depth,
         disparity_smoothness=parameters.disparity_smoothness,
         auto_loss=auto_loss if parameters.automasking else None, return_viz=do_visualization,
+        compute_automask=parameters.automasking and auto_loss is None,     # (no map handed in: the call forms it itself)
         K_cm=cache.K_cm, invK_cm=cache.invK_cm)
     if do_visualization:
         loss, vis_warped, vis_loss = out

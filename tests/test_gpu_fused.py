@@ -305,3 +305,38 @@ def test_host_entry_point_single_source_not_first_frame():
     assert abs(loss - ref.item()) <= 2e-6
     for a, b in zip(hv.grads["disparities"], dg):
         assert torch.allclose(a, b.grad.cpu(), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Cc", [1, 3])
+def test_automask_formed_inside_the_call_equals_the_pre_pass(Cc):
+    """desc.compute_automask: the automask pre-pass of the training loop (src/Monodepth.jl:159-164) folded into the fused
+    call gives bit for bit the result of handing in automasking_loss(...) computed beforehand; same through the host entry"""
+    N, H, W = 3, 48, 96
+    x, disps, rv, tv = O.synthetic_batch(N, Cc, H, W, seed=12)
+    K, invK = O.make_K(W, H)
+    dev = torch.device("cuda", 0)
+    xg = x.to(dev)
+
+    def run(**kw):
+        dg = [d.to(dev).requires_grad_(True) for d in disps]
+        rg = [r.to(dev).requires_grad_(True) for r in rv]
+        tg = [t.to(dev).requires_grad_(True) for t in tv]
+        loss = M.view_synthesis_loss(xg, dg, rg, tg, K.to(dev), invK.to(dev), **kw)
+        loss.backward()
+        return [loss.detach()] + [t.grad for t in dg + rg + tg]
+
+    auto = M.automasking_loss(M.SSIM(), xg, xg[:, 1], (0, 2))
+    a, b, c = run(auto_loss=auto), run(compute_automask=True), run()
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
+    assert not torch.equal(a[0], c[0])                      # (and the mask does change the loss)
+    with torch.no_grad():                                   # forward-only call
+        l0 = M.view_synthesis_loss(xg, [d.to(dev) for d in disps], [r.to(dev) for r in rv], [t.to(dev) for t in tv], K.to(dev), invK.to(dev), auto_loss=auto)
+        l1 = M.view_synthesis_loss(xg, [d.to(dev) for d in disps], [r.to(dev) for r in rv], [t.to(dev) for t in tv], K.to(dev), invK.to(dev), compute_automask=True)
+    assert torch.equal(l0, l1)
+    hv = M.HostViewSynthesisLoss(N, Cc, H, W, [(d.shape[-1], d.shape[-2]) for d in disps], K, invK, device=dev, automask="inside", groups=1)
+    lh = hv(x, disps, rv, tv)
+    assert abs(lh - a[0].item()) <= 2e-6
+    for p, q in zip(hv.grads["disparities"], a[1:1 + len(disps)]):
+        assert torch.allclose(p, q.cpu(), rtol=1e-5, atol=1e-9)
