@@ -188,16 +188,14 @@ def run_ours(args):
     set_bytes = 4 * (NB * 3 * CH * H_ * W_ * 2 + 2 * sum(int(NB * round(H_ * s) * round(W_ * s)) for s in SCALES))
     n_sets = max(4, int(2.5 * l2_bytes / set_bytes) + 1)
     sets, base = make_sets(n_sets, dev, 42 + rank)
-    if AM:   # the automask map of every ring slot (src/Monodepth.jl:159-164), computed once: it is an INPUT of the timed call
-        for st in sets:
-            st["am"] = M.automasking_loss(M.SSIM(), st["x"], st["x"][:, 1], (0, 2)).contiguous()
+    # (automasking: the map is formed INSIDE the timed call, desc.compute_automask -- the per-step pre-pass of src/Monodepth.jl:159-164)
 
     def desc_for(st):
         x = st["x"]
         return L.make_vsl_desc(
             target=x[:, 1], target_stride=x.stride(0), sources=[x[:, 0], x[:, 2]], source_strides=[x.stride(0)] * 2,
             disparities=st["disps"], K_cm=K_cm, invK_cm=invK_cm, rot=st["rv"], trans=st["tv"], pose_mode=1,
-            invert=[1, 0], automask=st["am"], smooth_weight=sw, loss_scale=1.0 / LS, normalize_disparity=True, loss=st["loss"],
+            invert=[1, 0], automask=None, compute_automask=AM, smooth_weight=sw, loss_scale=1.0 / LS, normalize_disparity=True, loss=st["loss"],
             grad_disparity=st["gd"], grad_rot=st["gr"], grad_trans=st["gt"],
             grad_source=(None if os.environ.get("MD2_BENCH_G0") else [st["gx"][:, 0], st["gx"][:, 2]]), zero_grad_source=True, shape=(NB, CH, H_, W_))
 
@@ -302,7 +300,7 @@ def run_ours(args):
     # buffers hold the results), so the steps are timed back to back on the host clock ----
     hx, hd, hr, ht = base
     Kd, invKd = K.to(dev), invK.to(dev)
-    h_am = sets[0]["am"].cpu() if AM else None
+    h_am = None
     import gc
 
     def time_host(grad_x, e_steps, lanes=1):
@@ -312,7 +310,7 @@ def run_ours(args):
         inputs from pinned host memory and its own results back; the loop collects every step's loss."""
         # (image groups overlap copies and kernels INSIDE a call; with two lanes the overlap comes from the next call)
         hv = M.HostViewSynthesisLoss(NB, CH, H_, W_, [(d.shape[-1], d.shape[-2]) for d in hd], K, invK, device=dev,
-                                     scales=SCALES, groups=args.e2e_groups if lanes == 1 else 1, grad_x=grad_x, automask=AM, lanes=lanes)
+                                     scales=SCALES, groups=args.e2e_groups if lanes == 1 else 1, grad_x=grad_x, automask="inside" if AM else False, lanes=lanes)
         for lane in range(lanes):
             hv.fill(lane, hx, hd, hr, ht, automask=h_am)
         if lanes == 1:
@@ -399,7 +397,7 @@ def run_ours(args):
                 a.copy_(b, non_blocking=True)
         for a in dd + dr + dt:
             a.grad = None
-        loss = M.view_synthesis_loss(dx, dd, dr, dt, Kd, invKd, K_cm=K_cm, invK_cm=invK_cm, auto_loss=sets[0]["am"] if AM else None)
+        loss = M.view_synthesis_loss(dx, dd, dr, dt, Kd, invKd, K_cm=K_cm, invK_cm=invK_cm, compute_automask=AM)
         loss.backward()
         h_loss.copy_(loss.detach(), non_blocking=True)
         for a, b in zip(h_gd + h_gp, dd + dr + dt):
@@ -423,7 +421,8 @@ def run_ours(args):
         "warmup": warm, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded KITTI-shaped triplets, random-init poses/disparities)",
         "config": {"workload": WORKLOAD, "width": W_, "height": H_, "batch_per_gpu": NB, "channels": CH,
-                   "sources": S_, "scales": LS, "automask": AM, "grad_source_images": True,
+                   "sources": S_, "scales": LS, "automask": AM, "automask_map": "formed inside the timed call (desc.compute_automask)" if AM else None,
+                   "grad_source_images": True,
                    "l2_policy": f"inputs larger than L2: ring of {n_sets} input/gradient sets ({n_sets * set_bytes / 1e6:.0f} MB) rotated per step",
                    "api": "md2_view_synthesis_loss_fwdbwd (C ABI), one call per step", "sharding": "batch, no data-path collective"},
         "images_per_s": round(3 * value, 1),
