@@ -117,9 +117,10 @@ class ClockSampler(threading.Thread):
             pass
 
     def run(self):
+        # (a query every 10 ms: NVML calls take a driver-wide lock, and eight ranks polling every 2 ms showed up as launch jitter)
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.002)
+            time.sleep(0.010)
 
     def summary(self):
         s = sorted(self.samples)

@@ -31,6 +31,11 @@
 
 namespace md2 {
 
+#ifndef MD2_M2_UNROLL
+#define MD2_M2_UNROLL 1   // row-loop unroll factor of the marching kernel (1: rolled)
+#endif
+constexpr int M2_UNROLL = MD2_M2_UNROLL;
+
 // ---------------------------------------------------------------------------------------------------------------
 // SV<S>: one float per source frame with element-wise arithmetic; S = 2 is a packed f32x2 register pair
 // ---------------------------------------------------------------------------------------------------------------
@@ -840,6 +845,7 @@ struct March2 {
                 k.amn = g_ld(c.am + qn * c.W);
             }
         }
+#pragma unroll M2_UNROLL
         for (int i = i0, it = 0; i < iend; ++i, ++it) step(c, k, i, it);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
