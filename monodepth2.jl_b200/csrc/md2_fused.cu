@@ -831,7 +831,10 @@ static int march2_resident() {
         const size_t smem = sizeof(float) * (size_t)M::SMEM_FLOATS;
         int occ = 0;
         if (cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) occ = 0;
-        cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG, GRAD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        // value + gradient: 16 rings of 12 KB need the whole shared-memory carve-out; forward-only: 2 KB per warp -- leave the rest
+        // of the 256 KB to the L1 (the gathers of the sources live there)
+        cudaFuncSetAttribute(march2_kernel<C, S, AM, DBG, GRAD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             GRAD ? (int)cudaSharedmemCarveoutMaxShared : 30);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march2_kernel<C, S, AM, DBG, GRAD>, M::THREADS, smem) != cudaSuccess) occ = 0;
         resident = occ > 0 ? occ : 8;
         if (getenv("MD2_DEBUG")) fprintf(stderr, "[md2] march2_kernel<%d,%d>: %d resident warps/SM, %zu B smem/warp\n", C, S, resident, smem);
