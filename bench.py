@@ -128,17 +128,27 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def make_sets(n_sets, dev, seed0):
+def make_sets(n_sets, dev, seed0, smooth=False):
     """ring of independent input + gradient-output sets, each built from the package's seeded
     synthetic generator (monodepth2_jl_b200.synthetic; the tests check that it produces exactly
-    the data of the oracle-side generator)."""
+    the data of the oracle-side generator).
+    smooth=True: disparities as a depth network produces them -- smooth fields (a coarse random field, bilinearly
+    enlarged, the same scene at every scale) instead of the generator's low-passed noise with +-10 % per-pixel jitter per ring
+    slot.  The warp of a smooth disparity samples neighbouring cells for neighbouring pixels (coalesced gathers and
+    reductions); the noisy default scatters them over ~14 sectors per warp instruction and is the harsher case."""
     from monodepth2_jl_b200 import synthetic as SY
     base = SY.synthetic_batch(NB, CH, H_, W_, seed=seed0)
     sets = []
     g = torch.Generator().manual_seed(seed0 + 1)
     for i in range(n_sets):
         x, disps, rv, tv = base
-        if i:   # cheap decorrelated variants of the base batch (different data per ring slot)
+        if smooth:
+            coarse = torch.randn(NB, 1, max(2, H_ // 32), max(2, W_ // 32), generator=g)
+            disps = [torch.sigmoid(1.5 * torch.nn.functional.interpolate(coarse, size=tuple(d.shape[-2:]), mode="bilinear", align_corners=True)).contiguous()
+                     for d in disps]
+            if i:
+                x = (x + 0.02 * torch.rand(x.shape, generator=g)).clamp(0, 1)
+        elif i:   # cheap decorrelated variants of the base batch (different data per ring slot)
             x = (x + 0.02 * torch.rand(x.shape, generator=g)).clamp(0, 1)
             disps = [(d * (0.9 + 0.2 * torch.rand(d.shape, generator=g))).clamp(0.01, 0.99) for d in disps]
         sets.append(dict(
@@ -266,6 +276,26 @@ def run_ours(args):
     variants = {"fwdbwd_warm_l2_ms": round(timed(lambda i: step(0), n_var), 5), "fwd_only_cold_ms": round(timed(step_fwd, n_var), 5),
                 "fwd_only_warm_l2_ms": round(timed(lambda i: step_fwd(0), n_var), 5),
                 "note": "same workload; warm = one input set back to back (L2-resident), cold = the ring; fwd_only = md2_view_synthesis_loss_fwd (loss value only)"}
+
+    # ---- the same workload on smooth disparities (what a depth network produces), cold ring: step and marching kernel ----
+    sets_s, _ = make_sets(n_sets, dev, 4242 + rank, smooth=True)
+    descs_s = [desc_for(st) for st in sets_s]
+
+    def step_s(i):
+        if fwdbwd(handle, C.byref(descs_s[i % n_sets]), 1.0, sptr):
+            raise RuntimeError(lib.md2_last_error().decode())
+    for i in range(2 * n_sets + 2):
+        step_s(i)
+    variants["fwdbwd_smooth_disparity_ms"] = round(timed(step_s, n_var), 5)
+    ctx.profile(True)
+    for i in range(n_var):
+        step_s(i)
+    sk, sn = ctx.profile_read()
+    ctx.profile(False)
+    variants["march_kernel_smooth_disparity_ms"] = round(sk / max(sn, 1), 5)
+    variants["smooth_note"] = ("smooth disparities = a coarse random field bilinearly enlarged (same scene at every scale), as a depth network produces them; "
+                               "the headline workload keeps the generator's noisy disparities (neighbouring pixels sample cells several pixels apart), the harsher case")
+    del sets_s, descs_s
 
     # ---- roofline of the dominant kernel: second pass with per-launch CUDA events ----
     ctx.profile(True)

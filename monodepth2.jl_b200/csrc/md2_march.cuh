@@ -169,8 +169,13 @@ template <class T> MD2_DEV void keep(T*& v) { asm volatile("" : "+l"(v)); }
 MD2_DEV float g_ld(const float* q) { float v; asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(q)); return v; }
 MD2_DEV float g_ld1(const float* q) { float v; asm("ld.global.nc.f32 %0, [%1+4];" : "=f"(v) : "l"(q)); return v; }
 MD2_DEV void g_st(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v)); }
+#if defined(MD2_FAKE_RED)   // timing experiment only (wrong results): plain stores in place of the reductions
+MD2_DEV void g_red(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v)); }
+MD2_DEV void g_red1(float* q, float v) { asm volatile("st.global.f32 [%0+4], %1;" ::"l"(q), "f"(v)); }
+#else
 MD2_DEV void g_red(float* q, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v)); }
 MD2_DEV void g_red1(float* q, float v) { asm volatile("red.global.add.f32 [%0+4], %1;" ::"l"(q), "f"(v)); }
+#endif
 // pull a line into L1 one row ahead of its use (every row of the march touches new lines)
 #ifndef MD2_PREFETCH
 #define MD2_PREFETCH 0   // measured: with the register pipeline of warp F the L1 prefetch of source rows costs more than it saves
