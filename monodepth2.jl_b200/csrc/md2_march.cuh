@@ -95,6 +95,7 @@ inline float g_ld1(const float* q) { return q[1]; }
 inline void g_st(float* q, float v) { *q = v; }
 inline void g_red(float* q, float v) { *q += v; }
 inline void g_red1(float* q, float v) { q[1] += v; }
+inline void g_red_pair(float* q, float a, float b) { q[0] += a; q[1] += b; }
 inline void g_pf(const float*) {}
 #define MD2_POSE(p, idx) ((p).pose_ab[(idx)])
 #else
@@ -176,6 +177,14 @@ MD2_DEV void g_red1(float* q, float v) { asm volatile("st.global.f32 [%0+4], %1;
 MD2_DEV void g_red(float* q, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v)); }
 MD2_DEV void g_red1(float* q, float v) { asm volatile("red.global.add.f32 [%0+4], %1;" ::"l"(q), "f"(v)); }
 #endif
+// q[0] += a, q[1] += b: one 64-bit vector reduction where the pair is 8-byte aligned (half the sector operations of two
+// scalar ones), two scalar reductions otherwise -- three predicated instructions, no branch
+MD2_DEV void g_red_pair(float* q, float a, float b) {
+    asm volatile("{ .reg .pred p; .reg .b64 t; and.b64 t, %0, 4; setp.eq.b64 p, t, 0;\n"
+                 "  @p red.global.add.v2.f32 [%0], {%1, %2};\n"
+                 "  @!p red.global.add.f32 [%0], %1;\n"
+                 "  @!p red.global.add.f32 [%0+4], %2; }" ::"l"(q), "f"(a), "f"(b));
+}
 // pull a line into L1 one row ahead of its use (every row of the march touches new lines)
 #ifndef MD2_PREFETCH
 #define MD2_PREFETCH 0   // measured: with the register pipeline of warp F the L1 prefetch of source rows costs more than it saves

@@ -129,6 +129,9 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 #ifndef MD2_M2_RC
 #define MD2_M2_RC 0
 #endif
+#ifndef MD2_M2_RED2
+#define MD2_M2_RED2 0   // 0: scalar reductions; 1: vector pairs for C = 3; 2: always
+#endif
 #ifndef MD2_M2_MERGE
 #define MD2_M2_MERGE 0
 #endif
@@ -690,8 +693,13 @@ struct March2 {
                             float* o1 = c.gb[s] + (off[s] + c.W);
 #pragma unroll
                             for (int ch = 0; ch < C; ++ch) {
-                                g_red(o + ch * c.HW, t0[ch].v[s]); g_red1(o + ch * c.HW, t1[ch].v[s]);
-                                g_red(o1 + ch * c.HW, b0[ch].v[s]); g_red1(o1 + ch * c.HW, b1[ch].v[s]);
+                                if (MD2_M2_RED2 == 2 || (MD2_M2_RED2 == 1 && C == 3)) {   // 64-bit vector reductions where the tap pair is aligned
+                                    g_red_pair(o + ch * c.HW, t0[ch].v[s], t1[ch].v[s]);
+                                    g_red_pair(o1 + ch * c.HW, b0[ch].v[s], b1[ch].v[s]);
+                                } else {
+                                    g_red(o + ch * c.HW, t0[ch].v[s]); g_red1(o + ch * c.HW, t1[ch].v[s]);
+                                    g_red(o1 + ch * c.HW, b0[ch].v[s]); g_red1(o1 + ch * c.HW, b1[ch].v[s]);
+                                }
                             }
                         }
                     }
