@@ -346,7 +346,7 @@ are host arrays written in place.
 """
 function vsl_fwdbwd_host!(loss::Vector{Float32}, grads, x::Array{Float32,5}, disparities, rvecs, tvecs,
                           K::Matrix{Float32}, invK::Matrix{Float32}; target_id, source_ids, scales, min_depth, max_depth,
-                          disparity_smoothness, normalize = true, groups = 2)
+                          disparity_smoothness, normalize = true, groups = 2, lane = nothing)
     W, H, C, Lf, N = size(x); S = length(source_ids); L = length(disparities)
     gd, gr, gt = grads
     hp(a) = a === nothing ? P32(0) : reinterpret(P32, pointer(a))
@@ -364,11 +364,20 @@ function vsl_fwdbwd_host!(loss::Vector{Float32}, grads, x::Array{Float32,5}, dis
         pad([hp(g) for g in gt], MAX_S, P32(0)), pad(P32[], MAX_S, P32(0)),
         pad(P32[], MAX_S, P32(0)), P32(0), P32(0), Int32(1), CuPtr{Int32}(0), Int32(0)))
     GC.@preserve x disparities rvecs tvecs K invK loss gd gr gt begin
-        check(ccall((:md2_view_synthesis_loss_fwdbwd_host, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Cint),
-                    ctx(), desc, 1f0, Cint(groups)))
+        if lane === nothing          # synchronous: returns when every output is in host memory
+            check(ccall((:md2_view_synthesis_loss_fwdbwd_host, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Cint),
+                        ctx(), desc, 1f0, Cint(groups)))
+        else                         # asynchronous: enqueue on lane 0 .. 2 and return; collect with vsl_host_wait(lane).
+            # The caller keeps every array of this call alive and untouched until then (a data loader one or two steps ahead)
+            check(ccall((:md2_view_synthesis_loss_fwdbwd_host_submit, LIB), Cint, (Ptr{Cvoid}, Ptr{VslDesc}, Cfloat, Cint, Cint),
+                        ctx(), desc, 1f0, Cint(groups), Cint(lane)))
+            return nothing
+        end
     end
     loss[1]
 end
+"""`vsl_host_wait(lane)`: block until the call submitted on `lane` has written its loss and gradients to the host arrays."""
+vsl_host_wait(lane::Integer) = check(ccall((:md2_host_wait, LIB), Cint, (Ptr{Cvoid}, Cint), ctx(), Cint(lane)))
 
 # the tail of train_loss as one differentiable function of (disparities, rvecs, tvecs)
 function view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK; kw...)
@@ -489,6 +498,6 @@ end
 
 # `warp` is the only NEW name (the reference calls it and never defines it): `using .B200: warp` in Monodepth.jl.
 # view_synthesis_loss / vsl_fwdbwd / vsl_fwdbwd_host! are this binding's own additions.
-export warp, view_synthesis_loss, vsl_fwdbwd, vsl_fwdbwd_host!
+export warp, view_synthesis_loss, vsl_fwdbwd, vsl_fwdbwd_host!, vsl_host_wait
 
 end # module B200
