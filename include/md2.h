@@ -52,8 +52,8 @@ int64_t md2_launch_count(const md2_ctx* ctx);
 int md2_profile_enable(md2_ctx* ctx, int32_t on);
 int md2_profile_read(md2_ctx* ctx, float* total_ms, int64_t* launches);
 /* md2_profile_enable(ctx, 2): time stamps around all three launches of the fused calls (prep | marching kernel | finish);
- * md2_profile_read_phases returns the three summed durations.  The events between the launches take away their
- * programmatic overlap, so the three add up to a little more than an un-profiled step. */
+ * md2_profile_read_phases returns the three summed durations.  The event records between the launches add to the
+ * gaps between them, so the three add up to a little more than an un-profiled step. */
 int md2_profile_read_phases(md2_ctx* ctx, float* prep_ms, float* march_ms, float* finish_ms, int64_t* launches);
 
 /* ---- A1  disparity_to_depth            src/utils.jl:175-179 ------------------------- */

@@ -108,10 +108,11 @@ int launch_reduce_partials(md2_ctx* ctx, const float* partial, float* out0, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// programmatic dependent launch: the three kernels of a call are chained with
+// programmatic dependent launch: with MD2_PDL (bit mask, see pdl_mask) the three kernels of a call are chained with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's blocks are scheduled (launch latency, block
 // set-up) while the previous kernel drains; pdl_wait() returns once the previous kernel has completed and its writes are
-// visible, pdl_trigger() lets the next kernel start launching.  MD2_PDL=0 falls back to plain stream order.
+// visible, pdl_trigger() lets the next kernel start launching.  Default 0 = plain stream order: measured faster (the
+// dependent's early-resident warps take registers from the running kernel: 83.0 vs 74.6 us per step at 416x128x8).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
