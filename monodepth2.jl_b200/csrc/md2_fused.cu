@@ -115,7 +115,14 @@ int launch_reduce_partials(md2_ctx* ctx, const float* partial, float* out0, int 
 // dependent's early-resident warps take registers from the running kernel: 83.0 vs 74.6 us per step at 416x128x8).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef MD2_PDL_EARLY
+#define MD2_PDL_EARLY 1   // 1: a block lets the dependent kernel start launching as soon as it runs; 0: only when it exits
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if MD2_PDL_EARLY
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // bit 0: the marching kernel may overlap the prep kernel's tail, bit 1: the finish kernel the marching kernel's
 static int pdl_mask() {
