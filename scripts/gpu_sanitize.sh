@@ -17,6 +17,8 @@ for (N, C, H, W, am) in [(2, 1, 40, 72, False), (2, 3, 33, 70, True)]:
     auto = M.automasking_loss(M.SSIM(), xg.detach(), xg.detach()[:, 1], (0, 2)) if am else None
     loss = M.view_synthesis_loss(xg, dg, rg, tg, K.to(dev), invK.to(dev), auto_loss=auto)
     loss.backward()
+    if am:   # the automask map formed inside the call
+        M.view_synthesis_loss(xg, dg, rg, tg, K.to(dev), invK.to(dev), compute_automask=True).backward()
     with torch.no_grad():
         l2 = M.view_synthesis_loss(xg.detach(), [d.detach() for d in dg], [r.detach() for r in rg], [t.detach() for t in tg], K.to(dev), invK.to(dev), auto_loss=auto)
     # stand-alone operators with tiles / merged scatter
