@@ -129,6 +129,9 @@ MD2_DEV void g_st_if(float* q, float v, bool pr) {
 #ifndef MD2_M2_RC
 #define MD2_M2_RC 0
 #endif
+#ifndef MD2_M2_HCARRY
+#define MD2_M2_HCARRY 0
+#endif
 #ifndef MD2_M2_RED2
 #define MD2_M2_RED2 0   // 0: scalar reductions; 1: vector pairs for C = 3; 2: always
 #endif
@@ -167,6 +170,9 @@ struct March2 {
     static constexpr int H_X = 0, H_XX = S * C, H_XY = 2 * S * C, H_Y = 3 * S * C, H_YY = H_Y + C;
     static constexpr int NHF = H_YY + C;
     static constexpr int NH4 = (NHF + 3) / 4;
+    // keep the window sums of the previous row in registers (one ring load less per row and 128-bit word) where the register
+    // budget has room for them: C = 1
+    static constexpr bool HCARRY = MD2_M2_HCARRY != 0 && C == 1;
     static constexpr int NSLOT = 4;                      // pixel packets of rows i-2 .. i+1 are in flight
     static constexpr int NHIST = 2;                      // window sums of rows i-2, i-1 (row i takes the slot of row i-2 once that has been read)
     static constexpr int HIST0 = GRAD ? NSLOT * NP4 * 32 : 0;  // Vec4 index of the history region (forward-only: no pixel packets)
@@ -229,6 +235,7 @@ struct March2 {
         V B[3 * C], Cq[3 * C];   // vertical adjoint accumulators of pixel rows i-1 and i
         V P0[3], P1[3], Ph[3];   // pose accumulators
         float warp_sum;
+        float hprev[HCARRY ? NH4 * 4 : 1];   // HCARRY: window sums of row i-1 (otherwise read back from the ring like those of row i-2)
         float ssx, ssy, dsum;    // forward-only: smoothness / mean-disparity sums (src/utils.jl:159-173, src/training.jl:64)
     };
 
@@ -340,9 +347,15 @@ struct March2 {
             const int sa = hist_vec(it - 2), sb = hist_vec(it - 1);
 #pragma unroll
             for (int w4 = 0; w4 < NH4; ++w4) {
-                const Vec4 a4 = s_ld4(c.rr, sa + w4 * 32), b4 = s_ld4(c.rr, sb + w4 * 32);
+                const Vec4 a4 = s_ld4(c.rr, sa + w4 * 32);
                 ha[4 * w4] = a4.x; ha[4 * w4 + 1] = a4.y; ha[4 * w4 + 2] = a4.z; ha[4 * w4 + 3] = a4.w;
-                hb[4 * w4] = b4.x; hb[4 * w4 + 1] = b4.y; hb[4 * w4 + 2] = b4.z; hb[4 * w4 + 3] = b4.w;
+                if (HCARRY) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hb[4 * w4 + j] = k.hprev[4 * w4 + j];
+                } else {
+                    const Vec4 b4 = s_ld4(c.rr, sb + w4 * 32);
+                    hb[4 * w4] = b4.x; hb[4 * w4 + 1] = b4.y; hb[4 * w4 + 2] = b4.z; hb[4 * w4 + 3] = b4.w;
+                }
             }
         }
         // =========================== C(i) ===========================
@@ -405,6 +418,10 @@ struct March2 {
             for (int w4 = 0; w4 < NH4; ++w4) {
                 Vec4 c4; c4.x = hs[4 * w4]; c4.y = hs[4 * w4 + 1]; c4.z = hs[4 * w4 + 2]; c4.w = hs[4 * w4 + 3];
                 s_st4(c.rr, sc + w4 * 32, c4);
+            }
+            if (HCARRY) {
+#pragma unroll
+                for (int j = 0; j < NH4 * 4; ++j) k.hprev[j] = hs[j];
             }
         }
         // pixel packet of row i-2 (for P)
@@ -840,6 +857,8 @@ struct March2 {
         for (int ch = 0; ch < C; ++ch) { k.xmp[ch] = sv_bc<S>(0.f); k.ymp[ch] = 0.f; }
         k.Dp = 0.f; k.selp = -1; k.ghp = 0.f; k.ey_prev = 0.f; k.warp_sum = 0.f; k.zc = 0.f; k.amn = 0.f;
         k.ssx = 0.f; k.ssy = 0.f; k.dsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < (HCARRY ? NH4 * 4 : 1); ++j) k.hprev[j] = 0.f;
         const int i0 = c.Y0 - (GRAD ? HALO : 1), iend = c.Y1 + (GRAD ? HALO : 1);   // (forward-only: windows reach one row out)
         {   // prime the pipeline: raw loads of row i0, then A(i0)
             k.gy = image_row(i0, c.H);
