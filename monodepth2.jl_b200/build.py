@@ -47,10 +47,15 @@ def build(force=False, verbose=False):
                     raise RuntimeError(f"nvcc build of {s} failed:\n" + r.stdout + r.stderr)
                 if verbose:
                     print(r.stderr)
-    if todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+    # (the library remembers which flag set it was linked from: a tuning build must not survive as the default library)
+    stamp = os.path.join(OBJ, "linked.tag")
+    linked = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    if todo or linked != tag or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         r = subprocess.run([nvcc, "-shared", "--cudart", "shared", "-o", LIB] + objs, cwd=CSRC, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link of libmd2_b200.so failed:\n" + r.stdout + r.stderr)
+        with open(stamp, "w") as f:
+            f.write(tag)
     return LIB
 
 
