@@ -670,11 +670,22 @@ def cpu_baseline(base, budget_s=15.0, steps=None, warmup=1, one_thread=True):
         cpu_step(base, K, invK)
         one = time.time() - t0
         torch.set_num_threads(cores)
+    c_one = None
+    if one_thread:   # the scalar C restatement (oracle/c_oracle.c: float64, hand-derived reverse pass), one thread
+        try:
+            from oracle import c_oracle as CO
+            auto = O.automasking_loss(O.SSIM(), base[0], base[0][:, 1], (0, 2)) if AM else None
+            t0 = time.time()
+            CO.view_synthesis_loss(base[0], base[1], base[2], base[3], K, invK, auto_loss=auto)
+            c_one = time.time() - t0
+        except Exception as e:   # (no C compiler on the box and no prebuilt library: the figure is optional)
+            print(f"c_oracle unavailable: {e}", file=sys.stderr)
     return {"value": round(NB / mean, 3), "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{len(times)} steps of the same workload (batch {NB}, {W_}x{H_}, 4 scales, fwd+bwd) through the "
                       f"PyTorch-CPU restatement of the reference (Julia is not installed), fp32, {cores} threads; "
                       f"best {NB / min(times):.3f} frames/s", "ms_per_step": round(mean * 1e3, 2),
-            "value_1_thread": round(NB / one, 3) if one else None}
+            "value_1_thread": round(NB / one, 3) if one else None,
+            "value_c_oracle_f64_1_thread": round(NB / c_one, 3) if c_one else None}
 
 
 def run_reference(args):
