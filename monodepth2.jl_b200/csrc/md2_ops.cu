@@ -514,6 +514,169 @@ __global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_kernel(PmArgs a, fl
     }
 }
 
+// ---- the same operator with the tiles staged by the copy engine (TMA bulk copies, sm_90+) ------------------------------
+// Interior tiles (x0 >= 4, x0 + 36 <= W, rows 16-byte aligned): every tile row is ONE cp.async.bulk of 40 floats (the 34
+// needed + the 16-byte alignment margin) issued by one thread per row, completion counted on an mbarrier; no per-element
+// address arithmetic, no register round trip, and the (channel, source) passes are double-buffered: the copies of pass
+// k + 1 are in flight while pass k computes (one __syncthreads per pass instead of three).  Tiles on the left / right image
+// border (reflected columns) and unaligned shapes stage through the threads into the same layout.
+#ifndef MD2_PM_BULK
+#define MD2_PM_BULK 1
+#endif
+constexpr int PM_PITCH = 40, PM_COL0 = 3;              // smem pitch (floats); tile-local column of image column x0 - 1
+constexpr int PM_ROWS = FWD_TH + 2;
+constexpr unsigned PM_ROW_BYTES = PM_PITCH * 4, PM_TILE_BYTES = PM_ROWS * PM_ROW_BYTES;
+
+__device__ __forceinline__ unsigned pm_smem(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void pm_bar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PM_DONE_%=;\n"
+        "bra PM_WAIT_%=;\n"
+        "PM_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// all threads call; thread 0 arms the barrier with the byte count, threads 0 .. PM_ROWS-1 issue one row copy each
+__device__ __forceinline__ void pm_issue_tile(float* sm, unsigned bar, const float* plane, int x0, int y0, int W, int H) {
+    if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PM_TILE_BYTES) : "memory");
+    if (threadIdx.x < PM_ROWS) {
+        const float* src = plane + (long long)fold_coord(y0 - 1 + (int)threadIdx.x, H) * W + (x0 - 1 - PM_COL0);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(pm_smem(sm + threadIdx.x * PM_PITCH)), "l"(src), "r"(PM_ROW_BYTES), "r"(bar) : "memory");
+    }
+}
+// border tiles: the same layout through the threads (reflect-pad(1) of the columns, as load_tile)
+__device__ __forceinline__ void pm_stage_tile(float* __restrict__ sm, const float* __restrict__ plane, int x0, int y0, int W, int H) {
+    const int tx = threadIdx.x % TILE_W, tr = threadIdx.x / TILE_W;
+    const int ca = fold_coord(x0 - 1 + tx, W), cb = fold_coord(x0 - 1 + TILE_W + tx, W);
+#pragma unroll
+    for (int ty = tr; ty < PM_ROWS; ty += TILE_THREADS / TILE_W) {
+        const float* row = plane + (long long)fold_coord(y0 - 1 + ty, H) * W;
+        sm[ty * PM_PITCH + PM_COL0 + tx] = row[ca];
+        if (tx < 2) sm[ty * PM_PITCH + PM_COL0 + TILE_W + tx] = row[cb];
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_bulk_kernel(PmArgs a, float* __restrict__ out, int* __restrict__ argmin) {
+    __shared__ __align__(128) float ys[2][PM_ROWS * PM_PITCH];
+    __shared__ __align__(128) float xs[2][PM_ROWS * PM_PITCH];
+    __shared__ __align__(8) unsigned long long bars[4];          // 0, 1: ys[0], ys[1];  2, 3: xs[0], xs[1]
+    const long long HW = (long long)a.W * a.H;
+    const int n = blockIdx.z, x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * FWD_TH;
+    const int tx = threadIdx.x % TILE_W, tr = threadIdx.x / TILE_W;
+    const int gx = x0 + tx, gy0 = y0 + tr * FWD_RPT;
+    const float* y = a.target + n * a.target_ns;
+    const int S = a.S;
+    // block-uniform: can the copy engine stage this tile (16-byte aligned rows, no reflected columns)?
+    bool bulk = (a.W & 3) == 0 && x0 >= 4 && x0 + TILE_W + 4 <= a.W && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const float* pb[MAX_S];                                      // (registers: no run-time indexing of the parameter block)
+#pragma unroll
+    for (int s = 0; s < MAX_S; ++s) {
+        pb[s] = s < S ? a.pred[s] + n * a.pred_ns[s] : y;
+        bulk = bulk && (reinterpret_cast<uintptr_t>(pb[s]) & 15) == 0;
+    }
+    auto pred_of = [&](int s) {
+        const float* q = pb[0];
+#pragma unroll
+        for (int j = 1; j < MAX_S; ++j) q = (s == j) ? pb[j] : q;
+        return q;
+    };
+    const unsigned bar0 = pm_smem(&bars[0]);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * j) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        pm_issue_tile(ys[0], bar0, y, x0, y0, a.W, a.H);
+        pm_issue_tile(xs[0], bar0 + 16u, pb[0], x0, y0, a.W, a.H);
+    }
+    float ss[MAX_S][FWD_RPT], l1[MAX_S][FWD_RPT];
+#pragma unroll
+    for (int s = 0; s < MAX_S; ++s)
+#pragma unroll
+        for (int r = 0; r < FWD_RPT; ++r) { ss[s][r] = 0.f; l1[s][r] = 0.f; }
+    const int passes = C * S;
+#pragma unroll 1
+    for (int k = 0, c = 0, s = 0; k < passes; ++k) {
+        const float* ysm = ys[c & 1];
+        const float* xsm = xs[k & 1];
+        if (bulk) {
+            // prefetch the next pass: its buffers were last read in pass k - 1, which every thread has left (barrier below)
+            if (k + 1 < passes) {
+                const int s1 = (s + 1 == S) ? 0 : s + 1, c1 = (s + 1 == S) ? c + 1 : c;
+                if (s1 == 0) pm_issue_tile(ys[c1 & 1], bar0 + 8u * (c1 & 1), y + c1 * HW, x0, y0, a.W, a.H);
+                pm_issue_tile(xs[(k + 1) & 1], bar0 + 16u + 8u * ((k + 1) & 1), pred_of(s1) + c1 * HW, x0, y0, a.W, a.H);
+            }
+            if (s == 0) pm_bar_wait(bar0 + 8u * (c & 1), (c >> 1) & 1);
+            pm_bar_wait(bar0 + 16u + 8u * (k & 1), (k >> 1) & 1);
+        } else {
+            if (s == 0) pm_stage_tile(ys[c & 1], y + c * HW, x0, y0, a.W, a.H);
+            pm_stage_tile(xs[k & 1], pred_of(s) + c * HW, x0, y0, a.W, a.H);
+            __syncthreads();
+        }
+        {
+            const int cbase = (tr * FWD_RPT + 1) * PM_PITCH + PM_COL0 + 1 + tx;
+            const float xr = xsm[cbase], yr = ysm[cbase];
+            float ha[3], hb[3], haa[3], hbb[3], hab[3], yc[3], xc[3];
+            float accs[FWD_RPT], accl[FWD_RPT];
+#pragma unroll
+            for (int j = 0; j < FWD_RPT + 2; ++j) {
+                const int o = (tr * FWD_RPT + j) * PM_PITCH + PM_COL0 + tx;
+                const float al = xsm[o] - xr, ac = xsm[o + 1] - xr, ar = xsm[o + 2] - xr;
+                const float bl = ysm[o] - yr, bc = ysm[o + 1] - yr, br = ysm[o + 2] - yr;
+                const int m3 = j % 3;
+                ha[m3] = al + ac + ar; hb[m3] = bl + bc + br;
+                haa[m3] = fmaf(ar, ar, fmaf(ac, ac, al * al)); hbb[m3] = fmaf(br, br, fmaf(bc, bc, bl * bl));
+                hab[m3] = fmaf(ar, br, fmaf(ac, bc, al * bl));
+                xc[m3] = xsm[o + 1]; yc[m3] = ysm[o + 1];
+                if (j >= 2) {
+                    const int m = (j - 1) % 3;
+                    accs[j - 2] = ssim_from_sums(xr, yr, ha[0] + ha[1] + ha[2], hb[0] + hb[1] + hb[2], haa[0] + haa[1] + haa[2],
+                                                 hbb[0] + hbb[1] + hbb[2], hab[0] + hab[1] + hab[2]);
+                    accl[j - 2] = fabsf(yc[m] - xc[m]);
+                }
+            }
+#pragma unroll
+            for (int sq = 0; sq < MAX_S; ++sq)      // (static register indexing of the per-source accumulators)
+                if (sq == s) {
+#pragma unroll
+                    for (int r = 0; r < FWD_RPT; ++r) { ss[sq][r] += accs[r]; l1[sq][r] += accl[r]; }
+                }
+        }
+        __syncthreads();                            // every thread is done with the buffers of pass k
+        if (++s == S) { s = 0; ++c; }
+    }
+    if (gx >= a.W) return;
+#pragma unroll
+    for (int r = 0; r < FWD_RPT; ++r) {
+        const int gy = gy0 + r;
+        if (gy >= a.H) break;
+        const long long i = (long long)n * HW + (long long)gy * a.W + gx;
+        float best = 0.f; int bi = -1;
+        if (a.mask) best = a.mask[i];
+#pragma unroll
+        for (int sq = 0; sq < MAX_S; ++sq) {
+            if (sq >= S) break;
+            const float pe = a.alpha * (ss[sq][r] * (1.0f / C)) + (1.0f - a.alpha) * (l1[sq][r] * (1.0f / C));
+            if ((sq == 0 && !a.mask) || pe < best) { best = pe; bi = sq; }
+        }
+        out[i] = best;
+        if (argmin) argmin[i] = bi;
+    }
+}
+
+template <int C>
+static void launch_photomin_fwd(const PmArgs& a, float* out, int* argmin, dim3 g, cudaStream_t st) {
+    if (MD2_PM_BULK) photomin_fwd_bulk_kernel<C><<<g, TILE_THREADS, 0, st>>>(a, out, argmin);
+    else photomin_fwd_kernel<C><<<g, TILE_THREADS, 0, st>>>(a, out, argmin);
+}
+
 // Backward, two phases per tile and channel like ssim_bwd_kernel; a window's coefficients are those of ITS selected
 // source (argmin of the forward), so the tiles of all S sources are staged side by side.
 template <int C>
@@ -609,8 +772,8 @@ int launch_automask(md2_ctx* ctx, int S, const float* const* frames, const int64
     a.target = target; a.target_ns = target_ns; a.mask = nullptr; a.alpha = PHOTO_ALPHA;
     MD2_REQUIRE(N <= 65535 && cdiv(H, FWD_TH) <= 65535, "N and H / 32 must be <= 65535");
     const dim3 g(cdiv(W, TILE_W), cdiv(H, FWD_TH), N);
-    if (C == 1) photomin_fwd_kernel<1><<<g, TILE_THREADS, 0, st>>>(a, out, nullptr);
-    else photomin_fwd_kernel<3><<<g, TILE_THREADS, 0, st>>>(a, out, nullptr);
+    if (C == 1) launch_photomin_fwd<1>(a, out, nullptr, g, st);
+    else launch_photomin_fwd<3>(a, out, nullptr, g, st);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -882,8 +1045,8 @@ int md2_photometric_min_fwd(md2_ctx* ctx, int32_t S, const float* const* pred, c
     MD2_REQUIRE(out != nullptr, "null output");
     MD2_REQUIRE(N <= 65535 && cdiv(H, FWD_TH) <= 65535, "N and H / 32 must be <= 65535");
     const dim3 g(cdiv(W, TILE_W), cdiv(H, FWD_TH), N);
-    if (C == 1) photomin_fwd_kernel<1><<<g, TILE_THREADS, 0, ST>>>(a, out, argmin);
-    else photomin_fwd_kernel<3><<<g, TILE_THREADS, 0, ST>>>(a, out, argmin);
+    if (C == 1) launch_photomin_fwd<1>(a, out, argmin, g, ST);
+    else launch_photomin_fwd<3>(a, out, argmin, g, ST);
     MD2_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -221,6 +221,26 @@ def test_automasking_and_apply_mask():
     assert torch.all(a.grad == 1) and torch.all(b.grad == 0)   # mask wins ties
 
 
+@pytest.mark.parametrize("C,H,W,off", [(3, 70, 160, 0), (1, 33, 100, 0), (3, 40, 99, 0), (3, 64, 128, 1), (1, 128, 416, 0), (3, 5, 72, 0)])
+def test_automask_prepass_copy_engine_and_border_tiles(C, H, W, off):
+    """photometric_min forward (the automask pre-pass): interior tiles are staged by cp.async.bulk row copies on mbarriers,
+    tiles on the left / right border, widths that are not a multiple of 4 and frames that are not 16-byte aligned (off = 1:
+    the batch starts one float into its allocation) through the threads -- every route against the oracle."""
+    torch.manual_seed(5)
+    N = 3
+    buf = torch.rand(N * 3 * C * H * W + off)
+    x = buf[off:].view(N, 3, C, H, W)
+    xg = buf.to(dev())[off:].view(N, 3, C, H, W)
+    assert xg.data_ptr() % 16 == (4 * off) % 16
+    og = M.automasking_loss(M.SSIM(), xg, xg[:, 1], (0, 2))
+    oc = O.automasking_loss(O.SSIM(), x.double(), x[:, 1].double(), (0, 2))
+    close(og, oc, 1e-5)
+    # one source (a single (channel, source) pass per channel: the other buffer parity pattern)
+    og1 = M.automasking_loss(M.SSIM(), xg, xg[:, 1], (2,))
+    oc1 = O.automasking_loss(O.SSIM(), x.double(), x[:, 1].double(), (2,))
+    close(og1, oc1, 1e-5)
+
+
 @pytest.mark.parametrize("normalize", [False, True])
 def test_smooth_loss_grads(normalize):
     torch.manual_seed(3)
