@@ -523,6 +523,9 @@ __global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_kernel(PmArgs a, fl
 #ifndef MD2_PM_BULK
 #define MD2_PM_BULK 1
 #endif
+#ifndef MD2_PM_MINB
+#define MD2_PM_MINB 4      // resident blocks per SM the register allocation aims at (4: <= 64 registers)
+#endif
 constexpr int PM_PITCH = 40, PM_COL0 = 3;              // smem pitch (floats); tile-local column of image column x0 - 1
 constexpr int PM_ROWS = FWD_TH + 2;
 constexpr unsigned PM_ROW_BYTES = PM_PITCH * 4, PM_TILE_BYTES = PM_ROWS * PM_ROW_BYTES;
@@ -539,13 +542,21 @@ __device__ __forceinline__ void pm_bar_wait(unsigned bar, unsigned parity) {
         "PM_DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// all threads call; thread 0 arms the barrier with the byte count, threads 0 .. PM_ROWS-1 issue one row copy each
-__device__ __forceinline__ void pm_issue_tile(float* sm, unsigned bar, const float* plane, int x0, int y0, int W, int H) {
+// All threads call.  Thread 0 arms the barrier with the byte count; lane 0 of every warp issues the copies of tile rows
+// warp, warp + 8, ... (a bulk copy takes warp-uniform operands: issued from the lanes of ONE warp the 34 rows of a tile
+// become a serial loop of that warp, and the whole block waits for it at the end of the pass -- measured: 36 % of the
+// block's time in the barrier).  roff[j]: element offset of tile row warp + 8 j inside a plane, formed once per block.
+constexpr int PM_RPW = (PM_ROWS + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32);     // rows per warp
+__device__ __forceinline__ void pm_issue_tile(float* sm, unsigned bar, const float* plane, const int (&roff)[PM_RPW]) {
+    const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PM_TILE_BYTES) : "memory");
-    if (threadIdx.x < PM_ROWS) {
-        const float* src = plane + (long long)fold_coord(y0 - 1 + (int)threadIdx.x, H) * W + (x0 - 1 - PM_COL0);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(pm_smem(sm + threadIdx.x * PM_PITCH)), "l"(src), "r"(PM_ROW_BYTES), "r"(bar) : "memory");
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned dst = pm_smem(sm) + (unsigned)warp * PM_ROW_BYTES;
+#pragma unroll
+        for (int j = 0; j < PM_RPW; ++j)
+            if (warp + 8 * j < PM_ROWS)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + (unsigned)(8 * j) * PM_ROW_BYTES), "l"(plane + roff[j]), "r"(PM_ROW_BYTES), "r"(bar) : "memory");
     }
 }
 // border tiles: the same layout through the threads (reflect-pad(1) of the columns, as load_tile)
@@ -561,7 +572,7 @@ __device__ __forceinline__ void pm_stage_tile(float* __restrict__ sm, const floa
 }
 
 template <int C>
-__global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_bulk_kernel(PmArgs a, float* __restrict__ out, int* __restrict__ argmin) {
+__global__ void __launch_bounds__(TILE_THREADS, MD2_PM_MINB) photomin_fwd_bulk_kernel(PmArgs a, float* __restrict__ out, int* __restrict__ argmin) {
     __shared__ __align__(128) float ys[2][PM_ROWS * PM_PITCH];
     __shared__ __align__(128) float xs[2][PM_ROWS * PM_PITCH];
     __shared__ __align__(8) unsigned long long bars[4];          // 0, 1: ys[0], ys[1];  2, 3: xs[0], xs[1]
@@ -586,6 +597,9 @@ __global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_bulk_kernel(PmArgs 
         return q;
     };
     const unsigned bar0 = pm_smem(&bars[0]);
+    int roff[PM_RPW];
+#pragma unroll
+    for (int j = 0; j < PM_RPW; ++j) roff[j] = fold_coord(y0 - 1 + (int)(threadIdx.x >> 5) + 8 * j, a.H) * a.W + (x0 - 1 - PM_COL0);
     if (bulk) {
         if (threadIdx.x == 0) {
 #pragma unroll
@@ -593,8 +607,8 @@ __global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_bulk_kernel(PmArgs 
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        pm_issue_tile(ys[0], bar0, y, x0, y0, a.W, a.H);
-        pm_issue_tile(xs[0], bar0 + 16u, pb[0], x0, y0, a.W, a.H);
+        pm_issue_tile(ys[0], bar0, y, roff);
+        pm_issue_tile(xs[0], bar0 + 16u, pb[0], roff);
     }
     float ss[MAX_S][FWD_RPT], l1[MAX_S][FWD_RPT];
 #pragma unroll
@@ -610,8 +624,8 @@ __global__ void __launch_bounds__(TILE_THREADS) photomin_fwd_bulk_kernel(PmArgs 
             // prefetch the next pass: its buffers were last read in pass k - 1, which every thread has left (barrier below)
             if (k + 1 < passes) {
                 const int s1 = (s + 1 == S) ? 0 : s + 1, c1 = (s + 1 == S) ? c + 1 : c;
-                if (s1 == 0) pm_issue_tile(ys[c1 & 1], bar0 + 8u * (c1 & 1), y + c1 * HW, x0, y0, a.W, a.H);
-                pm_issue_tile(xs[(k + 1) & 1], bar0 + 16u + 8u * ((k + 1) & 1), pred_of(s1) + c1 * HW, x0, y0, a.W, a.H);
+                if (s1 == 0) pm_issue_tile(ys[c1 & 1], bar0 + 8u * (c1 & 1), y + c1 * HW, roff);
+                pm_issue_tile(xs[(k + 1) & 1], bar0 + 16u + 8u * ((k + 1) & 1), pred_of(s1) + c1 * HW, roff);
             }
             if (s == 0) pm_bar_wait(bar0 + 8u * (c & 1), (c >> 1) & 1);
             pm_bar_wait(bar0 + 16u + 8u * (k & 1), (k >> 1) & 1);
