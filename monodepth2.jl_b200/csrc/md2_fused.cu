@@ -636,7 +636,10 @@ constexpr int FIN_THREADS = 128;
 #ifndef MD2_FIN_UNROLL
 #define MD2_FIN_UNROLL 16
 #endif
-constexpr int FIN_UNROLL = MD2_FIN_UNROLL;  // small blocks: the whole grid is resident at once (one latency chain, no waves)
+constexpr int FIN_UNROLL = MD2_FIN_UNROLL;
+#ifndef MD2_FIN_TIMING   // timing experiments only (wrong results): 1 = no pose finalisation, 2 = no pose blocks, 3 = no adjoint blocks, 4 = no loss block
+#define MD2_FIN_TIMING 0
+#endif  // small blocks: the whole grid is resident at once (one latency chain, no waves)
 
 __global__ void __launch_bounds__(FIN_THREADS, MD2_FIN_MINB) finish_kernel(const __grid_constant__ FusedParams p, int NP, int ipg, int bwd, int low_rows) {
     extern __shared__ __align__(16) float vrow[];   // [W rounded up to 4] (adjoint blocks)
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MD2_FIN_MINB) finish_kernel(const
     const int LN = p.L * p.N;
     int b = blockIdx.x;
     if (b == 0) {
-        if (p.mode == 1) return;
+        if (p.mode == 1 || MD2_FIN_TIMING == 4) return;
         // FIN_THREADS / 32 ... lanes per (scale, image) group: strided partial sums with the loads issued in unrolled batches
         // (a rolled loop would pay one L2 round trip per iteration), then a fixed-order butterfly over the lanes of a group
         constexpr int GL = 4;                                 // lanes per group
@@ -706,6 +709,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MD2_FIN_MINB) finish_kernel(const
     b -= 1;
     if (!bwd) return;
     if (b < p.S * p.N) {
+        if (MD2_FIN_TIMING == 2) return;
         // pose gradient of (source s, image nn): 12 sums over all scales and segments.  Three lanes per row (one float4
         // each; NP and NSTAT are multiples of 4), FIN_PR row groups, loads issued in unrolled batches; then 12 threads add
         // the row-group partials in order, in double
@@ -732,10 +736,11 @@ __global__ void __launch_bounds__(FIN_THREADS, MD2_FIN_MINB) finish_kernel(const
             pacc[0][threadIdx.x] = a;
         }
         __syncthreads();
-        if (threadIdx.x == 0) finalize_pose(p.pose, s, nn, &pacc[0][0], &pacc[0][0] + 9);
+        if (threadIdx.x == 0 && MD2_FIN_TIMING != 1) finalize_pose(p.pose, s, nn, &pacc[0][0], &pacc[0][0] + 9);
         return;
     }
     b -= p.S * p.N;
+    if (MD2_FIN_TIMING == 3) return;
     // (image, low-res scale, low-res row) of this block: block-uniform scalar code
     const int n = b / low_rows;
     int yi = b - n * low_rows, l = -1;
