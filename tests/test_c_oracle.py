@@ -240,3 +240,52 @@ def test_forced_decisions_three_way(N, C, H, W, am, seed):
     ref_c = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, auto_loss=auto, choices=out["choices"])
     _compare(ref_c, ref_t)
     check_vsl(out, ref_c, tag=f"emul vs C oracle, forced {N},{C},{H},{W},{am}")
+
+
+# ------------------------------- the committed golden fixtures (tests/golden/, made by the first oracle) -------------------------------
+
+def test_golden_vsl_small():
+    """the C oracle reproduces the float64 loss / gradients the torch oracle committed for the seeded 4-scale automask case"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vsl_small.npz"))
+    x = torch.from_numpy(g["x"])
+    disps = [torch.from_numpy(g[f"disp{i}"]) for i in range(4)]
+    rv = [torch.from_numpy(g[f"rvec{s}"]) for s in range(2)]
+    tv = [torch.from_numpy(g[f"tvec{s}"]) for s in range(2)]
+    # (the fixture keeps the automask map in float32; the committed loss was formed with the float64 map)
+    auto = O.automasking_loss(O.SSIM(), x.double(), x.double()[:, 1], (0, 2))
+    assert torch.allclose(auto.float(), torch.from_numpy(g["auto"]), atol=1e-7)
+    out = CO.view_synthesis_loss(x, disps, rv, tv, torch.from_numpy(g["K"]), torch.from_numpy(g["invK"]), auto_loss=auto)
+    assert abs(out["loss"] - float(g["loss"])) < 1e-12
+    for i in range(4):
+        assert rel_max(out["gdisp"][i], torch.from_numpy(g[f"gdisp{i}"])) < 1e-9
+    for s in range(2):
+        assert rel_max(out["grvec"][s], torch.from_numpy(g[f"grvec{s}"])) < 1e-9
+        assert rel_max(out["gtvec"][s], torch.from_numpy(g[f"gtvec{s}"])) < 1e-9
+
+
+def test_golden_simple_depth_c1():
+    """config 1 on the reference's own res/image.png triplet (src/dtk.jl:16-47): the slow_depth start point and a second point"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simple_depth_c1.npz"))
+    x = torch.from_numpy(g["frames"]).permute(0, 3, 1, 2).to(F64).div(255.0).unsqueeze(0).contiguous()
+    W, H = 416, 128
+    K, invK = O.make_K(W, H, f=float(g["focal"]), dtype=F64)
+    disp = torch.full((1, 1, H, W), 0.5, dtype=F64)
+    rv = [torch.tensor([[0.0, 0.0, 0.01]], dtype=F64) for _ in range(2)]
+    tv = [torch.zeros(1, 3, dtype=F64) for _ in range(2)]
+    out = CO.simple_depth_loss(x, disp, rv, tv, K, invK)
+    assert abs(out["loss"] - float(g["loss"])) < 1e-12
+    for s in range(2):
+        assert rel_max(out["grvec"][s], torch.from_numpy(g["grvec"][s])) < 1e-9
+        assert rel_max(out["gtvec"][s], torch.from_numpy(g["gtvec"][s])) < 1e-9
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=F64), torch.arange(W, dtype=F64), indexing="ij")
+    disp2 = (0.5 + 0.2 * torch.sin(xx / 37.0) * torch.cos(yy / 23.0)).reshape(1, 1, H, W)
+    rv2 = [torch.from_numpy(g["rvec2"][s]) for s in range(2)]
+    tv2 = [torch.from_numpy(g["tvec2"][s]) for s in range(2)]
+    out = CO.simple_depth_loss(x, disp2, rv2, tv2, K, invK)
+    assert abs(out["loss"] - float(g["loss2"])) < 1e-12
+    assert rel_max(out["gdisp"][0], torch.from_numpy(g["gdisp2"]).double()) < 1e-6      # (committed as float32)
+    for s in range(2):
+        assert rel_max(out["grvec"][s], torch.from_numpy(g["grvec2"][s])) < 1e-9
+        assert rel_max(out["gtvec"][s], torch.from_numpy(g["gtvec2"][s])) < 1e-9
