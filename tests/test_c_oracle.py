@@ -289,3 +289,26 @@ def test_golden_simple_depth_c1():
     for s in range(2):
         assert rel_max(out["grvec"][s], torch.from_numpy(g["grvec2"][s])) < 1e-9
         assert rel_max(out["gtvec"][s], torch.from_numpy(g["gtvec2"][s])) < 1e-9
+
+
+@pytest.mark.parametrize("trial", range(8))
+def test_fuzz_marching_source_against_the_c_oracle(trial):
+    """random odd shapes / scale counts / chunk heights: the float32 marching-kernel source (tests/emul) against the C oracle with
+    its decisions forced -- EVERY gradient element within BASELINE.json's bars.  (The two share nothing: a bug common to the
+    kernel's formulation and the torch oracle's primitives would show here.)"""
+    import random
+    from emul_util import emul_vsl
+    from util import check_vsl
+    rnd = random.Random(1000 + trial)
+    N, C = rnd.choice([1, 2, 3]), rnd.choice([1, 3])
+    H, W = rnd.randint(2, 70), rnd.randint(2, 120)
+    L, am, R = rnd.choice([1, 2, 3, 4]), rnd.random() < 0.5, rnd.choice([8, 12, 16, 33])
+    scales = (0.125, 0.25, 0.5, 1.0)[4 - L:]
+    x, disps, rv, tv = O.synthetic_batch(N, C, H, W, scales=scales, seed=200 + trial, pose_sigma=rnd.choice([0.01, 0.03]))
+    K, invK = O.make_K(W, H)
+    auto = O.automasking_loss(O.SSIM(), x.double(), x.double()[:, 1], (0, 2)) if am else None
+    out = emul_vsl(x, disps, rv, tv, K, invK, mode=2, scales=scales, automask=auto.float().contiguous() if am else None,
+                   debug_choices=True, R=R)
+    out["loss"] = out["loss"].item()
+    ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, scales=scales, auto_loss=auto, choices=out["choices"])
+    check_vsl(out, ref, tag=f"fuzz {trial}: N={N} C={C} {W}x{H} L={L} automask={am} R={R}")
