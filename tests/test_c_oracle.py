@@ -312,3 +312,17 @@ def test_fuzz_marching_source_against_the_c_oracle(trial):
     out["loss"] = out["loss"].item()
     ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, scales=scales, auto_loss=auto, choices=out["choices"])
     check_vsl(out, ref, tag=f"fuzz {trial}: N={N} C={C} {W}x{H} L={L} automask={am} R={R}")
+
+
+def test_config2_full_size_marching_source_against_the_c_oracle():
+    """BASELINE.json configs[1] at full size (416x128, batch 8, C = 1, 4 native-size scales; the very batch bench.py times, chunk
+    height 33 as chosen on the B200): the marching-kernel source under the fibre emulator against the C oracle with its
+    decisions forced -- loss 1e-5, EVERY gradient element 1e-4."""
+    from emul_util import emul_vsl
+    from util import check_vsl
+    x, disps, rv, tv = O.synthetic_batch(8, 1, 128, 416, seed=42)
+    K, invK = O.make_K(416, 128)
+    out = emul_vsl(x, disps, rv, tv, K, invK, mode=2, debug_choices=True, R=33)
+    out["loss"] = out["loss"].item()
+    ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, choices=out["choices"])
+    check_vsl(out, ref, tag="config 2, full size")
