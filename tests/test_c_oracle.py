@@ -326,3 +326,17 @@ def test_config2_full_size_marching_source_against_the_c_oracle():
     out["loss"] = out["loss"].item()
     ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, choices=out["choices"])
     check_vsl(out, ref, tag="config 2, full size")
+
+
+def test_config3_geometry_marching_source_against_the_c_oracle():
+    """BASELINE.json configs[2] geometry (640x192, C = 3, automask + min-reprojection), 2 of its 12 images (the emulator runs
+    every warp as 32 fibres: the whole batch would take minutes; all 12 run on the GPU in tests/test_gpu_forced.py)"""
+    from emul_util import emul_vsl
+    from util import check_vsl
+    x, disps, rv, tv = O.synthetic_batch(2, 3, 192, 640, seed=42)
+    K, invK = O.make_K(640, 192)
+    auto = O.automasking_loss(O.SSIM(), x.double(), x.double()[:, 1], (0, 2))
+    out = emul_vsl(x, disps, rv, tv, K, invK, mode=2, automask=auto.float().contiguous(), debug_choices=True, R=32)
+    out["loss"] = out["loss"].item()
+    ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, auto_loss=auto, choices=out["choices"])
+    check_vsl(out, ref, tag="config 3 geometry")
