@@ -356,9 +356,11 @@ CO_API int co_view_synthesis_loss(
     double* loss_out, double* gx,                                        /* gx [N][L][C][H][W] or NULL (source frames only) */
     double* const* gdisps, double* grvecs, double* gtvecs,               /* gradients (NULL: value only) */
     double* viz_warped, double* viz_loss,                                /* last scale: [S][N][C][H][W], [N][H][W], or NULL */
-    const int* choices)   /* NULL, or the discrete decisions of the implementation under test, [n_scales][N][H][W][1+S] as
+    const int* choices,   /* NULL, or the discrete decisions of the implementation under test, [n_scales][N][H][W][1+S] as
                            * include/md2.h (md2_vsl_desc.debug_choices) lays them out: the same piece of the piecewise-smooth
                            * loss is then evaluated (values as always; only the branch of every kink is taken from there) */
+    int* choices_out)     /* NULL, or receives THIS evaluation's own decisions in the same layout (the gather cell reported as
+                           * the kernels keep it: the 2x2 cell inside the image, i.e. x0 <= W-2, y0 <= H-2) */
 {
     if (H < 2 || W < 2 || S < 1 || n_scales < 1) return 1;
     const int HW = H * W;
@@ -424,6 +426,29 @@ CO_API int co_view_synthesis_loss(
                         }
                         sc.pe[s * HW + p] = alpha * (ss / C) + (1.0 - alpha) * (l1 / C);
                     }
+            int* co = choices_out ? choices_out + ((long)(i * N + n) * HW) * fs : NULL;
+            if (co) {
+                for (int p = 0; p < HW; ++p) {
+                    int w0 = 0;
+                    for (int s = 0; s < S; ++s) {
+                        const cell_t c = sc.cells[s * HW + p];
+                        const int x0c = c.x0 > W - 2 ? W - 2 : c.x0, y0c = c.y0 > H - 2 ? H - 2 : c.y0;
+                        co[p * fs + 1 + s] = x0c | (y0c << 14) | (c.mx << 29) | (c.my << 30);
+                        for (int ch = 0; ch < C; ++ch) {
+                            const double* xw = sc.warped + (s * C + ch) * HW;
+                            const double raw = ssim_raw(window(xw, tgt + (long)ch * HW, H, W, p / W, p % W));
+                            const double df = xw[p] - tgt[ch * HW + p];
+                            if (raw >= 0.0 && raw <= 1.0) w0 |= 1 << (2 + s * C + ch);
+                            w0 |= (df > 0.0 ? 1 : (df < 0.0 ? 2 : 0)) << (8 + 2 * (s * C + ch));
+                        }
+                    }
+                    const double dx = (p % W) + 1 < W ? D[n * HW + p] - D[n * HW + p + 1] : 0.0;
+                    const double dy = (p / W) + 1 < H ? D[n * HW + p] - D[n * HW + p + W] : 0.0;
+                    w0 |= (dx > 0.0 ? 1 : (dx < 0.0 ? 2 : 0)) << 20;
+                    w0 |= (dy > 0.0 ? 1 : (dy < 0.0 ? 2 : 0)) << 22;
+                    co[p * fs] = w0;
+                }
+            }
             for (int p = 0; p < HW; ++p) {
                 double v = sc.pe[p];
                 int sel = 0;
@@ -432,6 +457,7 @@ CO_API int co_view_synthesis_loss(
                 if (auto_loss && auto_loss[n * HW + p] <= v) { v = auto_loss[n * HW + p]; sel = -1; }   /* the mask is first in the cat */
                 if (fc) { sel = (fc[p * fs] & 3) - 1; v = sel < 0 ? auto_loss[n * HW + p] : sc.pe[sel * HW + p]; }
                 sc.sel[p] = sel; sc.wl[p] = v;
+                if (co) co[p * fs] |= sel + 1;
                 photo += v;
             }
             if (i == n_scales - 1) {   /* visualisation outputs (src/training.jl:71-74) */

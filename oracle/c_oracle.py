@@ -108,11 +108,13 @@ def grid_sample_border(inp, grid):
 
 def view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK, *, target_id=1, source_ids=(0, 2),
                         scales=(0.125, 0.25, 0.5, 1.0), min_depth=0.1, max_depth=100.0, disparity_smoothness=1e-3,
-                        auto_loss=None, normalize_disp=True, alpha=0.85, grad=True, viz=False, choices=None):
+                        auto_loss=None, normalize_disp=True, alpha=0.85, grad=True, viz=False, choices=None,
+                        export_choices=False):
     """Value and hand-derived gradients of the train_loss tail (src/training.jl:42-78).  Returns a dict with loss, gdisp,
     grvec, gtvec, gx (source frames only: the target frame is data, as in the fused CUDA call) [, viz_warped, viz_loss].
     `choices` (int32 (L,N,H,W,1+S), md2_vsl_desc.debug_choices): evaluate with the discrete decisions of the implementation
-    under test forced, like torch_oracle.view_synthesis_loss_forced."""
+    under test forced, like torch_oracle.view_synthesis_loss_forced.  export_choices: also return this evaluation's own
+    decisions in that layout (out["choices"])."""
     x = _f64(x)
     N, L, Cc, H, W = x.shape
     S, n = len(source_ids), len(disparities)
@@ -131,6 +133,8 @@ def view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK, *, target_id=1, s
         choices = choices.detach().cpu().to(torch.int32).contiguous()
         assert tuple(choices.shape) == (n, N, H, W, 1 + S), choices.shape
         chp = C.cast(choices.data_ptr(), C.POINTER(C.c_int))
+    cho = torch.zeros(n, N, H, W, 1 + S, dtype=torch.int32) if export_choices else None
+    chop = C.cast(cho.data_ptr(), C.POINTER(C.c_int)) if export_choices else None
     arr = lambda ts: (_D * n)(*[_p(t) for t in ts])
     ints = lambda v: (C.c_int * len(v))(*v)
     sc = (C.c_double * n)(*[float(s) for s in scales[:n]])
@@ -139,7 +143,7 @@ def view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK, *, target_id=1, s
         _p(rv), _p(tv), _p(Kd), _p(iKd), int(target_id), S, ints(list(source_ids)), sc,
         C.c_double(min_depth), C.c_double(max_depth), C.c_double(disparity_smoothness), _p(al),
         int(bool(normalize_disp)), C.c_double(alpha), C.byref(loss), _p(gx) if grad else None,
-        arr(gd) if grad else None, _p(grv) if grad else None, _p(gtv) if grad else None, _p(vw), _p(vl), chp)
+        arr(gd) if grad else None, _p(grv) if grad else None, _p(gtv) if grad else None, _p(vw), _p(vl), chp, chop)
     if rc != 0:
         raise ValueError(f"co_view_synthesis_loss: status {rc}")
     out = {"loss": loss.value}
@@ -147,6 +151,8 @@ def view_synthesis_loss(x, disparities, rvecs, tvecs, K, invK, *, target_id=1, s
         out.update(gdisp=gd, grvec=list(grv), gtvec=list(gtv), gx=gx)
     if viz:
         out.update(viz_warped=list(vw), viz_loss=vl.unsqueeze(1))
+    if export_choices:
+        out["choices"] = cho
     return out
 
 

@@ -326,6 +326,13 @@ def test_config2_full_size_marching_source_against_the_c_oracle():
     out["loss"] = out["loss"].item()
     ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, choices=out["choices"])
     check_vsl(out, ref, tag="config 2, full size")
+    # ... and the decisions themselves: the float64 oracle, left to decide on its own, takes the same branch at all but a
+    # handful of the 1.7 M pixels (forcing cannot hide a wrong cell / arg-min / mask: it would show here)
+    own = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, grad=False, export_choices=True)
+    assert abs(own["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    from util import DECISION_FLIP_MAX, decision_mismatch
+    for kind, f in decision_mismatch(out["choices"], own["choices"], 1).items():
+        assert f <= DECISION_FLIP_MAX, (kind, f)
 
 
 def test_config3_geometry_marching_source_against_the_c_oracle():
@@ -340,3 +347,7 @@ def test_config3_geometry_marching_source_against_the_c_oracle():
     out["loss"] = out["loss"].item()
     ref = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, auto_loss=auto, choices=out["choices"])
     check_vsl(out, ref, tag="config 3 geometry")
+    own = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, auto_loss=auto, grad=False, export_choices=True)
+    from util import DECISION_FLIP_MAX, decision_mismatch
+    for kind, f in decision_mismatch(out["choices"], own["choices"], 3).items():
+        assert f <= DECISION_FLIP_MAX, (kind, f)

@@ -8,7 +8,7 @@ import torch
 from oracle import c_oracle as CO
 from oracle import torch_oracle as O
 from test_gpu_forced import check_forced, run_cuda
-from util import oracle_vsl_forced, rel_max
+from util import DECISION_FLIP_MAX, decision_mismatch, oracle_vsl_forced, rel_max
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,13 @@ def test_cuda_vs_c_oracle_forced(N, C, H, W, am):
         for a, b in zip(ref_c[k], ref_t[k]):
             assert rel_max(a, b) <= 1e-9, (k, rel_max(a, b))
     assert rel_max(ref_c["gx"][:, [0, 2]], ref_t["gx"][:, [0, 2]]) <= 1e-9
+    # the decisions themselves: the float64 oracle, left to decide on its own, takes the same branch at all but a handful of
+    # pixels (forcing cannot hide a wrong gather cell / arg-min / mask: it would show here)
+    own = CO.view_synthesis_loss(x, disps, rv, tv, K, invK, auto_loss=auto, grad=False, export_choices=True)
+    mism = decision_mismatch(out["choices"], own["choices"], C)
+    print("decision mismatch fractions", (N, C, H, W, am), mism)
+    for kind, f in mism.items():
+        assert f <= DECISION_FLIP_MAX, (kind, f)
 
 
 def test_slow_depth_objective_vs_c_oracle():

@@ -206,3 +206,20 @@ def check_vsl_statistical(out, ref, source_ids=(0, 2), tag="", frac=0.995, pose_
     if out.get("gx") is not None:
         ids = list(source_ids)
         stat(out["gx"][:, ids], ref["gx"][:, ids], "gx")
+
+
+def decision_mismatch(ca, cb, C, S=2):
+    """fractions of the pixels at which two sets of exported decisions (md2_vsl_desc.debug_choices layout, (L,N,H,W,1+S))
+    differ, per kind of decision"""
+    a, b = O.decode_choices(ca, C, S), O.decode_choices(cb, C, S)
+    frac = lambda m: m.double().mean().item()
+    return {"sel": frac(a["sel"] != b["sel"]),
+            "cell": frac((a["x0"] != b["x0"]) | (a["y0"] != b["y0"])),
+            "clip mask": frac((a["mx"] != b["mx"]) | (a["my"] != b["my"])),
+            "clamp pass": frac(a["pass"] != b["pass"]),
+            "l1 sign": frac(a["l1"] != b["l1"]),
+            "smooth sign x": frac(a["smx"][..., :-1] != b["smx"][..., :-1]),
+            "smooth sign y": frac(a["smy"][..., :-1, :] != b["smy"][..., :-1, :])}
+
+
+DECISION_FLIP_MAX = 1e-4   # float32 against float64: a decision may differ only where its margin is within float32 rounding
